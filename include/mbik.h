@@ -1,0 +1,167 @@
+/*
+ * mbik.h -- C ABI of the B200-native batched ManyBoneIK solve loop (libmbik.so).
+ *
+ * This is the drop-in boundary for ONE path of the reference module: the per-frame iterative
+ * constrained IK solve, i.e. the body of
+ *     ManyBoneIK3D::_process_modification()            reference src/many_bone_ik_3d.cpp:645-694
+ *       -> IKBoneSegment3D::segment_solver()           reference src/ik_bone_segment_3d.cpp:210-240
+ * The reference has no FFI of its own (the path sits behind a C++ virtual of a Godot engine module,
+ * src/many_bone_ik_3d.h:90); these entry points are what a maintainer would bind from that override
+ * (see INTEGRATION.md for the stub).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Semantics: one call solves `n_poses` INDEPENDENT skeleton poses of the same rig.  For every pose
+ * the result equals what the reference computes in the first _process_modification() after
+ * _bone_list_changed() rebuilt the rig with the skeleton in `start_pose` (default: the rig's rest
+ * pose) and the pin targets in `targets`.
+ *
+ * All transforms use Godot's in-memory Transform3D layout with real_t = float:
+ *   12 floats = basis rows [xx xy xz  yx yy yz  zx zy zz] followed by origin [ox oy oz].
+ */
+#ifndef MBIK_H
+#define MBIK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBIK_VERSION 1
+
+/* status codes (reference error behaviour: never throws, ERR_FAIL_* -> default return;
+ * src/ik_bone_segment_3d.cpp:130-133) */
+#define MBIK_OK 0
+#define MBIK_ERR_INVALID_ARG (-1)
+#define MBIK_ERR_CUDA (-2)
+#define MBIK_ERR_UNSUPPORTED (-3) /* rig larger than the compiled kernel variants */
+#define MBIK_ERR_NO_DEVICE (-4)   /* no CUDA device: there is NO CPU fallback */
+#define MBIK_ERR_ALLOC (-5)
+
+/* per-pose status bits written to out_status */
+#define MBIK_POSE_NONFINITE_RESET 1u /* a solved bone's basis was non-finite and was reset to identity at
+                                        write-back (reference src/ik_bone_3d.cpp:174-176) */
+
+/* One row of ManyBoneIK3D::pins (IKEffectorTemplate3D fields, reference
+ * src/ik_effector_template_3d.h:40-45). */
+typedef struct mbik_pin_desc {
+	int32_t bone;                     /* skeleton bone index (stands for the bone name) */
+	float weight;                     /* default 0 in the reference: benches must set it */
+	float motion_propagation_factor;  /* clamped to [0,1] like IKEffector3D::set_motion_propagation_factor */
+	float direction_priorities[3];    /* default (0.2, 0, 0.2) */
+} mbik_pin_desc;
+
+/* One entry of ManyBoneIK3D::kusudama_open_cones[i] (Vector4: centre xyz, radius w;
+ * reference src/many_bone_ik_3d.h:58). */
+typedef struct mbik_cone_desc {
+	float center[3];
+	float radius;
+} mbik_cone_desc;
+
+/* One row of the constraint tables constraint_names / joint_twist / kusudama_open_cone_count
+ * (reference src/many_bone_ik_3d.h:53-59). */
+typedef struct mbik_constraint_desc {
+	int32_t bone;        /* skeleton bone index */
+	float twist_from;    /* joint_twist.x = min axial angle */
+	float twist_range;   /* joint_twist.y = range */
+	int32_t n_cones;     /* kusudama_open_cone_count */
+	int32_t cone_offset; /* first cone of this row in mbik_rig_desc::cones */
+} mbik_constraint_desc;
+
+/* Everything _bone_list_changed() (reference src/many_bone_ik_3d.cpp:1011-1068) reads. */
+typedef struct mbik_rig_desc {
+	int32_t n_bones;                          /* Skeleton3D::get_bone_count() */
+	const int32_t *parent;                    /* [n_bones], -1 = parentless; children are visited in ascending index */
+	const float *rest_local;                  /* [n_bones][12] Skeleton3D::get_bone_pose() at build time */
+	int32_t n_pins;
+	const mbik_pin_desc *pins;
+	int32_t n_constraints;
+	const mbik_constraint_desc *constraints;
+	const mbik_cone_desc *cones;
+	int32_t n_bone_damp;                      /* size of ManyBoneIK3D::bone_damp (indexed by skeleton bone id; may be 0) */
+	const float *bone_damp;
+	float default_damp;                       /* radians; reference default 0.0872665 (5 deg) */
+	int32_t iterations_per_frame;             /* reference default 15 */
+	int32_t stabilization_passes;             /* reference default 0 */
+	int32_t constraint_mode;                  /* reference default false */
+} mbik_rig_desc;
+
+/* Per-call overrides.  Negative values mean "use the rig's". */
+typedef struct mbik_solve_params {
+	int32_t iterations;   /* overrides iterations_per_frame (read every frame in the reference, :685) */
+	int32_t device;       /* CUDA device ordinal for this call; -1 = current device */
+	uint32_t flags;       /* MBIK_IO_* */
+	void *stream;         /* cudaStream_t for MBIK_IO_DEVICE calls (NULL = default stream) */
+} mbik_solve_params;
+
+#define MBIK_IO_HOST 0u   /* buffers are host memory (pinned or pageable); the call copies, solves and returns when done */
+#define MBIK_IO_DEVICE 1u /* buffers are device memory on params->device; the call enqueues on params->stream and returns */
+
+typedef struct mbik_rig mbik_rig; /* opaque: host schedule + per-device copies */
+
+/* Schedule facts, for tests and callers that size buffers. */
+typedef struct mbik_rig_info {
+	int32_t n_bones;          /* skeleton bones */
+	int32_t n_solved;         /* bones in ManyBoneIK3D::bone_list */
+	int32_t n_segments;       /* kept IKBoneSegment3D count */
+	int32_t n_steps;          /* bone-steps per iteration (= n_solved) */
+	int32_t n_effectors;      /* pinned bones that are solved */
+	int32_t n_pins;
+	int32_t max_headings;     /* largest heading count of any segment */
+	int32_t n_cones;
+	int32_t iterations;
+	int32_t kernel_capacity;  /* solved-bone capacity of the kernel variant that will run */
+	int64_t rig_blob_bytes;   /* constants staged to shared memory per CTA */
+	double flops_per_solve;   /* algorithmic flop floor, SURVEY.md section 8(d) convention */
+} mbik_rig_info;
+
+int mbik_device_count(void);
+const char *mbik_strerror(int code);
+const char *mbik_last_error(void); /* thread-local detail string of the last failure */
+
+int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig);
+int mbik_rig_destroy(mbik_rig *rig);
+int mbik_rig_get_info(const mbik_rig *rig, mbik_rig_info *out_info);
+/* bone_list order (children segments first, tip -> root), reference src/ik_bone_segment_3d.cpp:56-72 */
+int mbik_rig_get_bone_order(const mbik_rig *rig, int32_t *out_bones /* [n_solved] */);
+/* heading weights of the segment that owns step `step` (reference :281-343); returns count */
+int mbik_rig_get_step_weights(const mbik_rig *rig, int32_t step, double *out_weights, int32_t capacity);
+/* per solved bone (bone_list order): bone-direction local basis[9], twist-axes local basis[9] (setup constants) */
+int mbik_rig_get_bone_frames(const mbik_rig *rig, float *out_dir_basis /* [n_solved][9] */, float *out_twist_basis /* [n_solved][9] */);
+/* per cone, flattened in constraint-row order: control point[3], tangent centre 1[3], tangent centre 2[3] */
+int mbik_rig_get_cone_geometry(const mbik_rig *rig, float *out /* [n_cones][9] */);
+
+/*
+ * The hot path.  Replaces the iteration loop + skeleton read/write of
+ * ManyBoneIK3D::_process_modification (reference src/many_bone_ik_3d.cpp:685-693, :91-116).
+ *   targets     [n_poses][n_pins][12]  skeleton-space pin targets (IKEffector3D::target_relative_to_skeleton_origin)
+ *   start_pose  [n_poses][n_bones][12] local bone poses to seed from, or NULL = rig rest pose
+ *   out_pose    [n_poses][n_bones][10] per bone: position xyz, rotation quaternion xyzw, scale xyz -- the three
+ *               values IKBone3D::set_skeleton_bone_pose writes (reference src/ik_bone_3d.cpp:170-179);
+ *               bones outside bone_list pass through
+ *   out_local   [n_poses][n_bones][12] raw local transforms (optional, may be NULL)
+ *   out_status  [n_poses] MBIK_POSE_* bits (optional, may be NULL)
+ */
+int mbik_solve_batch(mbik_rig *rig, const mbik_solve_params *params, size_t n_poses,
+		const float *targets, const float *start_pose,
+		float *out_pose, float *out_local, uint32_t *out_status);
+
+/* Same, host buffers only, sharded contiguously over `n_devices` GPUs (pose k's result does not depend on
+ * the split; no collective).  devices == NULL means 0..n_devices-1. */
+int mbik_solve_batch_multi(mbik_rig *rig, const mbik_solve_params *params, size_t n_poses,
+		const float *targets, const float *start_pose,
+		float *out_pose, float *out_local, uint32_t *out_status,
+		const int32_t *devices, int32_t n_devices);
+
+/* Pinned host allocation helpers (so a C caller can get full H2D/D2H bandwidth without linking CUDA). */
+void *mbik_alloc_pinned(size_t bytes);
+void mbik_free_pinned(void *p);
+
+/* Device time in milliseconds of the most recent kernel launch of this rig on `device`
+ * (cudaEvent pair recorded on the launching stream around the solve kernel). */
+int mbik_last_kernel_ms(mbik_rig *rig, int32_t device, float *out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBIK_H */
