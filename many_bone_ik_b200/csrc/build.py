@@ -1,0 +1,54 @@
+"""Build many_bone_ik_b200/libmbik.so in-tree with nvcc for sm_100a (no torch, no JIT cache).
+
+    python -m many_bone_ik_b200.csrc.build [--force]
+
+-fmad=false / -ffp-contract=off are belt and braces: every arithmetic op of the solve already goes through
+individually rounded intrinsics (mbik_math.cuh), which is what makes the kernel bit-identical to the
+reference arithmetic.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+OUT = os.path.join(PKG, "libmbik.so")
+SOURCES = ["mbik_capi.cu", "mbik_flatten.cu", "mbik_kernel.cu"]
+HEADERS = ["mbik_blob.h", "mbik_flatten.h", "mbik_kernel.h", "mbik_math.cuh", os.path.join("..", "..", "include", "mbik.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-fvisibility=hidden", "-shared", "-cudart", "static",
+]
+
+
+def nvcc_path():
+    for p in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if p and (os.path.isabs(p) and os.path.exists(p) or not os.path.isabs(p)):
+            return p
+    return "nvcc"
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(HERE, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libmbik.so")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

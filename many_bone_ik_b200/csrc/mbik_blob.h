@@ -1,0 +1,94 @@
+// mbik_blob.h -- the flattened rig ("schedule") shared by the host flattener and the solve kernel.
+//
+// One contiguous, 16-byte aligned blob of rig constants.  The kernel stages it into shared memory
+// with one TMA bulk copy per CTA; every lane then reads the same words (broadcast).  Layout:
+//   BlobHeader | BlobStep[n_steps] | BlobBone[n_solved] | BlobEff[n_effs] | BlobFk[n_fk] |
+//   BlobCone[n_cones] | BlobPass[n_pass] | rest_local[n_bones*12]
+// Solved bones are renumbered in topological order ("t index": parents before children) so that the
+// per-iteration FK refresh is a linear pass.
+#pragma once
+#include <stdint.h>
+
+namespace mbik {
+
+enum : uint32_t {
+	STEP_TRANSLATE = 1u,    // bone belongs to a root segment (reference src/ik_bone_segment_3d.cpp:217-223)
+	STEP_NODE_PARENT = 2u,  // the bone's IKNode3D has a parent node (false only for non-last skeleton roots)
+	STEP_IK_PARENT = 4u,    // the bone has an IKBone3D parent -> constraint snaps apply (:155)
+	STEP_SWING = 8u,        // kusudama orientationally constrained
+	STEP_TWIST = 16u,       // kusudama axially constrained
+	STEP_SEG_ROOT = 32u,    // bone == segment root (previous_deviation reset, :178-180)
+	STEP_STABILIZE = 64u,   // segment runs the stabilisation loop (root segments only, many_bone_ik_3d.cpp:1021)
+};
+
+struct BlobHeader {
+	uint32_t magic;       // 'MBIK'
+	uint32_t total_bytes; // multiple of 16
+	int32_t n_bones, n_solved, n_steps, n_pins, n_effs, n_fk, n_cones, n_pass;
+	int32_t iterations, constraint_mode, stabilization_passes, reserved0;
+	uint32_t off_steps, off_bones, off_effs, off_fk, off_cones, off_pass, off_rest, reserved1;
+};
+
+struct BlobStep { // 48 bytes
+	int32_t bone;    // t index
+	int32_t parent;  // t index of the IK parent, -1 for a skeleton root
+	uint32_t flags;
+	int32_t eff_off, eff_cnt;   // the owning segment's effector list
+	int32_t fk_off, fk_cnt;     // transforms to refresh below `bone` before headings are built
+	int32_t cone_off, cone_cnt; // the bone's kusudama cones
+	int32_t n_headings;
+	double cos_half_damp;       // cos(damp / 2.0), damp per src/ik_bone_segment_3d.cpp:229-237
+};
+
+struct BlobBone { // per solved bone, t order; 160 bytes
+	int32_t skel_bone;
+	int32_t parent;          // t index or -1
+	uint32_t flags;          // STEP_NODE_PARENT only
+	float twist_cos;         // twist_half_range_half_cos = cos(range / 4)
+	float dir_basis[9];      // bone-direction node local basis (origin is zero)
+	float orient_basis[9];   // constraint-orientation node local basis (identity after a rebuild)
+	float twist_basis[9];    // constraint-twist node local basis (after _update_constraint)
+	float twist_center[9];   // Basis(twist_center_rot)
+};
+
+struct BlobEff { // one entry per (segment, effector); 64 bytes
+	int32_t bone;            // t index of the effector's bone
+	int32_t pin;             // row of the pins table = target slot
+	float prio[3];           // direction priorities (axis used iff > 0)
+	int32_t n_headings;      // 1 + 2 * (#priorities > 0)
+	double w_origin;         // heading weight of the origin heading
+	double w_axis[3];        // heading weight of each axis pair (0 when unused)
+	int32_t pad[2];
+};
+
+struct BlobFk { // G[child] = G[parent] * L[child]
+	int16_t child, parent;
+};
+
+struct BlobCone { // 160 bytes
+	float cp[3];            // control point (what get_control_point() returns)
+	float ncp[3];           // cp.normalized() (closest_to_cone re-normalises, src/ik_open_cone_3d.cpp:360)
+	float sin_half_r, cos_half_r; // sin/cos((float)radius * 0.5f) for get_quaternion_axis_angle(axis, radius)
+	double radius_cos;      // cos(radius) in double
+	// data about the path to the NEXT cone (unused on the last cone)
+	double tan_cos;         // cos(tangent circle radius)
+	float tc1[3], tc2[3];   // tangent circle centres
+	float sin_half_t, cos_half_t; // sin/cos((float)tangent_radius * 0.5f)
+	float c1xc2[3];         // cp x next.cp                      (not normalised, :287)
+	float c1xt1[3];         // (cp x tc1).normalized()           (:290)
+	float t1xc2[3];         // (tc1 x next.cp).normalized()      (:291)
+	float t2xc1[3];         // (tc2 x cp).normalized()           (:305)
+	float c2xt2[3];         // (next.cp x tc2).normalized()      (:306)
+	float pad[5];
+};
+
+struct BlobPass { // skeleton bones outside bone_list: copied through to the output
+	int32_t skel_bone;
+};
+
+static_assert(sizeof(BlobStep) == 48, "BlobStep layout");
+static_assert(sizeof(BlobBone) == 160, "BlobBone layout");
+static_assert(sizeof(BlobEff) == 64, "BlobEff layout");
+static_assert(sizeof(BlobCone) == 160, "BlobCone layout");
+
+} // namespace mbik

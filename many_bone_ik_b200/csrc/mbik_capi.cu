@@ -1,0 +1,504 @@
+// mbik_capi.cu -- the extern "C" boundary declared in include/mbik.h.
+// Host runtime around the solve kernel: rig handles, per-device rig copies and staging buffers,
+// host<->device copies on per-device streams, contiguous multi-GPU sharding (one worker thread per
+// device, no collective).  There is no CPU fallback: without a CUDA device the solve entry points fail.
+#include "../../include/mbik.h"
+#include "mbik_flatten.h"
+#include "mbik_kernel.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+	g_last_error = msg;
+	return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+	return fail(MBIK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+struct DeviceState {
+	int device = -1;
+	unsigned char *blob = nullptr;
+	cudaStream_t stream = nullptr; // used for MBIK_IO_HOST calls
+	cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+	bool timed = false;
+	// staging for host-I/O calls, grown on demand and reused (no allocation in steady state)
+	float *d_targets = nullptr, *d_start = nullptr, *d_out = nullptr, *d_local = nullptr;
+	uint32_t *d_status = nullptr;
+	size_t cap_targets = 0, cap_start = 0, cap_out = 0, cap_local = 0, cap_status = 0;
+};
+
+} // namespace
+
+struct mbik_rig {
+	mbik::FlatRig flat;
+	int n_solved = 0;
+	std::mutex mu;
+	std::map<int, DeviceState> devices;
+};
+
+namespace {
+
+void free_device_state(DeviceState &ds) {
+	if (ds.device < 0) {
+		return;
+	}
+	cudaSetDevice(ds.device);
+	cudaFree(ds.blob);
+	cudaFree(ds.d_targets);
+	cudaFree(ds.d_start);
+	cudaFree(ds.d_out);
+	cudaFree(ds.d_local);
+	cudaFree(ds.d_status);
+	if (ds.ev_start) {
+		cudaEventDestroy(ds.ev_start);
+	}
+	if (ds.ev_stop) {
+		cudaEventDestroy(ds.ev_stop);
+	}
+	if (ds.stream) {
+		cudaStreamDestroy(ds.stream);
+	}
+}
+
+// Get (creating on first use) the per-device copy of the rig.  Caller has set the device.
+int get_device_state(mbik_rig *rig, int device, DeviceState **out) {
+	std::lock_guard<std::mutex> lock(rig->mu);
+	auto it = rig->devices.find(device);
+	if (it != rig->devices.end()) {
+		*out = &it->second;
+		return MBIK_OK;
+	}
+	DeviceState ds;
+	ds.device = device;
+	cudaError_t e = cudaMalloc((void **)&ds.blob, rig->flat.blob.size());
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "cudaMalloc(rig blob)");
+	}
+	e = cudaMemcpy(ds.blob, rig->flat.blob.data(), rig->flat.blob.size(), cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) {
+		cudaFree(ds.blob);
+		return cuda_fail(e, "cudaMemcpy(rig blob)");
+	}
+	e = cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) {
+		e = cudaEventCreate(&ds.ev_start);
+	}
+	if (e == cudaSuccess) {
+		e = cudaEventCreate(&ds.ev_stop);
+	}
+	if (e != cudaSuccess) {
+		free_device_state(ds);
+		return cuda_fail(e, "stream/event creation");
+	}
+	auto ins = rig->devices.emplace(device, ds);
+	*out = &ins.first->second;
+	return MBIK_OK;
+}
+
+template <class T>
+int ensure_capacity(T **p, size_t *cap, size_t bytes) {
+	if (bytes <= *cap) {
+		return MBIK_OK;
+	}
+	if (*p) {
+		cudaFree(*p);
+		*p = nullptr;
+		*cap = 0;
+	}
+	cudaError_t e = cudaMalloc((void **)p, bytes);
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "cudaMalloc(staging)");
+	}
+	*cap = bytes;
+	return MBIK_OK;
+}
+
+int resolve_device(const mbik_solve_params *params, int *device) {
+	int dev = params ? params->device : -1;
+	if (dev < 0) {
+		cudaError_t e = cudaGetDevice(&dev);
+		if (e != cudaSuccess) {
+			return fail(MBIK_ERR_NO_DEVICE, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+		}
+	}
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count <= 0) {
+		return fail(MBIK_ERR_NO_DEVICE, "no CUDA device: mbik has no CPU fallback");
+	}
+	if (dev >= count) {
+		return fail(MBIK_ERR_INVALID_ARG, "device ordinal out of range");
+	}
+	*device = dev;
+	return MBIK_OK;
+}
+
+// one shard on one device; host or device buffers
+int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user_stream, int iterations, size_t n_poses,
+		const float *targets, const float *start_pose, float *out_pose, float *out_local, uint32_t *out_status) {
+	if (n_poses == 0) {
+		return MBIK_OK;
+	}
+	cudaError_t e = cudaSetDevice(device);
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "cudaSetDevice");
+	}
+	DeviceState *ds = nullptr;
+	int rc = get_device_state(rig, device, &ds);
+	if (rc != MBIK_OK) {
+		return rc;
+	}
+	const mbik::FlatRig &F = rig->flat;
+	const size_t nb = (size_t)F.n_bones, np = F.pins.size();
+	mbik::SolveArgs a;
+	a.blob = ds->blob;
+	a.blob_bytes = (uint32_t)F.blob.size();
+	a.iterations = iterations;
+	a.n_poses = n_poses;
+
+	if (flags & MBIK_IO_DEVICE) {
+		a.targets = targets;
+		a.start_pose = start_pose;
+		a.out_pose = out_pose;
+		a.out_local = out_local;
+		a.out_status = out_status;
+		cudaEventRecord(ds->ev_start, user_stream);
+		e = mbik::launch_solve(a, rig->n_solved, user_stream);
+		cudaEventRecord(ds->ev_stop, user_stream);
+		ds->timed = true;
+		if (e != cudaSuccess) {
+			return cuda_fail(e, "kernel launch");
+		}
+		return MBIK_OK;
+	}
+
+	// host buffers: stage through device memory on this device's stream
+	const size_t bt = n_poses * np * 12 * sizeof(float), bs = n_poses * nb * 12 * sizeof(float);
+	const size_t bo = n_poses * nb * 10 * sizeof(float), bl = n_poses * nb * 12 * sizeof(float), bst = n_poses * sizeof(uint32_t);
+	if ((rc = ensure_capacity(&ds->d_targets, &ds->cap_targets, bt ? bt : 16)) != MBIK_OK ||
+			(rc = ensure_capacity(&ds->d_out, &ds->cap_out, bo)) != MBIK_OK ||
+			(start_pose && (rc = ensure_capacity(&ds->d_start, &ds->cap_start, bs)) != MBIK_OK) ||
+			(out_local && (rc = ensure_capacity(&ds->d_local, &ds->cap_local, bl)) != MBIK_OK) ||
+			(out_status && (rc = ensure_capacity(&ds->d_status, &ds->cap_status, bst)) != MBIK_OK)) {
+		return rc;
+	}
+	cudaStream_t st = ds->stream;
+	if (bt) {
+		cudaMemcpyAsync(ds->d_targets, targets, bt, cudaMemcpyHostToDevice, st);
+	}
+	if (start_pose) {
+		cudaMemcpyAsync(ds->d_start, start_pose, bs, cudaMemcpyHostToDevice, st);
+	}
+	a.targets = ds->d_targets;
+	a.start_pose = start_pose ? ds->d_start : nullptr;
+	a.out_pose = ds->d_out;
+	a.out_local = out_local ? ds->d_local : nullptr;
+	a.out_status = out_status ? ds->d_status : nullptr;
+	cudaEventRecord(ds->ev_start, st);
+	e = mbik::launch_solve(a, rig->n_solved, st);
+	cudaEventRecord(ds->ev_stop, st);
+	ds->timed = true;
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "kernel launch");
+	}
+	cudaMemcpyAsync(out_pose, ds->d_out, bo, cudaMemcpyDeviceToHost, st);
+	if (out_local) {
+		cudaMemcpyAsync(out_local, ds->d_local, bl, cudaMemcpyDeviceToHost, st);
+	}
+	if (out_status) {
+		cudaMemcpyAsync(out_status, ds->d_status, bst, cudaMemcpyDeviceToHost, st);
+	}
+	e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "solve (stream synchronize)");
+	}
+	return MBIK_OK;
+}
+
+int check_solve_args(mbik_rig *rig, const mbik_solve_params *params, size_t n_poses, const float *targets, float *out_pose, int *iterations) {
+	if (!rig) {
+		return fail(MBIK_ERR_INVALID_ARG, "rig is NULL");
+	}
+	if (n_poses > 0 && (!out_pose || (!targets && !rig->flat.pins.empty()))) {
+		return fail(MBIK_ERR_INVALID_ARG, "targets/out_pose must not be NULL");
+	}
+	int it = (params && params->iterations >= 0) ? params->iterations : rig->flat.iterations;
+	if (it < 0) {
+		it = 0;
+	}
+	*iterations = it;
+	return MBIK_OK;
+}
+
+} // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int mbik_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		return 0;
+	}
+	return n;
+}
+
+const char *mbik_strerror(int code) {
+	switch (code) {
+		case MBIK_OK: return "ok";
+		case MBIK_ERR_INVALID_ARG: return "invalid argument";
+		case MBIK_ERR_CUDA: return "CUDA error";
+		case MBIK_ERR_UNSUPPORTED: return "unsupported rig";
+		case MBIK_ERR_NO_DEVICE: return "no CUDA device (no CPU fallback)";
+		case MBIK_ERR_ALLOC: return "allocation failure";
+		default: return "unknown error";
+	}
+}
+
+const char *mbik_last_error(void) { return g_last_error.c_str(); }
+
+int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
+	if (!desc || !out_rig) {
+		return fail(MBIK_ERR_INVALID_ARG, "desc/out_rig is NULL");
+	}
+	*out_rig = nullptr;
+	mbik_rig *rig = new (std::nothrow) mbik_rig();
+	if (!rig) {
+		return fail(MBIK_ERR_ALLOC, "out of memory");
+	}
+	int rc = mbik::flatten_rig(desc, rig->flat);
+	if (rc != MBIK_OK) {
+		std::string msg = rig->flat.error;
+		delete rig;
+		return fail(rc, msg);
+	}
+	rig->n_solved = (int)rig->flat.bone_order.size();
+	if (mbik::kernel_capacity_for(rig->n_solved) < 0) {
+		delete rig;
+		return fail(MBIK_ERR_UNSUPPORTED, "rig has more solved bones than the largest kernel variant (128)");
+	}
+	if (desc->stabilization_passes > 0) {
+		delete rig;
+		return fail(MBIK_ERR_UNSUPPORTED, "stabilization_passes > 0 is not implemented yet (reference default is 0)");
+	}
+	if (rig->flat.blob.size() > 200 * 1024) {
+		delete rig;
+		return fail(MBIK_ERR_UNSUPPORTED, "rig constants exceed the shared-memory budget (200 KiB)");
+	}
+	*out_rig = rig;
+	return MBIK_OK;
+}
+
+int mbik_rig_destroy(mbik_rig *rig) {
+	if (!rig) {
+		return MBIK_OK;
+	}
+	for (auto &kv : rig->devices) {
+		free_device_state(kv.second);
+	}
+	delete rig;
+	return MBIK_OK;
+}
+
+int mbik_rig_get_info(const mbik_rig *rig, mbik_rig_info *o) {
+	if (!rig || !o) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	const mbik::FlatRig &F = rig->flat;
+	o->n_bones = F.n_bones;
+	o->n_solved = rig->n_solved;
+	o->n_segments = F.n_kept_segments;
+	o->n_steps = (int)F.steps.size();
+	o->n_effectors = F.n_effectors;
+	o->n_pins = (int)F.pins.size();
+	o->max_headings = F.max_headings;
+	o->n_cones = (int)F.cones.size();
+	o->iterations = F.iterations;
+	o->kernel_capacity = mbik::kernel_capacity_for(rig->n_solved);
+	o->rig_blob_bytes = (int64_t)F.blob.size();
+	o->flops_per_solve = F.flops_per_solve;
+	return MBIK_OK;
+}
+
+int mbik_rig_get_bone_order(const mbik_rig *rig, int32_t *out_bones) {
+	if (!rig || !out_bones) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	for (size_t i = 0; i < rig->flat.bone_order.size(); i++) {
+		out_bones[i] = rig->flat.bone_order[i];
+	}
+	return MBIK_OK;
+}
+
+int mbik_rig_get_step_weights(const mbik_rig *rig, int32_t step, double *out_weights, int32_t capacity) {
+	if (!rig || step < 0 || step >= (int)rig->flat.bone_order.size()) {
+		return fail(MBIK_ERR_INVALID_ARG, "bad step");
+	}
+	const mbik::FlatSegment &S = rig->flat.segments[rig->flat.seg_of_bone[rig->flat.bone_order[step]]];
+	for (int i = 0; i < (int)S.weights.size() && i < capacity && out_weights; i++) {
+		out_weights[i] = S.weights[i];
+	}
+	return (int)S.weights.size();
+}
+
+int mbik_rig_get_bone_frames(const mbik_rig *rig, float *out_dir_basis, float *out_twist_basis) {
+	if (!rig) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	const mbik::FlatRig &F = rig->flat;
+	for (size_t i = 0; i < F.bone_order.size(); i++) {
+		const mbik::BlobBone &B = F.bones[F.t_of_bone[F.bone_order[i]]];
+		if (out_dir_basis) {
+			memcpy(out_dir_basis + 9 * i, B.dir_basis, sizeof(float) * 9);
+		}
+		if (out_twist_basis) {
+			memcpy(out_twist_basis + 9 * i, B.twist_basis, sizeof(float) * 9);
+		}
+	}
+	return MBIK_OK;
+}
+
+int mbik_rig_get_cone_geometry(const mbik_rig *rig, float *out) {
+	if (!rig || !out) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	const mbik::FlatRig &F = rig->flat;
+	for (size_t i = 0; i < F.cone_row_index.size(); i++) {
+		float *o = out + 9 * i;
+		int k = F.cone_row_index[i];
+		if (k < 0) {
+			memset(o, 0, sizeof(float) * 9);
+			continue;
+		}
+		const mbik::BlobCone &c = F.cones[k];
+		memcpy(o, c.cp, sizeof(float) * 3);
+		memcpy(o + 3, c.tc1, sizeof(float) * 3);
+		memcpy(o + 6, c.tc2, sizeof(float) * 3);
+	}
+	return (int)F.cone_row_index.size();
+}
+
+int mbik_solve_batch(mbik_rig *rig, const mbik_solve_params *params, size_t n_poses, const float *targets, const float *start_pose,
+		float *out_pose, float *out_local, uint32_t *out_status) {
+	int iterations = 0;
+	int rc = check_solve_args(rig, params, n_poses, targets, out_pose, &iterations);
+	if (rc != MBIK_OK) {
+		return rc;
+	}
+	int device = -1;
+	if ((rc = resolve_device(params, &device)) != MBIK_OK) {
+		return rc;
+	}
+	uint32_t flags = params ? params->flags : MBIK_IO_HOST;
+	cudaStream_t stream = params ? (cudaStream_t)params->stream : nullptr;
+	int prev = -1;
+	cudaGetDevice(&prev);
+	rc = solve_on_device(rig, device, flags, stream, iterations, n_poses, targets, start_pose, out_pose, out_local, out_status);
+	if (prev >= 0 && prev != device) {
+		cudaSetDevice(prev);
+	}
+	return rc;
+}
+
+int mbik_solve_batch_multi(mbik_rig *rig, const mbik_solve_params *params, size_t n_poses, const float *targets, const float *start_pose,
+		float *out_pose, float *out_local, uint32_t *out_status, const int32_t *devices, int32_t n_devices) {
+	int iterations = 0;
+	int rc = check_solve_args(rig, params, n_poses, targets, out_pose, &iterations);
+	if (rc != MBIK_OK) {
+		return rc;
+	}
+	int count = mbik_device_count();
+	if (count <= 0) {
+		return fail(MBIK_ERR_NO_DEVICE, "no CUDA device: mbik has no CPU fallback");
+	}
+	if (n_devices <= 0) {
+		return fail(MBIK_ERR_INVALID_ARG, "n_devices must be > 0");
+	}
+	if (params && (params->flags & MBIK_IO_DEVICE)) {
+		return fail(MBIK_ERR_INVALID_ARG, "mbik_solve_batch_multi takes host buffers only");
+	}
+	std::vector<int> devs(n_devices);
+	for (int i = 0; i < n_devices; i++) {
+		devs[i] = devices ? devices[i] : i;
+		if (devs[i] < 0 || devs[i] >= count) {
+			return fail(MBIK_ERR_INVALID_ARG, "device ordinal out of range");
+		}
+	}
+	const size_t nb = (size_t)rig->flat.n_bones, np = rig->flat.pins.size();
+	std::vector<int> rcs(n_devices, MBIK_OK);
+	std::vector<std::string> msgs(n_devices);
+	std::vector<std::thread> workers;
+	for (int g = 0; g < n_devices; g++) {
+		// contiguous split of the pose index range: device g gets [g*n/G, (g+1)*n/G)
+		size_t b = n_poses * (size_t)g / (size_t)n_devices, e = n_poses * (size_t)(g + 1) / (size_t)n_devices;
+		workers.emplace_back([&, g, b, e]() {
+			rcs[g] = solve_on_device(rig, devs[g], MBIK_IO_HOST, nullptr, iterations, e - b, targets + b * np * 12,
+					start_pose ? start_pose + b * nb * 12 : nullptr, out_pose + b * nb * 10, out_local ? out_local + b * nb * 12 : nullptr,
+					out_status ? out_status + b : nullptr);
+			if (rcs[g] != MBIK_OK) {
+				msgs[g] = g_last_error;
+			}
+		});
+	}
+	for (auto &w : workers) {
+		w.join();
+	}
+	for (int g = 0; g < n_devices; g++) {
+		if (rcs[g] != MBIK_OK) {
+			return fail(rcs[g], msgs[g]);
+		}
+	}
+	return MBIK_OK;
+}
+
+void *mbik_alloc_pinned(size_t bytes) {
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+		g_last_error = "cudaMallocHost failed";
+		return nullptr;
+	}
+	return p;
+}
+
+void mbik_free_pinned(void *p) {
+	if (p) {
+		cudaFreeHost(p);
+	}
+}
+
+int mbik_last_kernel_ms(mbik_rig *rig, int32_t device, float *out_ms) {
+	if (!rig || !out_ms) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lock(rig->mu);
+	auto it = rig->devices.find(device);
+	if (it == rig->devices.end() || !it->second.timed) {
+		return fail(MBIK_ERR_INVALID_ARG, "no launch recorded on that device");
+	}
+	cudaSetDevice(device);
+	cudaError_t e = cudaEventSynchronize(it->second.ev_stop);
+	if (e == cudaSuccess) {
+		e = cudaEventElapsedTime(out_ms, it->second.ev_start, it->second.ev_stop);
+	}
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "event timing");
+	}
+	return MBIK_OK;
+}
+
+#pragma GCC visibility pop
+} // extern "C"

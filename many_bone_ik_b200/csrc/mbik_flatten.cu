@@ -1,0 +1,821 @@
+// mbik_flatten.cu -- host-side flattener (see mbik_flatten.h).  Pure host code; compiled by nvcc only so
+// that it shares mbik_math.cuh with the kernel.  Citations are to /root/reference.
+#include "mbik_flatten.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+
+namespace mbik {
+namespace {
+
+const double kPi = 3.1415926535897932384626433833;
+
+X34 load_x34(const float *p) {
+	X34 t;
+	for (int i = 0; i < 9; i++) {
+		t.b.m[i] = p[i];
+	}
+	t.o = v3(p[9], p[10], p[11]);
+	return t;
+}
+
+// IKKusudama3D::get_quaternion_axis_angle (src/ik_kusudama_3d.cpp:417-427): divides by |axis|^2
+Q4 quat_axis_angle_len2(V3 axis, float angle) {
+	float d = vlen2(axis);
+	if (d == 0) {
+		return q4(0, 0, 0, 1);
+	}
+	float sin_angle = sinf(r_mul(angle, 0.5f));
+	float cos_angle = cosf(r_mul(angle, 0.5f));
+	float s = r_div(sin_angle, d);
+	return q4(r_mul(axis.x, s), r_mul(axis.y, s), r_mul(axis.z, s), cos_angle);
+}
+
+// engine Basis(axis, angle) -- only used by _update_constraint through Vector3::rotated
+M3 m3_axis_angle(V3 a, float angle) {
+	V3 sq = v3(r_mul(a.x, a.x), r_mul(a.y, a.y), r_mul(a.z, a.z));
+	float cosine = cosf(angle);
+	M3 r;
+	r.m[0] = r_add(sq.x, r_mul(cosine, r_sub(1.0f, sq.x)));
+	r.m[4] = r_add(sq.y, r_mul(cosine, r_sub(1.0f, sq.y)));
+	r.m[8] = r_add(sq.z, r_mul(cosine, r_sub(1.0f, sq.z)));
+	float sine = sinf(angle);
+	float t = r_sub(1.0f, cosine);
+	float xyzt = r_mul(r_mul(a.x, a.y), t);
+	float zyxs = r_mul(a.z, sine);
+	r.m[1] = r_sub(xyzt, zyxs);
+	r.m[3] = r_add(xyzt, zyxs);
+	xyzt = r_mul(r_mul(a.x, a.z), t);
+	zyxs = r_mul(a.y, sine);
+	r.m[2] = r_add(xyzt, zyxs);
+	r.m[6] = r_sub(xyzt, zyxs);
+	xyzt = r_mul(r_mul(a.y, a.z), t);
+	zyxs = r_mul(a.x, sine);
+	r.m[5] = r_sub(xyzt, zyxs);
+	r.m[7] = r_add(xyzt, zyxs);
+	return r;
+}
+
+float godot_acosf(float x) { return x < -1.0f ? (float)kPi : (x > 1.0f ? 0.0f : acosf(x)); }
+
+// ---- IKRay3D pieces used by the tangent-circle construction (src/ik_ray_3d.cpp) -------------------------
+struct Ray {
+	V3 p1, p2;
+};
+// :64-73
+void ray_elongate(Ray &r, float amt) {
+	V3 mid = vmuls(vadd(r.p1, r.p2), 0.5f);
+	V3 h1 = vsub(r.p1, mid), h2 = vsub(r.p2, mid);
+	V3 a1 = vmuls(vnorm(h1), amt), a2 = vmuls(vnorm(h2), amt);
+	r.p1 = vadd(vadd(h1, a1), mid);
+	r.p2 = vadd(vadd(h2, a2), mid);
+}
+// :75-85 + plane_intersect_test :146-166
+V3 ray_intersects_plane(const Ray &r, V3 ta, V3 tb, V3 tc) {
+	ta = vsub(ta, r.p1);
+	tb = vsub(tb, r.p1);
+	tc = vsub(tc, r.p1);
+	V3 u = vsub(tb, ta), v = vsub(tc, ta);
+	V3 n = vnorm(vcross(u, v));
+	V3 dir = vsub(r.p2, r.p1);
+	V3 w0 = vsub(v3(0, 0, 0), ta);
+	float a = -vdot(n, w0);
+	float b = vdot(n, dir);
+	float rr = r_div(a, b);
+	V3 I = vmuls(dir, rr);
+	return vadd(I, r.p1);
+}
+// :87-94 + :112-144 with the sphere at the origin, radius 1
+void ray_intersects_unit_sphere(const Ray &r, V3 &S1, V3 &S2) {
+	V3 c = v3(0, 0, 0);
+	V3 rp1 = vsub(r.p1, c), rp2 = vsub(r.p2, c);
+	S1 = v3(0, 0, 0);
+	S2 = v3(0, 0, 0);
+	V3 e = vnorm(vsub(rp2, rp1));
+	V3 h = vsub(v3(0, 0, 0), rp1);
+	float lf = vdot(e, h);
+	float radpow = r_mul(1.0f, 1.0f);
+	float hdh = vlen2(h);
+	float lfpow = r_mul(lf, lf);
+	float s = r_add(r_sub(radpow, hdh), lfpow);
+	if (!(s < 0.0f)) {
+		s = r_sqrt(s);
+		if (lf < s) {
+			if (r_add(lf, s) >= 0) {
+				s = -s;
+			}
+		}
+		S1 = vadd(vmuls(e, r_sub(lf, s)), rp1);
+		S2 = vadd(vmuls(e, r_add(lf, s)), rp1);
+	}
+	S1 = vadd(S1, c);
+	S2 = vadd(S2, c);
+}
+
+// IKLimitCone3D::get_orthogonal (src/ik_open_cone_3d.cpp:267-283)
+V3 cone_get_orthogonal(V3 p) {
+	float threshold = r_mul(vlen(p), 0.6f);
+	if (threshold > 0.f) {
+		if (fabsf(p.x) <= threshold) {
+			float inv = r_div(1.f, r_sqrt(r_add(r_mul(p.y, p.y), r_mul(p.z, p.z))));
+			return v3(0.f, r_mul(inv, p.z), r_mul(-inv, p.y));
+		} else if (fabsf(p.y) <= threshold) {
+			float inv = r_div(1.f, r_sqrt(r_add(r_mul(p.x, p.x), r_mul(p.z, p.z))));
+			return v3(r_mul(-inv, p.z), 0.f, r_mul(inv, p.x));
+		}
+		float inv = r_div(1.f, r_sqrt(r_add(r_mul(p.x, p.x), r_mul(p.y, p.y))));
+		return v3(r_mul(inv, p.y), r_mul(-inv, p.x), 0.f);
+	}
+	return v3(0, 0, 0);
+}
+
+struct HostCone {
+	V3 cp;
+	double radius, radius_cos;
+	V3 tc1 = v3(0, 0, 0), tc2 = v3(0, 0, 0);
+	double tan_r = 0, tan_cos = 0;
+};
+
+// IKLimitCone3D::update_tangent_handles (src/ik_open_cone_3d.cpp:36-120)
+void update_tangent_handles(HostCone &A, const HostCone &B) {
+	double radA = A.radius, radB = B.radius;
+	V3 a = A.cp, b = B.cp;
+	V3 arc_normal = vnorm(vcross(a, b));
+	double tRadius = (kPi - (radA + radB)) / 2;
+	double bA = radA + tRadius, bB = radB + tRadius;
+
+	V3 scaledAxisA = vmuls(a, (float)cos(bA));
+	V3 planeDir1A = q_xform(quat_axis_angle_len2(arc_normal, (float)bA), a);
+	V3 planeDir2A = q_xform(quat_axis_angle_len2(a, (float)(kPi / 2)), planeDir1A);
+
+	V3 scaledAxisB = vmuls(b, (float)cos(bB));
+	V3 planeDir1B = q_xform(quat_axis_angle_len2(arc_normal, (float)bB), b);
+	V3 planeDir2B = q_xform(quat_axis_angle_len2(b, (float)(kPi / 2)), planeDir1B);
+
+	Ray r1B{ planeDir1B, scaledAxisB }, r2B{ planeDir1B, planeDir2B };
+	ray_elongate(r1B, 99);
+	ray_elongate(r2B, 99);
+	V3 i1 = ray_intersects_plane(r1B, scaledAxisA, planeDir1A, planeDir2A);
+	V3 i2 = ray_intersects_plane(r2B, scaledAxisA, planeDir1A, planeDir2A);
+	Ray ir{ i1, i2 };
+	ray_elongate(ir, 99);
+	V3 s1, s2;
+	ray_intersects_unit_sphere(ir, s1, s2);
+	A.tc1 = vnorm(s1);
+	A.tc2 = vnorm(s2);
+	A.tan_r = tRadius;
+	A.tan_cos = cos(tRadius);
+	if (f_is_zero_approx(vlen2(A.tc1))) {
+		A.tc1 = vnorm(cone_get_orthogonal(A.cp));
+	}
+	if (f_is_zero_approx(vlen2(A.tc2))) {
+		A.tc2 = vnorm(cone_get_orthogonal(vmuls(A.tc1, -1.0f)));
+	}
+}
+
+// IKLimitCone3D::set_control_point (src/ik_open_cone_3d.cpp:159-166)
+V3 set_control_point(V3 p) {
+	if (f_is_zero_approx(vlen2(p))) {
+		return v3(0, 1, 0);
+	}
+	return vnorm(p);
+}
+
+template <class T>
+uint32_t append_section(std::vector<unsigned char> &blob, const std::vector<T> &v) {
+	while (blob.size() % 16) {
+		blob.push_back(0);
+	}
+	uint32_t off = (uint32_t)blob.size();
+	if (!v.empty()) {
+		const unsigned char *p = reinterpret_cast<const unsigned char *>(v.data());
+		blob.insert(blob.end(), p, p + sizeof(T) * v.size());
+	}
+	return off;
+}
+
+} // namespace
+
+int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
+	if (!d || d->n_bones <= 0 || !d->parent || !d->rest_local) {
+		R.error = "rig description needs n_bones > 0, parent[] and rest_local[]";
+		return MBIK_ERR_INVALID_ARG;
+	}
+	if ((d->n_pins > 0 && !d->pins) || (d->n_constraints > 0 && !d->constraints) || (d->n_bone_damp > 0 && !d->bone_damp)) {
+		R.error = "null table with non-zero count";
+		return MBIK_ERR_INVALID_ARG;
+	}
+	const int nb = d->n_bones;
+	R.n_bones = nb;
+	R.parent.assign(d->parent, d->parent + nb);
+	R.rest_local.resize(nb);
+	for (int b = 0; b < nb; b++) {
+		if (R.parent[b] >= nb || R.parent[b] == b) {
+			R.error = "bad parent index";
+			return MBIK_ERR_INVALID_ARG;
+		}
+		R.rest_local[b] = load_x34(d->rest_local + 12 * b);
+	}
+	R.pins.assign(d->pins, d->pins + d->n_pins);
+	for (auto &p : R.pins) {
+		// IKEffector3D::set_motion_propagation_factor clamps to [0,1] (src/ik_effector_3d.cpp:173-175)
+		double v = p.motion_propagation_factor;
+		p.motion_propagation_factor = (float)(v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v));
+	}
+	R.iterations = d->iterations_per_frame;
+
+	// Skeleton3D queries: children ascending, parentless ascending (engine process order)
+	std::vector<std::vector<int>> sk_children(nb);
+	std::vector<int> sk_roots;
+	for (int b = 0; b < nb; b++) {
+		if (R.parent[b] >= 0) {
+			sk_children[R.parent[b]].push_back(b);
+		} else {
+			sk_roots.push_back(b);
+		}
+	}
+	{ // reject cycles
+		for (int b = 0; b < nb; b++) {
+			int hops = 0;
+			for (int p = R.parent[b]; p >= 0; p = R.parent[p]) {
+				if (++hops > nb) {
+					R.error = "parent table has a cycle";
+					return MBIK_ERR_INVALID_ARG;
+				}
+			}
+		}
+	}
+	if (sk_roots.empty()) {
+		R.error = "skeleton has no parentless bone";
+		return MBIK_ERR_INVALID_ARG;
+	}
+
+	// first pin row naming a bone wins (IKBone3D ctor, src/ik_bone_3d.cpp:209-222)
+	std::vector<int> pin_of_bone(nb, -1);
+	for (int i = 0; i < (int)R.pins.size(); i++) {
+		int b = R.pins[i].bone;
+		if (b >= 0 && b < nb && pin_of_bone[b] < 0) {
+			pin_of_bone[b] = i;
+		}
+	}
+
+	// ---- IK bone graph: every IKBone3D the reference creates, including those of dropped segments ----
+	std::vector<char> ik_exists(nb, 0);
+	std::vector<int> ik_parent(nb, -1);
+	std::vector<std::vector<int>> ik_children(nb); // creation order (IKBone3D::set_parent push_back, :46-55)
+	std::vector<float> ik_default_damp(nb, 0.f);
+
+	// ---- segment generation (src/ik_bone_segment_3d.cpp:247-264, :352-427) ----
+	std::function<int(int, int)> build_segment = [&](int root_bone, int parent_seg) -> int {
+		int si = (int)R.segments.size();
+		R.segments.emplace_back();
+		R.segments[si].root_bone = root_bone;
+		R.segments[si].parent_seg = parent_seg;
+		ik_exists[root_bone] = 1;
+		ik_default_damp[root_bone] = (float)kPi; // segment roots are created with Math_PI (:252)
+		if (parent_seg >= 0) {
+			int ptip = R.segments[parent_seg].tip_bone;
+			ik_parent[root_bone] = ptip;
+			ik_children[ptip].push_back(root_bone);
+		}
+		int current_tip = root_bone;
+		while (true) { // generate_default_segments with p_tip_bone == -1
+			const std::vector<int> &children = sk_children[current_tip];
+			bool pinned = pin_of_bone[current_tip] >= 0;
+			if (children.empty() || children.size() > 1 || pinned) {
+				// _process_children
+				R.segments[si].tip_bone = current_tip;
+				for (int child : children) {
+					int ci = build_segment(child, si);
+					if (R.segments[ci].pinned_descendants) {
+						R.segments[si].pinned_descendants = true;
+						R.segments[si].child_segs.push_back(ci);
+					} else {
+						R.segments[ci].kept = false;
+					}
+				}
+				break;
+			}
+			// _create_next_bone
+			int next = children[0];
+			ik_exists[next] = 1;
+			ik_default_damp[next] = d->default_damp;
+			ik_parent[next] = current_tip;
+			ik_children[current_tip].push_back(next);
+			current_tip = next;
+		}
+		// _finalize_segment
+		FlatSegment &S = R.segments[si];
+		S.tip_bone = current_tip;
+		if (pin_of_bone[current_tip] >= 0) {
+			S.pinned_descendants = true;
+		}
+		for (int b = current_tip;; b = ik_parent[b]) {
+			S.bones.push_back(b);
+			if (b == root_bone) {
+				break;
+			}
+		}
+		return si;
+	};
+
+	std::vector<char> node_has_parent(nb, 1); // IKNode3D parent of the aligned node
+	for (size_t ri = 0; ri < sk_roots.size(); ri++) {
+		int si = build_segment(sk_roots[ri], -1);
+		R.segments[si].stabilize = d->stabilization_passes; // only root segments receive it (many_bone_ik_3d.cpp:1021)
+		R.root_segments.push_back(si);
+		// `ik_origin.instantiate()` per root frees the previous origin node, un-parenting the earlier roots
+		node_has_parent[sk_roots[ri]] = (ri + 1 == sk_roots.size()) ? 1 : 0;
+	}
+	// dropped segments: mark whole subtrees as not kept
+	{
+		std::function<void(int, bool)> mark = [&](int si, bool kept) {
+			R.segments[si].kept = kept;
+			(void)kept;
+		};
+		// a dropped segment's descendants were never linked into a kept parent's child_segs; their `kept`
+		// flag stays true from construction, so recompute reachability from the roots instead.
+		for (auto &s : R.segments) {
+			s.kept = false;
+		}
+		std::function<void(int)> reach = [&](int si) {
+			R.segments[si].kept = true;
+			for (int c : R.segments[si].child_segs) {
+				reach(c);
+			}
+		};
+		for (int si : R.root_segments) {
+			reach(si);
+		}
+		(void)mark;
+	}
+
+	// ---- bone_list (create_bone_list recursive, :56-72) ----
+	R.seg_of_bone.assign(nb, -1);
+	std::function<void(int)> list_bones = [&](int si) {
+		for (int c : R.segments[si].child_segs) {
+			list_bones(c);
+		}
+		for (int b : R.segments[si].bones) {
+			R.bone_order.push_back(b);
+			R.seg_of_bone[b] = si;
+		}
+	};
+	for (int si : R.root_segments) {
+		list_bones(si);
+	}
+	const int ns = (int)R.bone_order.size();
+	R.n_kept_segments = 0;
+	for (auto &s : R.segments) {
+		R.n_kept_segments += s.kept ? 1 : 0;
+	}
+
+	// ---- effector lists (update_pinned_list, :74-88) and heading weights (:281-343) ----
+	std::function<void(int)> pinned_list = [&](int si) {
+		FlatSegment &S = R.segments[si];
+		for (int c : S.child_segs) {
+			pinned_list(c);
+		}
+		bool pinned = pin_of_bone[S.tip_bone] >= 0;
+		if (pinned) {
+			S.effectors.push_back(S.tip_bone);
+		}
+		double mpf = pinned ? (double)R.pins[pin_of_bone[S.tip_bone]].motion_propagation_factor : 1.0;
+		if (mpf > 0.0) {
+			for (int c : S.child_segs) {
+				S.effectors.insert(S.effectors.end(), R.segments[c].effectors.begin(), R.segments[c].effectors.end());
+			}
+		}
+	};
+	for (int si : R.root_segments) {
+		pinned_list(si);
+	}
+	std::function<void(int, std::vector<double> &, double)> penalty = [&](int si, std::vector<double> &out, double falloff) {
+		if (falloff <= 0.0) {
+			return;
+		}
+		double current_falloff = 1.0;
+		FlatSegment &S = R.segments[si];
+		if (pin_of_bone[S.tip_bone] >= 0) {
+			const mbik_pin_desc &pin = R.pins[pin_of_bone[S.tip_bone]];
+			double weight = pin.weight;
+			out.push_back(weight * falloff);
+			float pm = std::max(std::max(pin.direction_priorities[0], pin.direction_priorities[1]), pin.direction_priorities[2]);
+			double max_pin_weight = pm;
+			max_pin_weight = max_pin_weight == 0.0 ? 1.0 : max_pin_weight;
+			for (int i = 0; i < 3; ++i) {
+				double priority = pin.direction_priorities[i];
+				if (priority > 0.0) {
+					double sub = weight * (priority / max_pin_weight) * falloff;
+					out.push_back(sub);
+					out.push_back(sub);
+				}
+			}
+			current_falloff = pin.motion_propagation_factor;
+		}
+		for (int c : S.child_segs) {
+			penalty(c, out, falloff * current_falloff);
+		}
+	};
+	for (auto &S : R.segments) {
+		if (!S.kept) {
+			continue;
+		}
+		int si = (int)(&S - &R.segments[0]);
+		penalty(si, S.weights, 1.0);
+		int h = 0;
+		for (int e : S.effectors) {
+			const mbik_pin_desc &pin = R.pins[pin_of_bone[e]];
+			h += 1;
+			for (int a = 0; a < 3; a++) {
+				h += pin.direction_priorities[a] > 0.0 ? 2 : 0;
+			}
+		}
+		if (h != (int)S.weights.size()) {
+			R.error = "effector list and heading weights disagree (motion_propagation_factor underflow?)";
+			return MBIK_ERR_UNSUPPORTED;
+		}
+		R.max_headings = std::max(R.max_headings, h);
+	}
+
+	// ---- topological numbering of solved bones ----
+	R.t_of_bone.assign(nb, -1);
+	{
+		std::vector<char> solved(nb, 0);
+		for (int b : R.bone_order) {
+			solved[b] = 1;
+		}
+		std::function<void(int)> visit = [&](int b) {
+			if (!solved[b]) {
+				return;
+			}
+			R.t_of_bone[b] = (int)R.topo.size();
+			R.topo.push_back(b);
+			for (int c : ik_children[b]) {
+				visit(c);
+			}
+		};
+		for (int r : sk_roots) {
+			visit(r);
+		}
+		if ((int)R.topo.size() != ns) {
+			R.error = "internal: topological order incomplete";
+			return MBIK_ERR_UNSUPPORTED;
+		}
+		for (int b = 0; b < nb; b++) {
+			if (!solved[b]) {
+				R.pass.push_back(BlobPass{ b });
+			}
+		}
+	}
+
+	// ---- setup-time poses: _update_ik_bones_transform (many_bone_ik_3d.cpp:91-102) seeds bone_list members
+	//      from the skeleton; IK bones of dropped segments keep an identity local pose ----
+	std::vector<X34> ik_local(nb, x_identity());
+	for (int b : R.bone_order) {
+		ik_local[b] = R.rest_local[b];
+	}
+	std::function<X34(int)> ik_global = [&](int b) -> X34 {
+		if (ik_parent[b] >= 0) {
+			return x_mul(ik_global(ik_parent[b]), ik_local[b]);
+		}
+		if (node_has_parent[b]) {
+			return x_mul(x_identity(), ik_local[b]); // child of the identity ik_origin node
+		}
+		return ik_local[b];
+	};
+
+	// ---- bone direction frames (IKBone3D::update_default_bone_direction_transform, src/ik_bone_3d.cpp:57-93),
+	//      evaluated in bone_list order: children before parents ----
+	std::vector<M3> dir_basis(nb, m3_identity());
+	auto dir_global_basis = [&](int b) { return m3_mul(ik_global(b).b, dir_basis[b]); };
+	for (int b : R.bone_order) {
+		V3 centroid = v3(0, 0, 0);
+		int child_count = 0;
+		for (int c : ik_children[b]) {
+			centroid = vadd(centroid, ik_global(c).o);
+			child_count++;
+		}
+		if (child_count > 0) {
+			centroid = vdivs(centroid, (float)child_count);
+		} else {
+			// reference: loops over Skeleton3D children (none, or IK children would exist) then divides by 0
+			for (int c : sk_children[b]) {
+				X34 g = R.rest_local[c];
+				for (int p = R.parent[c]; p >= 0; p = R.parent[p]) {
+					g = x_mul(R.rest_local[p], g); // not reached in practice; kept for completeness
+				}
+				centroid = vadd(centroid, g.o);
+			}
+			centroid = vdivs(centroid, (float)sk_children[b].size());
+		}
+		X34 G = ik_global(b);
+		centroid = vsub(centroid, G.o);
+		if (f_is_zero_approx(vlen2(centroid))) {
+			int src = ik_parent[b] >= 0 ? ik_parent[b] : b;
+			centroid = m3_col(dir_global_basis(src), 1);
+		}
+		if (!f_is_zero_approx(vlen2(centroid)) && (!ik_children[b].empty() || !sk_children[b].empty())) {
+			centroid = vnorm(centroid);
+			V3 bone_direction = vnorm(m3_col(dir_global_basis(b), 1));
+			M3 rot = m3_from_quat(q_shortest_arc(centroid, bone_direction));
+			// rotate_local_with_global on the direction node, whose parent is the aligned node (always present)
+			dir_basis[b] = m3_mul(m3_mul(m3_mul(m3_inverse(G.b), rot), G.b), dir_basis[b]);
+		}
+	}
+
+	// ---- constraints (many_bone_ik_3d.cpp:1037-1067) ----
+	struct BoneConstraint {
+		bool present = false;
+		std::vector<HostCone> cones;
+		std::vector<int> desc_cone_index;
+		Q4 twist_center_rot = q4(0, 0, 0, 1);
+		float twist_cos = 0;
+	};
+	std::vector<BoneConstraint> cons(nb);
+	std::vector<M3> twist_basis(nb, m3_identity());
+	int n_desc_cones = 0;
+	for (int ci = 0; ci < d->n_constraints; ci++) {
+		n_desc_cones = std::max(n_desc_cones, d->constraints[ci].cone_offset + std::max(0, d->constraints[ci].n_cones));
+	}
+	R.cone_row_index.assign(n_desc_cones, -1);
+	for (int ci = 0; ci < d->n_constraints; ci++) {
+		const mbik_constraint_desc &cd = d->constraints[ci];
+		int b = cd.bone;
+		if (b < 0 || b >= nb || R.t_of_bone[b] < 0) {
+			continue; // not in bone_list: the row is ignored
+		}
+		if (cd.n_cones < 0 || (cd.n_cones > 0 && !d->cones)) {
+			R.error = "bad cone table";
+			return MBIK_ERR_INVALID_ARG;
+		}
+		BoneConstraint bc;
+		bc.present = true;
+		auto update_tangent_radii = [&]() { // src/ik_kusudama_3d.cpp:91-101
+			for (size_t i = 0; i + 1 < bc.cones.size(); i++) {
+				update_tangent_handles(bc.cones[i], bc.cones[i + 1]);
+			}
+		};
+		for (int j = 0; j < cd.n_cones; j++) {
+			const mbik_cone_desc &c = d->cones[cd.cone_offset + j];
+			V3 ctr = v3(c.center[0], c.center[1], c.center[2]);
+			if (f_is_zero_approx(vlen2(ctr))) {
+				ctr = v3(0, 1, 0); // set_kusudama_open_cone_center (many_bone_ik_3d.cpp:586-601)
+			}
+			HostCone hc;
+			hc.radius = std::max(1.0e-38, (double)c.radius);
+			hc.radius_cos = cos(hc.radius);
+			hc.cp = set_control_point(vnorm(ctr));
+			bc.cones.push_back(hc);
+			bc.desc_cone_index.push_back(cd.cone_offset + j);
+			update_tangent_radii(); // add_open_cone (src/ik_kusudama_3d.cpp:160-166)
+		}
+		// set_axial_limits (src/ik_kusudama_3d.cpp:103-115)
+		{
+			V3 y_axis = v3(0, 1, 0), z_axis = v3(0, 0, 1);
+			Q4 twist_min_rot = quat_axis_angle_len2(y_axis, cd.twist_from);
+			V3 twist_min_vec = vnorm(q_xform(twist_min_rot, z_axis));
+			V3 twist_center_vec = vnorm(q_xform(twist_min_rot, twist_min_vec));
+			bc.twist_center_rot = q_shortest_arc(z_axis, twist_center_vec);
+			bc.twist_cos = cosf(r_div(cd.twist_range, 4.0f));
+		}
+		// _update_constraint(twist node) (src/ik_kusudama_3d.cpp:37-89)
+		{
+			std::vector<V3> directions;
+			if (bc.cones.size() == 1) {
+				directions.push_back(bc.cones[0].cp);
+			} else {
+				for (size_t i = 0; i + 1 < bc.cones.size(); i++) {
+					V3 a = bc.cones[i].cp, n = bc.cones[i + 1].cp;
+					Q4 q = q_shortest_arc(a, n);
+					V3 axis;
+					if (fabsf(q.w) > r_sub(1.0f, kCmpEps)) {
+						axis = v3(q.x, q.y, q.z);
+					} else {
+						float r = r_div(1.0f, r_sqrt(r_sub(1.0f, r_mul(q.w, q.w))));
+						axis = v3(r_mul(q.x, r), r_mul(q.y, r), r_mul(q.z, r));
+					}
+					float full = r_mul(2.0f, godot_acosf(q.w));
+					double angle = (double)full / 2.0;
+					V3 half = m3_xform(m3_axis_angle(axis, (float)angle), a);
+					half = vmuls(half, full);
+					half = vnorm(half);
+					directions.push_back(half);
+				}
+			}
+			V3 new_y = v3(0, 0, 0);
+			for (V3 dv : directions) {
+				new_y = vadd(new_y, dv);
+			}
+			if (!directions.empty()) {
+				new_y = vdivs(new_y, (float)directions.size());
+				new_y = vnorm(new_y);
+			}
+			if (ik_parent[b] >= 0) { // the twist node's parent is the parent bone's aligned node (src/ik_bone_3d.cpp:52-54)
+				M3 P = ik_global(ik_parent[b]).b;
+				M3 Gtw = m3_mul(P, twist_basis[b]);
+				Q4 q = q_shortest_arc(vnorm(m3_col(Gtw, 1)), vnorm(m3_xform(Gtw, new_y)));
+				twist_basis[b] = m3_mul(m3_mul(m3_mul(m3_inverse(P), m3_from_quat(q)), P), twist_basis[b]);
+			}
+			for (auto &c : bc.cones) {
+				c.cp = set_control_point(vnorm(c.cp));
+			}
+			update_tangent_radii();
+		}
+		cons[b] = bc;
+	}
+
+	// ---- emit per-bone constants, cones ----
+	R.bones.resize(ns);
+	std::vector<int> cone_off(nb, 0), cone_cnt(nb, 0);
+	for (int t = 0; t < ns; t++) {
+		int b = R.topo[t];
+		BlobBone &B = R.bones[t];
+		memset(&B, 0, sizeof(B));
+		B.skel_bone = b;
+		B.parent = ik_parent[b] >= 0 ? R.t_of_bone[ik_parent[b]] : -1;
+		B.flags = node_has_parent[b] ? STEP_NODE_PARENT : 0;
+		B.twist_cos = cons[b].twist_cos;
+		M3 ident = m3_identity();
+		memcpy(B.dir_basis, dir_basis[b].m, sizeof(float) * 9);
+		memcpy(B.orient_basis, ident.m, sizeof(float) * 9);
+		memcpy(B.twist_basis, twist_basis[b].m, sizeof(float) * 9);
+		M3 tc = m3_from_quat(cons[b].twist_center_rot);
+		memcpy(B.twist_center, tc.m, sizeof(float) * 9);
+		if (cons[b].present) {
+			cone_off[b] = (int)R.cones.size();
+			cone_cnt[b] = (int)cons[b].cones.size();
+			for (size_t i = 0; i < cons[b].cones.size(); i++) {
+				const HostCone &c = cons[b].cones[i];
+				BlobCone bc;
+				memset(&bc, 0, sizeof(bc));
+				V3 ncp = vnorm(c.cp);
+				bc.cp[0] = c.cp.x; bc.cp[1] = c.cp.y; bc.cp[2] = c.cp.z;
+				bc.ncp[0] = ncp.x; bc.ncp[1] = ncp.y; bc.ncp[2] = ncp.z;
+				float rf = (float)c.radius;
+				bc.sin_half_r = sinf(r_mul(rf, 0.5f));
+				bc.cos_half_r = cosf(r_mul(rf, 0.5f));
+				bc.radius_cos = c.radius_cos;
+				if (i + 1 < cons[b].cones.size()) {
+					const HostCone &n = cons[b].cones[i + 1];
+					bc.tan_cos = c.tan_cos;
+					bc.tc1[0] = c.tc1.x; bc.tc1[1] = c.tc1.y; bc.tc1[2] = c.tc1.z;
+					bc.tc2[0] = c.tc2.x; bc.tc2[1] = c.tc2.y; bc.tc2[2] = c.tc2.z;
+					float tf = (float)c.tan_r;
+					bc.sin_half_t = sinf(r_mul(tf, 0.5f));
+					bc.cos_half_t = cosf(r_mul(tf, 0.5f));
+					V3 a = vcross(c.cp, n.cp);
+					V3 e1 = vnorm(vcross(c.cp, c.tc1)), e2 = vnorm(vcross(c.tc1, n.cp));
+					V3 e3 = vnorm(vcross(c.tc2, c.cp)), e4 = vnorm(vcross(n.cp, c.tc2));
+					bc.c1xc2[0] = a.x; bc.c1xc2[1] = a.y; bc.c1xc2[2] = a.z;
+					bc.c1xt1[0] = e1.x; bc.c1xt1[1] = e1.y; bc.c1xt1[2] = e1.z;
+					bc.t1xc2[0] = e2.x; bc.t1xc2[1] = e2.y; bc.t1xc2[2] = e2.z;
+					bc.t2xc1[0] = e3.x; bc.t2xc1[1] = e3.y; bc.t2xc1[2] = e3.z;
+					bc.c2xt2[0] = e4.x; bc.c2xt2[1] = e4.y; bc.c2xt2[2] = e4.z;
+				}
+				R.cone_row_index[cons[b].desc_cone_index[i]] = (int)R.cones.size();
+				R.cones.push_back(bc);
+			}
+		}
+	}
+
+	// ---- per-segment effector entries ----
+	std::vector<int> seg_eff_off(R.segments.size(), 0);
+	std::vector<char> is_effector(nb, 0);
+	for (size_t si = 0; si < R.segments.size(); si++) {
+		FlatSegment &S = R.segments[si];
+		if (!S.kept) {
+			continue;
+		}
+		seg_eff_off[si] = (int)R.effs.size();
+		int h = 0;
+		for (int e : S.effectors) {
+			const mbik_pin_desc &pin = R.pins[pin_of_bone[e]];
+			BlobEff E;
+			memset(&E, 0, sizeof(E));
+			E.bone = R.t_of_bone[e];
+			E.pin = pin_of_bone[e];
+			E.w_origin = S.weights[h++];
+			E.n_headings = 1;
+			for (int a = 0; a < 3; a++) {
+				E.prio[a] = pin.direction_priorities[a];
+				if (pin.direction_priorities[a] > 0.0) {
+					E.w_axis[a] = S.weights[h];
+					h += 2;
+					E.n_headings += 2;
+				}
+			}
+			is_effector[e] = 1;
+			R.effs.push_back(E);
+		}
+	}
+	for (int b = 0; b < nb; b++) {
+		R.n_effectors += is_effector[b];
+	}
+
+	// ---- steps in bone_list order, with the FK refresh list of each ----
+	double flops_iter = 0;
+	int n_constrained = 0;
+	for (int b : R.bone_order) {
+		FlatSegment &S = R.segments[R.seg_of_bone[b]];
+		BlobStep st;
+		memset(&st, 0, sizeof(st));
+		st.bone = R.t_of_bone[b];
+		st.parent = ik_parent[b] >= 0 ? R.t_of_bone[ik_parent[b]] : -1;
+		bool translate = S.parent_seg < 0;
+		st.flags = (translate ? STEP_TRANSLATE : 0) | (node_has_parent[b] ? STEP_NODE_PARENT : 0) | (ik_parent[b] >= 0 ? STEP_IK_PARENT : 0) |
+				(cons[b].present ? (STEP_SWING | STEP_TWIST) : 0) | (b == S.root_bone ? STEP_SEG_ROOT : 0) | (S.stabilize > 0 ? STEP_STABILIZE : 0);
+		st.eff_off = seg_eff_off[R.seg_of_bone[b]];
+		st.eff_cnt = (int)S.effectors.size();
+		st.cone_off = cone_off[b];
+		st.cone_cnt = cone_cnt[b];
+		st.n_headings = (int)S.weights.size();
+		// damp selection, src/ik_bone_segment_3d.cpp:217-237
+		float default_damp = translate ? (float)kPi : d->default_damp;
+		float damp = default_damp;
+		if (b < d->n_bone_damp) {
+			damp = translate ? (float)kPi : d->bone_damp[b];
+		}
+		if (default_damp < damp) {
+			damp = default_damp;
+		}
+		st.cos_half_damp = cos((double)damp / 2.0);
+		// refresh list: union of the paths bone -> effector bones (exclusive of `bone`), parents first
+		std::vector<char> mark(nb, 0);
+		for (int e : S.effectors) {
+			for (int x = e; x != b && x >= 0; x = ik_parent[x]) {
+				mark[x] = 1;
+			}
+		}
+		st.fk_off = (int)R.fk.size();
+		for (int t = 0; t < ns; t++) {
+			int x = R.topo[t];
+			if (mark[x]) {
+				R.fk.push_back(BlobFk{ (int16_t)t, (int16_t)R.t_of_bone[ik_parent[x]] });
+			}
+		}
+		st.fk_cnt = (int)R.fk.size() - st.fk_off;
+		R.steps.push_back(st);
+
+		// algorithmic flop floor, SURVEY.md section 8(d)
+		double A = 0;
+		for (int e : S.effectors) {
+			int a = 0;
+			for (int k = 0; k < 3; k++) {
+				a += R.pins[pin_of_bone[e]].direction_priorities[k] > 0.0 ? 1 : 0;
+			}
+			A += 16 + 39 * a;
+		}
+		double H = st.n_headings;
+		double fs = A + 34 * H + (translate ? 20 * H + 8 : 0) + 82 + 40 + 150 + (translate ? 3 : 0) + 63.0 * st.eff_cnt;
+		if ((st.flags & STEP_IK_PARENT) && cons[b].present) {
+			fs += 82 + 14.0 * st.cone_cnt + 400;
+			n_constrained++;
+		}
+		flops_iter += fs;
+	}
+	flops_iter += 63.0 * (ns + 3.0 * n_constrained + R.n_effectors);
+	R.flops_per_solve = flops_iter * std::max(0, R.iterations);
+
+	if (ns > 32767) {
+		R.error = "too many solved bones";
+		return MBIK_ERR_UNSUPPORTED;
+	}
+
+	// ---- assemble the blob ----
+	BlobHeader hdr;
+	memset(&hdr, 0, sizeof(hdr));
+	hdr.magic = 0x4B49424Du;
+	hdr.n_bones = nb;
+	hdr.n_solved = ns;
+	hdr.n_steps = (int)R.steps.size();
+	hdr.n_pins = (int)R.pins.size();
+	hdr.n_effs = (int)R.effs.size();
+	hdr.n_fk = (int)R.fk.size();
+	hdr.n_cones = (int)R.cones.size();
+	hdr.n_pass = (int)R.pass.size();
+	hdr.iterations = R.iterations;
+	hdr.constraint_mode = d->constraint_mode;
+	hdr.stabilization_passes = d->stabilization_passes;
+	R.blob.clear();
+	R.blob.resize(sizeof(BlobHeader), 0);
+	hdr.off_steps = append_section(R.blob, R.steps);
+	hdr.off_bones = append_section(R.blob, R.bones);
+	hdr.off_effs = append_section(R.blob, R.effs);
+	hdr.off_fk = append_section(R.blob, R.fk);
+	hdr.off_cones = append_section(R.blob, R.cones);
+	hdr.off_pass = append_section(R.blob, R.pass);
+	std::vector<float> rest(nb * 12);
+	memcpy(rest.data(), d->rest_local, sizeof(float) * 12 * nb);
+	hdr.off_rest = append_section(R.blob, rest);
+	while (R.blob.size() % 16) {
+		R.blob.push_back(0);
+	}
+	hdr.total_bytes = (uint32_t)R.blob.size();
+	memcpy(R.blob.data(), &hdr, sizeof(hdr));
+	return MBIK_OK;
+}
+
+} // namespace mbik

@@ -1,0 +1,61 @@
+// mbik_flatten.h -- host-side flattener: mbik_rig_desc -> topologically ordered SoA schedule (blob).
+//
+// Re-derives, on flat arrays, everything ManyBoneIK3D::_bone_list_changed() builds as an object graph
+// (reference src/many_bone_ik_3d.cpp:1011-1068): the segment tree, bone_list order, per-segment
+// effector lists and heading weights, bone-direction frames, kusudama cone/tangent geometry and twist
+// frames.  Runs once per rig on the host; no GPU needed.
+#pragma once
+#include "../../include/mbik.h"
+#include "mbik_blob.h"
+#include "mbik_math.cuh"
+
+#include <string>
+#include <vector>
+
+namespace mbik {
+
+struct FlatSegment {
+	int root_bone = -1, tip_bone = -1; // skeleton ids
+	int parent_seg = -1;
+	std::vector<int> bones;      // tip -> root (skeleton ids)
+	std::vector<int> child_segs; // kept children, ascending skeleton child order
+	bool pinned_descendants = false;
+	bool kept = true;
+	std::vector<int> effectors;  // skeleton ids of the effector bones, reference list order
+	std::vector<double> weights; // one per heading
+	int stabilize = 0;
+};
+
+struct FlatRig {
+	// inputs (copied)
+	int n_bones = 0;
+	std::vector<int> parent;
+	std::vector<X34> rest_local;
+	std::vector<mbik_pin_desc> pins;
+	// derived
+	std::vector<FlatSegment> segments;  // creation order; dropped ones have kept=false
+	std::vector<int> root_segments;
+	std::vector<int> bone_order;        // bone_list (skeleton ids)
+	std::vector<int> seg_of_bone;       // skeleton id -> owning kept segment or -1
+	std::vector<int> topo;              // t index -> skeleton id
+	std::vector<int> t_of_bone;         // skeleton id -> t index or -1
+	std::vector<BlobStep> steps;
+	std::vector<BlobBone> bones;        // t order
+	std::vector<BlobEff> effs;
+	std::vector<BlobFk> fk;
+	std::vector<BlobCone> cones;        // per constraint row order of appearance on solved bones
+	std::vector<int> cone_row_index;    // for mbik_rig_get_cone_geometry: desc cone index -> blob cone index or -1
+	std::vector<BlobPass> pass;
+	std::vector<unsigned char> blob;
+	int max_headings = 0;
+	int n_effectors = 0;
+	int n_kept_segments = 0;
+	int iterations = 15;
+	double flops_per_solve = 0;
+	std::string error;
+};
+
+// Returns MBIK_OK or a negative error code (message in out.error).
+int flatten_rig(const mbik_rig_desc *desc, FlatRig &out);
+
+} // namespace mbik

@@ -1,0 +1,27 @@
+// mbik_kernel.h -- launch interface of the solve kernel (mbik_kernel.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mbik {
+
+constexpr int kBlockThreads = 128; // poses per CTA
+
+struct SolveArgs {
+	const unsigned char *blob; // device copy of the rig blob (16-byte aligned)
+	uint32_t blob_bytes;
+	int32_t iterations;
+	size_t n_poses;
+	const float *targets;    // [n_poses][n_pins][12]
+	const float *start_pose; // [n_poses][n_bones][12] or nullptr
+	float *out_pose;         // [n_poses][n_bones][10]
+	float *out_local;        // [n_poses][n_bones][12] or nullptr
+	uint32_t *out_status;    // [n_poses] or nullptr
+};
+
+// solved-bone capacity of the kernel variant used for a rig with n_solved bones, or -1 if unsupported
+int kernel_capacity_for(int n_solved);
+cudaError_t launch_solve(const SolveArgs &args, int n_solved, cudaStream_t stream);
+
+} // namespace mbik

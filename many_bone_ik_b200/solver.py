@@ -1,0 +1,138 @@
+"""Thin Python binding of the C ABI (include/mbik.h) -- what tests and bench.py call.
+
+`BatchedIKRig` wraps an opaque `mbik_rig*`.  Host buffers are numpy arrays; device buffers are anything with a
+`data_ptr()` (torch CUDA tensors) or raw integer device pointers.  No compute happens in Python, and there
+is no fallback: every solve goes through libmbik.so's CUDA kernel or raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import MBIK_IO_DEVICE, MBIK_IO_HOST, RigInfo, SolveParams
+
+
+class MbikError(RuntimeError):
+    def __init__(self, code, where):
+        lib = _capi.load_library()
+        self.code = code
+        detail = lib.mbik_last_error().decode(errors="replace")
+        super().__init__(f"{where}: {lib.mbik_strerror(code).decode()} ({code}): {detail}")
+
+
+def device_count():
+    return int(_capi.load_library().mbik_device_count())
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data_as(C.c_void_p)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(int(x))
+
+
+class BatchedIKRig:
+    """One rig = one reference `ManyBoneIK3D` configuration after `_bone_list_changed()`."""
+
+    def __init__(self, rig):
+        self.lib = _capi.load_library()
+        self.rig = rig
+        desc, keep = _capi.rig_to_desc(rig)
+        h = C.c_void_p()
+        rc = self.lib.mbik_rig_create(C.byref(desc), C.byref(h))
+        if rc != 0:
+            raise MbikError(rc, "mbik_rig_create")
+        self.handle = h
+        info = RigInfo()
+        rc = self.lib.mbik_rig_get_info(self.handle, C.byref(info))
+        if rc != 0:
+            raise MbikError(rc, "mbik_rig_get_info")
+        self.info = {f[0]: getattr(info, f[0]) for f in RigInfo._fields_}
+        self.n_bones = rig.n_bones
+        self.n_pins = rig.n_pins
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mbik_rig_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- schedule facts (host only; no GPU needed) -------------------------------------------------
+    def bone_order(self):
+        out = np.zeros(self.info["n_solved"], np.int32)
+        self.lib.mbik_rig_get_bone_order(self.handle, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        return out
+
+    def step_weights(self, step):
+        buf = np.zeros(512, np.float64)
+        n = self.lib.mbik_rig_get_step_weights(self.handle, int(step), buf.ctypes.data_as(C.POINTER(C.c_double)), 512)
+        if n < 0:
+            raise MbikError(n, "mbik_rig_get_step_weights")
+        return buf[:n].copy()
+
+    def bone_frames(self):
+        n = self.info["n_solved"]
+        d = np.zeros((n, 9), np.float32)
+        t = np.zeros((n, 9), np.float32)
+        fp = C.POINTER(C.c_float)
+        self.lib.mbik_rig_get_bone_frames(self.handle, d.ctypes.data_as(fp), t.ctypes.data_as(fp))
+        return d, t
+
+    def cone_geometry(self):
+        nc = sum(len(c["cones"]) for c in self.rig.constraints)
+        out = np.zeros((max(nc, 1), 9), np.float32)
+        n = self.lib.mbik_rig_get_cone_geometry(self.handle, out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out[:max(n, 0)].copy()
+
+    # ---- the hot path -------------------------------------------------------------------------------
+    def solve(self, targets, start_pose=None, iterations=-1, device=-1, want_local=False, devices=None):
+        """Host-buffer solve.  targets [n, n_pins, 12] float32 -> out_pose [n, n_bones, 10]
+        (+ out_local [n, n_bones, 12]) + status [n].  `devices`: list of ordinals -> sharded multi-GPU call."""
+        targets = np.ascontiguousarray(targets, np.float32)
+        n = targets.shape[0]
+        if targets.shape != (n, self.n_pins, 12):
+            raise ValueError(f"targets must be [n, {self.n_pins}, 12]")
+        if start_pose is not None:
+            start_pose = np.ascontiguousarray(start_pose, np.float32)
+            if start_pose.shape != (n, self.n_bones, 12):
+                raise ValueError(f"start_pose must be [n, {self.n_bones}, 12]")
+        out = np.empty((n, self.n_bones, 10), np.float32)
+        loc = np.empty((n, self.n_bones, 12), np.float32) if want_local else None
+        st = np.zeros(n, np.uint32)
+        p = SolveParams(int(iterations), int(device), MBIK_IO_HOST, None)
+        if devices is None:
+            rc = self.lib.mbik_solve_batch(self.handle, C.byref(p), n, _ptr(targets), _ptr(start_pose), _ptr(out), _ptr(loc), _ptr(st))
+        else:
+            devs = np.ascontiguousarray(devices, np.int32)
+            rc = self.lib.mbik_solve_batch_multi(self.handle, C.byref(p), n, _ptr(targets), _ptr(start_pose), _ptr(out), _ptr(loc), _ptr(st),
+                                                 devs.ctypes.data_as(C.POINTER(C.c_int32)), int(devs.shape[0]))
+        if rc != 0:
+            raise MbikError(rc, "mbik_solve_batch")
+        return (out, loc, st) if want_local else (out, st)
+
+    def solve_raw(self, n_poses, targets, out_pose, start_pose=None, out_local=None, out_status=None, iterations=-1,
+                  device=-1, flags=MBIK_IO_HOST, stream=None):
+        """Zero-copy call: pointers (numpy / torch tensors / ints) are passed straight through.
+        With flags=MBIK_IO_DEVICE the launch is asynchronous on `stream`."""
+        p = SolveParams(int(iterations), int(device), int(flags), C.c_void_p(int(stream)) if stream else None)
+        rc = self.lib.mbik_solve_batch(self.handle, C.byref(p), int(n_poses), _ptr(targets), _ptr(start_pose), _ptr(out_pose),
+                                       _ptr(out_local), _ptr(out_status))
+        if rc != 0:
+            raise MbikError(rc, "mbik_solve_batch")
+
+    def last_kernel_ms(self, device=0):
+        ms = C.c_float(0)
+        rc = self.lib.mbik_last_kernel_ms(self.handle, int(device), C.byref(ms))
+        if rc != 0:
+            raise MbikError(rc, "mbik_last_kernel_ms")
+        return float(ms.value)
