@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched ManyBoneIK solve loop (see the contract in DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], which also covers N=1): the `humanoid22` rig (22 bones, 5 pinned effectors,
+kusudama open-cone + twist limits on the 19 non-root solved bones, 10 iterations), 2^20 independent poses with
+seeded random effector targets, sharded contiguously over the N ranks (strong scaling, no collective in the
+solve).  One "step" = one pass of the hot path over the rank's shard.
+
+  value : skeleton-solves/s with inputs already resident in HBM (device-resident I/O, CUDA-event timed)
+  e2e   : the same through the C ABI with pinned HOST buffers, H2D + D2H inside the timed region
+  roofline / cpu_baseline / latency_p50_ms_4096 : see DESIGN.md "Measurement"
+
+`--impl reference` times the reference's CPU algorithm (the line-cited restatement under oracle/, the only
+runnable form of the reference in this image) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOTAL_POSES = 1 << 20
+LATENCY_BATCH = 4096
+METRIC = "ik_skeleton_solves_per_sec"
+UNIT = "solves/s"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "humanoid22 (22 bones, 5 effectors, 32 kusudama cones + twist, 10 iterations), 2^20 random-target poses "
+                    "(BASELINE configs[2]; the 1-GPU run solves all 2^20)",
+        "rig": "humanoid22", "iterations": 10, "total_poses": TOTAL_POSES, "poses_per_gpu": TOTAL_POSES // n_gpus,
+        "parallelism": f"dp{n_gpus} (contiguous pose shards, no collective)",
+        "cache": "inputs (252 MB targets) and outputs (923 MB) are larger than the 126 MB L2",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference (oracle) timing -- the ONLY place bench.py touches oracle/
+# --------------------------------------------------------------------------------------------------
+def time_cpu_reference(rig, budget_s=12.0, steps=1, warmup=0):
+    from many_bone_ik_b200 import rigs
+    from oracle import oracle_py as O
+    O.build()
+    cores = O.hardware_threads()
+    probe = max(cores * 8, 64)
+    T = rigs.random_targets(rig, 0, probe)
+    t0 = time.perf_counter()
+    O.solve_batch(rig, T, threads=cores)
+    rate = probe / max(time.perf_counter() - t0, 1e-6)
+    n = int(max(probe, min(rate * budget_s / max(steps + warmup, 1), 1 << 18)))
+    T = rigs.random_targets(rig, 0, n)
+    for _ in range(warmup):
+        O.solve_batch(rig, T, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.solve_batch(rig, T, threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} poses x {steps} pass(es) of the same workload, oracle restatement, all {cores} host threads, {dt:.1f} s"}, dt / steps * 1e3
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from many_bone_ik_b200 import rigs
+    rig = rigs.humanoid22()
+    cb, ms = time_cpu_reference(rig, budget_s=20.0, steps=max(args.steps, 1), warmup=max(min(args.warmup, 1), 0))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = line-cited CPU restatement of the reference solver (oracle/); the Godot module itself cannot be built here",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mbik", choices=["mbik", "reference"])
+    ap.add_argument("--poses", type=int, default=TOTAL_POSES, help="total poses (default 2^20); smaller values are for debugging only")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    from many_bone_ik_b200 import BatchedIKRig, rigs
+    from many_bone_ik_b200._capi import MBIK_IO_DEVICE, MBIK_IO_HOST
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: many_bone_ik_b200 has no CPU fallback")
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rig = rigs.humanoid22()
+    R = BatchedIKRig(rig)
+    total = args.poses
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    n = hi - lo
+    nb, npins = rig.n_bones, rig.n_pins
+
+    # synthetic inputs: this rank's slice, regenerated independently from the counter-based RNG
+    t_host = torch.empty((n, npins, 12), dtype=torch.float32, pin_memory=True)
+    CH = 1 << 16
+    for s in range(0, n, CH):
+        e = min(n, s + CH)
+        t_host[s:e] = torch.from_numpy(rigs.random_targets(rig, lo + s, e - s))
+    o_host = torch.empty((n, nb, 10), dtype=torch.float32, pin_memory=True)
+    t_dev = t_host.to(dev)
+    o_dev = torch.empty((n, nb, 10), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        R.solve_raw(n, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+
+    def step_host():
+        R.solve_raw(n, t_host.numpy(), o_host.numpy(), device=local_rank, flags=MBIK_IO_HOST)
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+        # per-launch kernel time from the library's own event pair on the launching stream (read after sync below)
+    ev1.record()
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    barrier()
+    # average kernel duration: time K more launches individually (same stream, same inputs)
+    for _ in range(min(args.steps, 5)):
+        step_device()
+        torch.cuda.synchronize()
+        kernel_ms.append(R.last_kernel_ms(local_rank))
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = max_over_ranks(dev_ms)
+    value = total * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (e2e) ----
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = total * args.steps / e2e_s
+
+    # correctness guard on a small sample of what was just computed (device path == host path, finite)
+    chk = min(n, 1024)
+    same = bool(torch.equal(o_dev[:chk].cpu(), o_host[:chk]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- p50 latency of a 4096-pose batch, device-resident (BASELINE configs[1]) ----
+    lt = t_dev[:LATENCY_BATCH].contiguous()
+    lo_ = torch.empty((LATENCY_BATCH, nb, 10), dtype=torch.float32, device=dev)
+    lat = []
+    for i in range(220):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        R.solve_raw(LATENCY_BATCH, lt, lo_, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 20:
+            lat.append(a.elapsed_time(b))
+    p50 = float(np.median(lat))
+
+    # ---- roofline of the one kernel (FP32 CUDA cores; HBM shown as the sanity figure) ----
+    import ctypes as C
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf = C.c_double(0)
+    R.lib.mbik_measure_fp32_tflops(local_rank, 5, C.byref(tf))
+    k_ms = float(np.mean(kernel_ms))
+    flops = R.info["flops_per_solve"]
+    bytes_per_solve = npins * 48 + nb * 40
+    ach_tf = flops * n / (k_ms * 1e-3) / 1e12
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {
+        "bound": "fp32", "kernel": "mbik_solve_kernel<24>", "achieved": ach_tf, "peak": float(tf.value), "unit": "TFLOP/s",
+        "frac": ach_tf / float(tf.value) if tf.value else None, "traffic": None,
+        "peak_source": "FP32 FMA micro-benchmark run in this process (mbik_measure_fp32_tflops)",
+        "flops_per_solve": flops, "kernel_ms": k_ms,
+        "note": "algorithmic flop floor of SURVEY 8(d); the kernel issues separately rounded FMUL/FADD (bit-exact parity), so 50% of the FMA peak is its structural ceiling",
+        "hbm": {"bound": "hbm", "achieved": bytes_per_solve * n / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_per_solve * n / (k_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_solve": bytes_per_solve,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"},
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu_baseline, _ = time_cpu_reference(rig, budget_s=12.0)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * npins * 48) * world, "d2h_bytes_per_step": int(n * nb * 40) * world,
+                "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": args.steps * world,
+        "latency_p50_ms_4096": p50,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "clocks": clocks,
+        "device_equals_host_path": same,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

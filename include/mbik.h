@@ -161,6 +161,10 @@ void mbik_free_pinned(void *p);
  * (cudaEvent pair recorded on the launching stream around the solve kernel). */
 int mbik_last_kernel_ms(mbik_rig *rig, int32_t device, float *out_ms);
 
+/* Bench helper (not on the solve path): best-of-`reps` FP32 FMA throughput of `device` in TFLOP/s, the measured
+ * denominator of the kernel's FP32 roofline. */
+int mbik_measure_fp32_tflops(int32_t device, int32_t reps, double *out_tflops);
+
 #ifdef __cplusplus
 }
 #endif
