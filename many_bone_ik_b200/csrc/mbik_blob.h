@@ -61,7 +61,7 @@ struct BlobEff { // one entry per (segment, effector); 64 bytes
 	int32_t pad[2];
 };
 
-struct BlobFk { // G[child] = G[parent] * L[child]
+struct BlobFk { // G[child] = G[parent] * L[child]; bit 15 of child = "store the result" (see mbik_flatten.cu)
 	int16_t child, parent;
 };
 

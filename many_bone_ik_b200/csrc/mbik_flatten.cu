@@ -757,6 +757,18 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 			}
 		}
 		st.fk_cnt = (int)R.fk.size() - st.fk_off;
+		// bit 15 of `child`: the kernel must write this global back to its cache because it is read again --
+		// as an effector frame of this step, or as the parent of a later, non-consecutive refresh op
+		for (int k = st.fk_off; k < st.fk_off + st.fk_cnt; k++) {
+			int child_t = R.fk[k].child;
+			bool needed = std::find(S.effectors.begin(), S.effectors.end(), R.topo[child_t]) != S.effectors.end();
+			for (int j = k + 2; j < st.fk_off + st.fk_cnt && !needed; j++) {
+				needed = R.fk[j].parent == child_t;
+			}
+			if (needed) {
+				R.fk[k].child = (int16_t)(child_t | 0x8000);
+			}
+		}
 		R.steps.push_back(st);
 
 		// algorithmic flop floor, SURVEY.md section 8(d)
@@ -779,7 +791,7 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	flops_iter += 63.0 * (ns + 3.0 * n_constrained + R.n_effectors);
 	R.flops_per_solve = flops_iter * std::max(0, R.iterations);
 
-	if (ns > 32767) {
+	if (ns > 16383) {
 		R.error = "too many solved bones";
 		return MBIK_ERR_UNSUPPORTED;
 	}

@@ -138,7 +138,7 @@ __device__ __forceinline__ void qcp_accumulate(QcpSums &s, V3 target, V3 moved, 
 	s.zz = r_add(s.zz, (double)r_mul(wc1.z, moved.z));
 }
 // calculate_rotation, general branch (:80-123)
-__device__ __noinline__ Q4 qcp_rotation(const QcpSums &s) {
+__device__ __forceinline__ Q4 qcp_rotation(const QcpSums &s) {
 	double max_eig = r_mul(r_add(s.ss1, s.ss2), 0.5);
 	double xz_p_zx = r_add(s.xz, s.zx), yz_p_zy = r_add(s.yz, s.zy), xy_p_yx = r_add(s.xy, s.yx);
 	double yz_m_zy = r_sub(s.yz, s.zy), xz_m_zx = r_sub(s.xz, s.zx), xy_m_yx = r_sub(s.xy, s.yx);
@@ -188,7 +188,7 @@ __device__ __noinline__ Q4 qcp_rotation(const QcpSums &s) {
 	return q_normalized(q4((float)qx, (float)qy, (float)qz, (float)qw));
 }
 // calculate_rotation, single-heading branch (:59-78)
-__device__ __noinline__ Q4 qcp_rotation_single(V3 u /*moved*/, V3 v /*target*/) {
+__device__ __forceinline__ Q4 qcp_rotation_single(V3 u /*moved*/, V3 v /*target*/) {
 	double norm_product = (double)r_mul(vlen(u), vlen(v));
 	if (norm_product == 0.0) {
 		return q4(0.0f, 0.0f, 0.0f, 1.0f);
@@ -208,7 +208,7 @@ __device__ __noinline__ Q4 qcp_rotation_single(V3 u /*moved*/, V3 v /*target*/) 
 // kusudama swing limit (src/ik_kusudama_3d.cpp:273-332, src/ik_open_cone_3d.cpp:285-381)
 // returns the point to aim at; in_bounds < 0 means the input was outside the limits
 // ---------------------------------------------------------------------------------------------------
-__device__ __noinline__ V3 point_in_limits(V3 in_point, const BlobCone *cones, int n_cones, float &in_bounds) {
+__device__ __forceinline__ V3 point_in_limits(V3 in_point, const BlobCone *cones, int n_cones, float &in_bounds) {
 	V3 point = vnorm(in_point);
 	float closest_cos = -2.0f;
 	in_bounds = -1.0f;
@@ -287,7 +287,7 @@ __device__ __noinline__ V3 point_in_limits(V3 in_point, const BlobCone *cones, i
 
 // IKKusudama3D::get_swing_twist about +Y followed by the twist clamp and recomposition
 // (src/ik_kusudama_3d.cpp:117-158); returns the new LOCAL basis of the bone
-__device__ __noinline__ M3 twist_snap(const M3 &Pb, const M3 &Pinv, const M3 &Lb, const M3 &twist_basis, const M3 &twist_center, float twist_cos) {
+__device__ __forceinline__ M3 twist_snap(const M3 &Pb, const M3 &Pinv, const M3 &Lb, const M3 &twist_basis, const M3 &twist_center, float twist_cos) {
 	M3 ctw = m3_mul(Pb, twist_basis); // global basis of the twist-axes node
 	M3 gts = m3_mul(Pb, Lb);          // global basis of the bone
 	M3 gtc = m3_mul(ctw, twist_center);
@@ -312,7 +312,7 @@ __device__ __noinline__ M3 twist_snap(const M3 &Pb, const M3 &Pinv, const M3 &Lb
 
 // damping clamp + the (numerically no-op) slerp toward the current global basis with weight 0
 // (src/ik_bone_segment_3d.cpp:143-151)
-__device__ __noinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const M3 &Gb) {
+__device__ __forceinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const M3 &Gb) {
 	M3 rot = m3_from_quat(q);
 	Q4 cq = clamp_to_cos_half_angle(m3_get_rotation_quat(rot), cos_half_damp);
 	M3 R1 = m3_from_quat(cq);
@@ -340,7 +340,7 @@ __device__ __noinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const M3 
 }
 
 // IKBone3D::set_skeleton_bone_pose (src/ik_bone_3d.cpp:170-179): position, rotation quaternion, scale
-__device__ __noinline__ uint32_t write_bone_pose(const X34 &local, float *out10) {
+__device__ __forceinline__ uint32_t write_bone_pose(const X34 &local, float *out10) {
 	uint32_t st = 0;
 	M3 b = local.b;
 	if (!m3_is_finite(b)) {
@@ -362,7 +362,7 @@ __device__ __noinline__ uint32_t write_bone_pose(const X34 &local, float *out10)
 // the kernel
 // ---------------------------------------------------------------------------------------------------
 template <int NB>
-__global__ void __launch_bounds__(kBlockThreads) mbik_solve_kernel(SolveArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, 1) mbik_solve_kernel(SolveArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t bar;
 
@@ -393,10 +393,11 @@ __global__ void __launch_bounds__(kBlockThreads) mbik_solve_kernel(SolveArgs a) 
 	const BlobPass *pass = reinterpret_cast<const BlobPass *>(smem + H.off_pass);
 	const float *rest = reinterpret_cast<const float *>(smem + H.off_rest);
 
-	const size_t pose = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (pose >= a.n_poses) {
-		return;
-	}
+	// Every thread stays alive for the whole kernel (CTA-wide barriers below); threads past the end of the
+	// batch redo the last pose and skip the stores.
+	const size_t pose_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = pose_raw < a.n_poses;
+	const size_t pose = live ? pose_raw : a.n_poses - 1;
 	const int ns = H.n_solved;
 	const int n_steps = H.n_steps;
 	const int n_bones = H.n_bones;
@@ -433,6 +434,10 @@ __global__ void __launch_bounds__(kBlockThreads) mbik_solve_kernel(SolveArgs a) 
 		}
 
 		for (int s = 0; s < n_steps; s++) {
+			// Keep the CTA's warps in lockstep at bone-step granularity: the step body is ~75 KB of straight-line
+			// SASS, far more than the instruction cache holds, so warps that drift apart each stream it from L2
+			// on their own (ncu: 60% of stall samples were stall_no_inst before this barrier).
+			__syncthreads();
 			const BlobStep &S = steps[s];
 			const int b = S.bone;
 			const uint32_t flags = S.flags;
@@ -444,9 +449,21 @@ __global__ void __launch_bounds__(kBlockThreads) mbik_solve_kernel(SolveArgs a) 
 			X34 Gb = node_parent ? x_mul(P, Lb) : Lb;
 			st_x34(G, b, Gb);
 			// refresh the globals on the paths down to this segment's effectors
-			for (int k = 0; k < S.fk_cnt; k++) {
-				BlobFk op = fk[S.fk_off + k];
-				st_x34(G, op.child, x_mul(ld_x34(G, op.parent), ld_x34(L, op.child)));
+			{
+				X34 run = Gb; // running product: most refresh lists are chains, so the parent is usually in registers
+				int run_node = b;
+				for (int k = 0; k < S.fk_cnt; k++) {
+					const BlobFk op = fk[S.fk_off + k];
+					const int child = op.child & 0x7fff;
+					if (op.parent != run_node) {
+						run = ld_x34(G, op.parent);
+					}
+					run = x_mul(run, ld_x34(L, child));
+					run_node = child;
+					if (op.child & 0x8000) { // read again later: an effector's bone or a branch point
+						st_x34(G, child, run);
+					}
+				}
 			}
 			M3 Pinv = m3_identity();
 			if (node_parent) {
@@ -582,23 +599,25 @@ __global__ void __launch_bounds__(kBlockThreads) mbik_solve_kernel(SolveArgs a) 
 	uint32_t status = 0;
 	float *my_out = a.out_pose + pose * (size_t)n_bones * 10;
 	float *my_loc = a.out_local ? a.out_local + pose * (size_t)n_bones * 12 : nullptr;
-	for (int t = 0; t < ns; t++) {
-		int sb = bones[t].skel_bone;
-		X34 l = ld_x34(L, t);
-		status |= write_bone_pose(l, my_out + (size_t)sb * 10);
-		if (my_loc) {
-			st_x34(my_loc, sb, l);
+	if (live) {
+		for (int t = 0; t < ns; t++) {
+			int sb = bones[t].skel_bone;
+			X34 l = ld_x34(L, t);
+			status |= write_bone_pose(l, my_out + (size_t)sb * 10);
+			if (my_loc) {
+				st_x34(my_loc, sb, l);
+			}
+		}
+		for (int k = 0; k < H.n_pass; k++) {
+			int sb = pass[k].skel_bone;
+			X34 l = my_start ? ldg_x34(my_start + (size_t)sb * 12) : ld_x34(rest, sb);
+			status |= write_bone_pose(l, my_out + (size_t)sb * 10);
+			if (my_loc) {
+				st_x34(my_loc, sb, l);
+			}
 		}
 	}
-	for (int k = 0; k < H.n_pass; k++) {
-		int sb = pass[k].skel_bone;
-		X34 l = my_start ? ldg_x34(my_start + (size_t)sb * 12) : ld_x34(rest, sb);
-		status |= write_bone_pose(l, my_out + (size_t)sb * 10);
-		if (my_loc) {
-			st_x34(my_loc, sb, l);
-		}
-	}
-	if (a.out_status) {
+	if (a.out_status && live) {
 		a.out_status[pose] = status;
 	}
 }

@@ -6,7 +6,7 @@
 
 namespace mbik {
 
-constexpr int kBlockThreads = 128; // poses per CTA
+constexpr int kBlockThreads = 384; // poses per CTA: one CTA per SM, all of its warps kept in lockstep
 
 struct SolveArgs {
 	const unsigned char *blob; // device copy of the rig blob (16-byte aligned)
