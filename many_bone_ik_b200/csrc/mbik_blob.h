@@ -3,9 +3,10 @@
 // One contiguous, 16-byte aligned blob of rig constants.  The kernel stages it into shared memory
 // with one TMA bulk copy per CTA; every lane then reads the same words (broadcast).  Layout:
 //   BlobHeader | BlobStep[n_steps] | BlobBone[n_solved] | BlobEff[n_effs] | BlobFk[n_fk] |
-//   BlobCone[n_cones] | BlobPass[n_pass] | rest_local[n_bones*12]
-// Solved bones are renumbered in topological order ("t index": parents before children) so that the
-// per-iteration FK refresh is a linear pass.
+//   BlobCone[n_cones] | BlobPass[n_pass] | chain[n_chain] (int16) | rest_local[n_bones*12]
+// Solved bones are renumbered in depth-first preorder ("t index": parents before children, children in
+// the reference's ascending order), which is also the order in which a segment's effector list
+// enumerates its effectors.
 #pragma once
 #include <stdint.h>
 
@@ -19,25 +20,32 @@ enum : uint32_t {
 	STEP_TWIST = 16u,       // kusudama axially constrained
 	STEP_SEG_ROOT = 32u,    // bone == segment root (previous_deviation reset, :178-180)
 	STEP_STABILIZE = 64u,   // segment runs the stabilisation loop (root segments only, many_bone_ik_3d.cpp:1021)
+	STEP_SEG_FIRST = 128u,  // first step of its segment (the tip): (re)build the segment's parent-global chain
+	STEP_SELF_EFF = 256u,   // the solved bone is itself the first effector of the list (pinned segment tip)
+	STEP_PUSH_SELF = 512u,  // the solved bone is a branch point of its walk: its global goes to stack slot 0
 };
 
 struct BlobHeader {
 	uint32_t magic;       // 'MBIK'
 	uint32_t total_bytes; // multiple of 16
 	int32_t n_bones, n_solved, n_steps, n_pins, n_effs, n_fk, n_cones, n_pass;
-	int32_t iterations, constraint_mode, stabilization_passes, reserved0;
-	uint32_t off_steps, off_bones, off_effs, off_fk, off_cones, off_pass, off_rest, reserved1;
+	int32_t iterations, constraint_mode, stabilization_passes, n_chain;
+	int32_t max_seg_len, max_stack, reserved0, reserved1;
+	uint32_t off_steps, off_bones, off_effs, off_fk, off_cones, off_pass, off_rest, off_chain;
 };
 
-struct BlobStep { // 48 bytes
+struct BlobStep { // 64 bytes
 	int32_t bone;    // t index
 	int32_t parent;  // t index of the IK parent, -1 for a skeleton root
 	uint32_t flags;
 	int32_t eff_off, eff_cnt;   // the owning segment's effector list
-	int32_t fk_off, fk_cnt;     // transforms to refresh below `bone` before headings are built
+	int32_t fk_off, fk_cnt;     // walk below `bone` that visits this segment's effector bones in list order
 	int32_t cone_off, cone_cnt; // the bone's kusudama cones
 	int32_t n_headings;
 	double cos_half_damp;       // cos(damp / 2.0), damp per src/ik_bone_segment_3d.cpp:229-237
+	int32_t pslot;              // slot of the segment chain buffer holding the global of this bone's parent
+	int32_t chain_off, chain_cnt; // STEP_SEG_FIRST: t indices skeleton-root .. parent(tip); the last seg_len are kept
+	int32_t seg_len;
 };
 
 struct BlobBone { // per solved bone, t order; 160 bytes
@@ -61,8 +69,15 @@ struct BlobEff { // one entry per (segment, effector); 64 bytes
 	int32_t pad[2];
 };
 
-struct BlobFk { // G[child] = G[parent] * L[child]; bit 15 of child = "store the result" (see mbik_flatten.cu)
-	int16_t child, parent;
+// One step of the depth-first walk from the solved bone down to the effectors of its segment's list:
+//   run = (src_slot >= 0 ? stack[src_slot] : run) * L[child];  if (push_slot >= 0) stack[push_slot] = run;
+//   if (eff >= 0) the headings of effector eff_off + eff are built from `run`.
+// A chain needs no stack at all; a branch point is pushed once and re-read for each further child.
+struct BlobFk { // 8 bytes
+	int16_t child;
+	int8_t src_slot, push_slot;
+	int16_t eff;
+	int16_t pad;
 };
 
 struct BlobCone { // 160 bytes
@@ -86,7 +101,8 @@ struct BlobPass { // skeleton bones outside bone_list: copied through to the out
 	int32_t skel_bone;
 };
 
-static_assert(sizeof(BlobStep) == 48, "BlobStep layout");
+static_assert(sizeof(BlobStep) == 64, "BlobStep layout");
+static_assert(sizeof(BlobFk) == 8, "BlobFk layout");
 static_assert(sizeof(BlobBone) == 160, "BlobBone layout");
 static_assert(sizeof(BlobEff) == 64, "BlobEff layout");
 static_assert(sizeof(BlobCone) == 160, "BlobCone layout");

@@ -46,6 +46,7 @@ struct DeviceState {
 struct mbik_rig {
 	mbik::FlatRig flat;
 	int n_solved = 0;
+	int variant = -1;
 	std::mutex mu;
 	std::map<int, DeviceState> devices;
 };
@@ -177,7 +178,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 		a.out_local = out_local;
 		a.out_status = out_status;
 		cudaEventRecord(ds->ev_start, user_stream);
-		e = mbik::launch_solve(a, rig->n_solved, user_stream);
+		e = mbik::launch_solve(a, rig->variant, user_stream);
 		cudaEventRecord(ds->ev_stop, user_stream);
 		ds->timed = true;
 		if (e != cudaSuccess) {
@@ -209,7 +210,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 	a.out_local = out_local ? ds->d_local : nullptr;
 	a.out_status = out_status ? ds->d_status : nullptr;
 	cudaEventRecord(ds->ev_start, st);
-	e = mbik::launch_solve(a, rig->n_solved, st);
+	e = mbik::launch_solve(a, rig->variant, st);
 	cudaEventRecord(ds->ev_stop, st);
 	ds->timed = true;
 	if (e != cudaSuccess) {
@@ -287,9 +288,10 @@ int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
 		return fail(rc, msg);
 	}
 	rig->n_solved = (int)rig->flat.bone_order.size();
-	if (mbik::kernel_capacity_for(rig->n_solved) < 0) {
+	rig->variant = mbik::kernel_variant_for(rig->n_solved, rig->flat.max_seg_len, rig->flat.max_stack);
+	if (rig->variant < 0) {
 		delete rig;
-		return fail(MBIK_ERR_UNSUPPORTED, "rig has more solved bones than the largest kernel variant (128)");
+		return fail(MBIK_ERR_UNSUPPORTED, "rig exceeds the largest kernel variant (128 solved bones, walk stack depth 16)");
 	}
 	if (desc->stabilization_passes > 0) {
 		delete rig;
@@ -328,7 +330,7 @@ int mbik_rig_get_info(const mbik_rig *rig, mbik_rig_info *o) {
 	o->max_headings = F.max_headings;
 	o->n_cones = (int)F.cones.size();
 	o->iterations = F.iterations;
-	o->kernel_capacity = mbik::kernel_capacity_for(rig->n_solved);
+	o->kernel_capacity = mbik::kernel_capacity_of_variant(rig->variant);
 	o->rig_blob_bytes = (int64_t)F.blob.size();
 	o->flops_per_solve = F.flops_per_solve;
 	return MBIK_OK;

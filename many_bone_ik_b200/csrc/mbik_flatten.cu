@@ -742,31 +742,105 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 			damp = default_damp;
 		}
 		st.cos_half_damp = cos((double)damp / 2.0);
-		// refresh list: union of the paths bone -> effector bones (exclusive of `bone`), parents first
+		// Walk below `bone`: union of the paths bone -> effector bones (exclusive of `bone`) in depth-first
+		// preorder (= t order).  Effector bones are met in the order of the reference's effector list, so the
+		// kernel can build headings on the fly; globals are kept only at branch points (a small stack).
 		std::vector<char> mark(nb, 0);
 		for (int e : S.effectors) {
 			for (int x = e; x != b && x >= 0; x = ik_parent[x]) {
 				mark[x] = 1;
 			}
 		}
-		st.fk_off = (int)R.fk.size();
-		for (int t = 0; t < ns; t++) {
-			int x = R.topo[t];
+		std::vector<int> marked_children(nb, 0);
+		for (int x = 0; x < nb; x++) {
 			if (mark[x]) {
-				R.fk.push_back(BlobFk{ (int16_t)t, (int16_t)R.t_of_bone[ik_parent[x]] });
+				marked_children[ik_parent[x]]++;
+			}
+		}
+		st.fk_off = (int)R.fk.size();
+		{
+			std::vector<int> slot_of(nb, -1); // stack slot holding the global of a branch point
+			int depth = 0;                    // slots in use
+			int prev = b;                     // bone whose global is in the running register
+			int next_eff = 0;
+			if (!S.effectors.empty() && S.effectors[0] == b) {
+				st.flags |= STEP_SELF_EFF;
+				next_eff = 1;
+			}
+			std::vector<int> open_branch; // branch points currently on the stack, innermost last
+			// the start bone is a branch point too when it has >= 2 marked children: it lives in slot 0
+			if (marked_children[b] >= 2) {
+				slot_of[b] = depth++; // pushed by the kernel before the walk
+				open_branch.push_back(b);
+				st.flags |= STEP_PUSH_SELF;
+			}
+			for (int t = 0; t < ns; t++) {
+				int x = R.topo[t];
+				if (!mark[x]) {
+					continue;
+				}
+				int par = ik_parent[x];
+				BlobFk op;
+				memset(&op, 0, sizeof(op));
+				op.child = (int16_t)t;
+				op.src_slot = -1;
+				op.push_slot = -1;
+				op.eff = -1;
+				if (par != prev) {
+					// returning to a branch point: everything pushed below it is dead
+					while (!open_branch.empty() && open_branch.back() != par) {
+						slot_of[open_branch.back()] = -1;
+						open_branch.pop_back();
+						depth--;
+					}
+					if (open_branch.empty() || slot_of[par] < 0) {
+						R.error = "internal: walk returned to a bone that is not on the branch stack";
+						return MBIK_ERR_UNSUPPORTED;
+					}
+					op.src_slot = (int8_t)slot_of[par];
+				}
+				if (marked_children[x] >= 2) {
+					slot_of[x] = depth++;
+					open_branch.push_back(x);
+					op.push_slot = (int8_t)slot_of[x];
+					if (depth > 100) {
+						R.error = "walk stack too deep";
+						return MBIK_ERR_UNSUPPORTED;
+					}
+				}
+				R.max_stack = std::max(R.max_stack, depth);
+				if (next_eff < (int)S.effectors.size() && S.effectors[next_eff] == x) {
+					op.eff = (int16_t)next_eff++;
+				}
+				prev = x;
+				R.fk.push_back(op);
+			}
+			R.max_stack = std::max(R.max_stack, depth);
+			if (next_eff != (int)S.effectors.size()) {
+				R.error = "internal: effector list is not in depth-first order";
+				return MBIK_ERR_UNSUPPORTED;
 			}
 		}
 		st.fk_cnt = (int)R.fk.size() - st.fk_off;
-		// bit 15 of `child`: the kernel must write this global back to its cache because it is read again --
-		// as an effector frame of this step, or as the parent of a later, non-consecutive refresh op
-		for (int k = st.fk_off; k < st.fk_off + st.fk_cnt; k++) {
-			int child_t = R.fk[k].child;
-			bool needed = std::find(S.effectors.begin(), S.effectors.end(), R.topo[child_t]) != S.effectors.end();
-			for (int j = k + 2; j < st.fk_off + st.fk_cnt && !needed; j++) {
-				needed = R.fk[j].parent == child_t;
-			}
-			if (needed) {
-				R.fk[k].child = (int16_t)(child_t | 0x8000);
+		// segment chain: the globals of the parents of this segment's bones, rebuilt at the segment's first step
+		{
+			int seg_len = (int)S.bones.size();
+			st.seg_len = seg_len;
+			R.max_seg_len = std::max(R.max_seg_len, seg_len);
+			// position of b in the segment counted from the root end
+			int pos_from_tip = (int)(std::find(S.bones.begin(), S.bones.end(), b) - S.bones.begin());
+			st.pslot = seg_len - 1 - pos_from_tip;
+			if (b == S.tip_bone) {
+				st.flags |= STEP_SEG_FIRST;
+				std::vector<int> up;
+				for (int x = ik_parent[S.tip_bone]; x >= 0; x = ik_parent[x]) {
+					up.push_back(x);
+				}
+				st.chain_off = (int)R.chain.size();
+				for (auto it2 = up.rbegin(); it2 != up.rend(); ++it2) {
+					R.chain.push_back((int16_t)R.t_of_bone[*it2]);
+				}
+				st.chain_cnt = (int)up.size();
 			}
 		}
 		R.steps.push_back(st);
@@ -811,6 +885,9 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	hdr.iterations = R.iterations;
 	hdr.constraint_mode = d->constraint_mode;
 	hdr.stabilization_passes = d->stabilization_passes;
+	hdr.n_chain = (int)R.chain.size();
+	hdr.max_seg_len = R.max_seg_len;
+	hdr.max_stack = R.max_stack;
 	R.blob.clear();
 	R.blob.resize(sizeof(BlobHeader), 0);
 	hdr.off_steps = append_section(R.blob, R.steps);
@@ -819,6 +896,7 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	hdr.off_fk = append_section(R.blob, R.fk);
 	hdr.off_cones = append_section(R.blob, R.cones);
 	hdr.off_pass = append_section(R.blob, R.pass);
+	hdr.off_chain = append_section(R.blob, R.chain);
 	std::vector<float> rest(nb * 12);
 	memcpy(rest.data(), d->rest_local, sizeof(float) * 12 * nb);
 	hdr.off_rest = append_section(R.blob, rest);

@@ -43,6 +43,8 @@ struct FlatRig {
 	std::vector<BlobBone> bones;        // t order
 	std::vector<BlobEff> effs;
 	std::vector<BlobFk> fk;
+	std::vector<int16_t> chain;
+	int max_seg_len = 0, max_stack = 0;
 	std::vector<BlobCone> cones;        // per constraint row order of appearance on solved bones
 	std::vector<int> cone_row_index;    // for mbik_rig_get_cone_geometry: desc cone index -> blob cone index or -1
 	std::vector<BlobPass> pass;

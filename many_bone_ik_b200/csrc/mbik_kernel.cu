@@ -359,9 +359,67 @@ __device__ __forceinline__ uint32_t write_bone_pose(const X34 &local, float *out
 }
 
 // ---------------------------------------------------------------------------------------------------
+// headings of one effector (src/ik_effector_3d.cpp:90-149) folded straight into the QCP accumulators
+// ---------------------------------------------------------------------------------------------------
+struct HeadingAcc {
+	QcpSums sums;
+	double total_w;       // pass 0: sum of weights
+	V3 csum_m, csum_t;    // pass 0: weighted sums of the tip / target headings
+	V3 neg_mc, neg_tc;    // pass 1 when translating: -centroids
+	V3 last_t, last_m;    // the single heading of a 1-heading list
+};
+
+__device__ __forceinline__ void heading_emit(HeadingAcc &A, int pass_i, bool translate, V3 th, V3 mh, double w) {
+	if (pass_i == 0) { // QCP::move_to_weighted_center (:139-160)
+		A.total_w = r_add(A.total_w, w);
+		A.csum_m = vadd(A.csum_m, vmuls(mh, (float)w));
+		A.csum_t = vadd(A.csum_t, vmuls(th, (float)w));
+	} else {
+		if (translate) { // QCP::translate (:129-133) with -centroid
+			mh = vadd(mh, A.neg_mc);
+			th = vadd(th, A.neg_tc);
+		}
+		qcp_accumulate(A.sums, th, mh, w);
+		A.last_t = th;
+		A.last_m = mh;
+	}
+}
+
+// Ge = global transform of the effector's bone, De = its bone-direction local basis, T = its target,
+// bo = origin of the SOLVED bone's bone-direction frame
+__device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, bool translate, const BlobEff &E, const X34 &Ge, const M3 &De,
+		const X34 &T, V3 bo) {
+	const M3 tipB = m3_mul(Ge.b, De);
+	const V3 tipO = xform_zero(Ge);
+	// heading 0: origins.  Target heading is taken from the EFFECTOR's own bone (:97), tip heading from the solved bone (:125)
+	V3 th = vsub(T.o, tipO);
+	V3 mh = vsub(tipO, bo);
+	float dist = vlen(vsub(bo, T.o));
+	float scale_by = dist < 1.0f ? dist : 1.0f; // MIN(distance, 1.0f)
+	heading_emit(A, pass_i, translate, th, mh, E.w_origin);
+#pragma unroll
+	for (int ax = 0; ax < 3; ax++) {
+		if (E.prio[ax] > 0.0f) {
+			const double wd = E.w_axis[ax];
+			const float w = (float)wd;
+			V3 col = m3_col(T.b, ax);
+			V3 thp = vsub(vadd(col, T.o), tipO);
+			thp = v3(r_mul(thp.x, w), r_mul(thp.y, w), r_mul(thp.z, w));
+			V3 thm = vsub(vsub(T.o, col), tipO);
+			thm = v3(r_mul(thm.x, w), r_mul(thm.y, w), r_mul(thm.z, w));
+			V3 tcol = vmuls(m3_col(tipB, ax), E.prio[ax]);
+			V3 mhp = vmuls(vsub(vadd(tcol, tipO), bo), scale_by);
+			V3 mhm = vmuls(vsub(vsub(tipO, tcol), bo), scale_by);
+			heading_emit(A, pass_i, translate, thp, mhp, wd);
+			heading_emit(A, pass_i, translate, thm, mhm, wd);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int NB>
+template <int NB, int NSEG, int NSTK>
 __global__ void __launch_bounds__(kBlockThreads, 1) mbik_solve_kernel(SolveArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t bar;
@@ -391,6 +449,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) mbik_solve_kernel(SolveArgs 
 	const BlobFk *fk = reinterpret_cast<const BlobFk *>(smem + H.off_fk);
 	const BlobCone *cones = reinterpret_cast<const BlobCone *>(smem + H.off_cones);
 	const BlobPass *pass = reinterpret_cast<const BlobPass *>(smem + H.off_pass);
+	const int16_t *chain = reinterpret_cast<const int16_t *>(smem + H.off_chain);
 	const float *rest = reinterpret_cast<const float *>(smem + H.off_rest);
 
 	// Every thread stays alive for the whole kernel (CTA-wide barriers below); threads past the end of the
@@ -406,8 +465,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) mbik_solve_kernel(SolveArgs 
 	const float *my_targets = a.targets + pose * (size_t)n_pins * 12;
 	const float *my_start = a.start_pose ? a.start_pose + pose * (size_t)n_bones * 12 : nullptr;
 
-	float L[NB * 12]; // local transform of every solved bone (t order)
-	float G[NB * 12]; // global transform cache
+	// Per-pose state (thread-local, lane-interleaved):
+	float L[NB * 12];      // local transform of every solved bone (t order) -- the only state carried between steps
+	float Pseg[NSEG * 12]; // globals of the parents of the current segment's bones (ancestors do not move while a
+	                       // segment is being solved, so this replaces the reference's lazy global-transform cache)
+	float Gstk[NSTK * 12]; // globals of the branch points of the current downward walk
 
 	// seed: ManyBoneIK3D::_update_ik_bones_transform -> IKBone3D::set_initial_pose (src/ik_bone_3d.cpp:161-168)
 	for (int t = 0; t < ns; t++) {
@@ -417,22 +479,6 @@ __global__ void __launch_bounds__(kBlockThreads, 1) mbik_solve_kernel(SolveArgs 
 	}
 
 	for (int it = 0; it < a.iterations; it++) {
-		// explicit FK in place of the lazy dirty-flag cache: every ancestor global a step reads below was
-		// (re)computed here, after the previous iteration's last write to an ancestor
-		for (int t = 0; t < ns; t++) {
-			int p = bones[t].parent;
-			X34 l = ld_x34(L, t);
-			X34 g;
-			if (p >= 0) {
-				g = x_mul(ld_x34(G, p), l);
-			} else if (bones[t].flags & STEP_NODE_PARENT) {
-				g = x_mul(x_identity(), l);
-			} else {
-				g = l;
-			}
-			st_x34(G, t, g);
-		}
-
 		for (int s = 0; s < n_steps; s++) {
 			// Keep the CTA's warps in lockstep at bone-step granularity: the step body is ~75 KB of straight-line
 			// SASS, far more than the instruction cache holds, so warps that drift apart each stream it from L2
@@ -444,27 +490,31 @@ __global__ void __launch_bounds__(kBlockThreads, 1) mbik_solve_kernel(SolveArgs 
 			const bool node_parent = (flags & STEP_NODE_PARENT) != 0;
 			const BlobBone &B = bones[b];
 
-			const X34 P = S.parent >= 0 ? ld_x34(G, S.parent) : x_identity();
-			X34 Lb = ld_x34(L, b);
-			X34 Gb = node_parent ? x_mul(P, Lb) : Lb;
-			st_x34(G, b, Gb);
-			// refresh the globals on the paths down to this segment's effectors
-			{
-				X34 run = Gb; // running product: most refresh lists are chains, so the parent is usually in registers
-				int run_node = b;
-				for (int k = 0; k < S.fk_cnt; k++) {
-					const BlobFk op = fk[S.fk_off + k];
-					const int child = op.child & 0x7fff;
-					if (op.parent != run_node) {
-						run = ld_x34(G, op.parent);
+			if (flags & STEP_SEG_FIRST) {
+				// explicit FK down the ancestor chain skeleton-root .. parent(tip); the last seg_len globals are the
+				// parents of this segment's bones (slot 0 = parent of the segment root)
+				const int off = S.chain_cnt - S.seg_len; // -1 for a root segment: its root has no IK parent
+				if (off < 0) {
+					st_x34(Pseg, 0, x_identity());
+				}
+				X34 g = x_identity();
+				for (int k = 0; k < S.chain_cnt; k++) {
+					const int t = chain[S.chain_off + k];
+					const X34 l = ld_x34(L, t);
+					if (k == 0) {
+						g = (bones[t].flags & STEP_NODE_PARENT) ? x_mul(x_identity(), l) : l;
+					} else {
+						g = x_mul(g, l);
 					}
-					run = x_mul(run, ld_x34(L, child));
-					run_node = child;
-					if (op.child & 0x8000) { // read again later: an effector's bone or a branch point
-						st_x34(G, child, run);
+					if (k - off >= 0) {
+						st_x34(Pseg, k - off, g);
 					}
 				}
 			}
+
+			const X34 P = S.parent >= 0 ? ld_x34(Pseg, S.pslot) : x_identity();
+			X34 Lb = ld_x34(L, b);
+			const X34 Gb = node_parent ? x_mul(P, Lb) : Lb;
 			M3 Pinv = m3_identity();
 			if (node_parent) {
 				Pinv = m3_inverse(P.b);
@@ -474,76 +524,50 @@ __global__ void __launch_bounds__(kBlockThreads, 1) mbik_solve_kernel(SolveArgs 
 				const V3 bo = xform_zero(Gb); // origin of the solved bone's bone-direction frame
 				const bool translate = (flags & STEP_TRANSLATE) != 0;
 				V3 moved_center = v3(0.0f, 0.0f, 0.0f), target_center = v3(0.0f, 0.0f, 0.0f);
-				V3 neg_mc = v3(0.0f, 0.0f, 0.0f), neg_tc = v3(0.0f, 0.0f, 0.0f);
-				QcpSums sums;
-				qcp_zero(sums);
-				V3 last_t = v3(0.0f, 0.0f, 0.0f), last_m = v3(0.0f, 0.0f, 0.0f);
-				// pass 0 (translate only): weighted centroids (QCP::move_to_weighted_center, :139-160)
-				// pass 1: inner product, on re-centred headings when translating (:225-248)
+				HeadingAcc A;
+				qcp_zero(A.sums);
+				A.neg_mc = A.neg_tc = A.last_t = A.last_m = v3(0.0f, 0.0f, 0.0f);
+				if (flags & STEP_PUSH_SELF) {
+					st_x34(Gstk, 0, Gb);
+				}
+				// pass 0 (translating root segment only): weighted centroids; pass 1: inner product (:225-248)
 				for (int pass_i = translate ? 0 : 1; pass_i < 2; pass_i++) {
-					double total_w = 0.0;
-					V3 csum_m = v3(0.0f, 0.0f, 0.0f), csum_t = v3(0.0f, 0.0f, 0.0f);
-					for (int e = 0; e < S.eff_cnt; e++) {
-						const BlobEff &E = effs[S.eff_off + e];
-						const X34 Ge = ld_x34(G, E.bone);
-						const M3 tipB = m3_mul(Ge.b, ld_m3(bones[E.bone].dir_basis));
-						const V3 tipO = xform_zero(Ge);
-						const X34 T = ldg_x34(my_targets + (size_t)E.pin * 12);
-						// heading 0: origins (src/ik_effector_3d.cpp:97-99, :125-127)
-						V3 th = vsub(T.o, tipO);
-						V3 mh = vsub(tipO, bo);
-						float dist = vlen(vsub(bo, T.o));
-						float scale_by = dist < 1.0f ? dist : 1.0f; // MIN(distance, 1.0f)
-#define MBIK_EMIT(TH, MH, W)                                              \
-	do {                                                                  \
-		if (pass_i == 0) {                                                \
-			total_w = r_add(total_w, (W));                                \
-			csum_m = vadd(csum_m, vmuls((MH), (float)(W)));               \
-			csum_t = vadd(csum_t, vmuls((TH), (float)(W)));               \
-		} else {                                                          \
-			V3 th_ = (TH), mh_ = (MH);                                    \
-			if (translate) {                                              \
-				mh_ = vadd(mh_, neg_mc);                                  \
-				th_ = vadd(th_, neg_tc);                                  \
-			}                                                             \
-			qcp_accumulate(sums, th_, mh_, (W));                          \
-			last_t = th_;                                                 \
-			last_m = mh_;                                                 \
-		}                                                                 \
-	} while (0)
-						MBIK_EMIT(th, mh, E.w_origin);
-#pragma unroll
-						for (int ax = 0; ax < 3; ax++) {
-							if (E.prio[ax] > 0.0f) {
-								const double wd = E.w_axis[ax];
-								const float w = (float)wd;
-								V3 col = m3_col(T.b, ax);
-								V3 thp = vsub(vadd(col, T.o), tipO);
-								thp = v3(r_mul(thp.x, w), r_mul(thp.y, w), r_mul(thp.z, w));
-								V3 thm = vsub(vsub(T.o, col), tipO);
-								thm = v3(r_mul(thm.x, w), r_mul(thm.y, w), r_mul(thm.z, w));
-								V3 tcol = vmuls(m3_col(tipB, ax), E.prio[ax]);
-								V3 mhp = vmuls(vsub(vadd(tcol, tipO), bo), scale_by);
-								V3 mhm = vmuls(vsub(vsub(tipO, tcol), bo), scale_by);
-								MBIK_EMIT(thp, mhp, wd);
-								MBIK_EMIT(thm, mhm, wd);
-							}
+					A.total_w = 0.0;
+					A.csum_m = A.csum_t = v3(0.0f, 0.0f, 0.0f);
+					if (flags & STEP_SELF_EFF) {
+						const BlobEff &E = effs[S.eff_off];
+						effector_headings(A, pass_i, translate, E, Gb, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo);
+					}
+					// depth-first walk down to the effectors of this segment's list: the lazily re-derived global
+					// transforms of the reference (src/math/ik_node_3d.cpp:93-113) as explicit running products
+					X34 run = Gb;
+					for (int k = 0; k < S.fk_cnt; k++) {
+						const BlobFk op = fk[S.fk_off + k];
+						if (op.src_slot >= 0) {
+							run = ld_x34(Gstk, op.src_slot);
 						}
-#undef MBIK_EMIT
+						run = x_mul(run, ld_x34(L, op.child));
+						if (op.push_slot >= 0) {
+							st_x34(Gstk, op.push_slot, run);
+						}
+						if (op.eff >= 0) {
+							const BlobEff &E = effs[S.eff_off + op.eff];
+							effector_headings(A, pass_i, translate, E, run, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo);
+						}
 					}
 					if (pass_i == 0) {
-						if (total_w > 0.0) {
-							moved_center = vdivs(csum_m, (float)total_w);
-							target_center = vdivs(csum_t, (float)total_w);
+						if (A.total_w > 0.0) {
+							moved_center = vdivs(A.csum_m, (float)A.total_w);
+							target_center = vdivs(A.csum_t, (float)A.total_w);
 						} else {
-							moved_center = csum_m;
-							target_center = csum_t;
+							moved_center = A.csum_m;
+							target_center = A.csum_t;
 						}
-						neg_mc = vmuls(moved_center, -1.0f);
-						neg_tc = vmuls(target_center, -1.0f);
+						A.neg_mc = vmuls(moved_center, -1.0f);
+						A.neg_tc = vmuls(target_center, -1.0f);
 					}
 				}
-				Q4 q = (S.n_headings == 1) ? qcp_rotation_single(last_m, last_t) : qcp_rotation(sums);
+				Q4 q = (S.n_headings == 1) ? qcp_rotation_single(A.last_m, A.last_t) : qcp_rotation(A.sums);
 				V3 translation = vsub(target_center, moved_center);
 
 				M3 R2 = damp_and_slerp0(q, S.cos_half_damp, Gb.b);
@@ -625,39 +649,40 @@ __global__ void __launch_bounds__(kBlockThreads, 1) mbik_solve_kernel(SolveArgs 
 // ---------------------------------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------------------------------
-template <int NB>
+template <int NB, int NSEG, int NSTK>
 static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 	size_t smem = a.blob_bytes;
-	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel<NB, NSEG, NSTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) {
 		return e;
 	}
 	unsigned grid = (unsigned)((a.n_poses + kBlockThreads - 1) / kBlockThreads);
-	mbik_solve_kernel<NB><<<grid, kBlockThreads, smem, stream>>>(a);
+	mbik_solve_kernel<NB, NSEG, NSTK><<<grid, kBlockThreads, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 
-int kernel_capacity_for(int n_solved) {
-	if (n_solved <= 24) {
-		return 24;
-	}
-	if (n_solved <= 64) {
-		return 64;
-	}
-	if (n_solved <= 128) {
-		return 128;
+// kernel variants: {solved-bone capacity, longest segment, walk-stack depth}
+static const int kVariants[][3] = { { 20, 8, 4 }, { 64, 16, 8 }, { 128, 128, 16 } };
+
+int kernel_variant_for(int n_solved, int max_seg_len, int max_stack) {
+	for (int v = 0; v < 3; v++) {
+		if (n_solved <= kVariants[v][0] && max_seg_len <= kVariants[v][1] && max_stack <= kVariants[v][2]) {
+			return v;
+		}
 	}
 	return -1;
 }
 
-cudaError_t launch_solve(const SolveArgs &a, int n_solved, cudaStream_t stream) {
-	switch (kernel_capacity_for(n_solved)) {
-		case 24:
-			return launch_variant<24>(a, stream);
-		case 64:
-			return launch_variant<64>(a, stream);
-		case 128:
-			return launch_variant<128>(a, stream);
+int kernel_capacity_of_variant(int v) { return (v >= 0 && v < 3) ? kVariants[v][0] : -1; }
+
+cudaError_t launch_solve(const SolveArgs &a, int variant, cudaStream_t stream) {
+	switch (variant) {
+		case 0:
+			return launch_variant<20, 8, 4>(a, stream);
+		case 1:
+			return launch_variant<64, 16, 8>(a, stream);
+		case 2:
+			return launch_variant<128, 128, 16>(a, stream);
 		default:
 			return cudaErrorInvalidValue;
 	}

@@ -20,8 +20,9 @@ struct SolveArgs {
 	uint32_t *out_status;    // [n_poses] or nullptr
 };
 
-// solved-bone capacity of the kernel variant used for a rig with n_solved bones, or -1 if unsupported
-int kernel_capacity_for(int n_solved);
-cudaError_t launch_solve(const SolveArgs &args, int n_solved, cudaStream_t stream);
+// index of the smallest kernel variant that fits the rig, or -1 if none does
+int kernel_variant_for(int n_solved, int max_seg_len, int max_stack);
+int kernel_capacity_of_variant(int variant);
+cudaError_t launch_solve(const SolveArgs &args, int variant, cudaStream_t stream);
 
 } // namespace mbik
