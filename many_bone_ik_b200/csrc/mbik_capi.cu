@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -29,16 +30,26 @@ int cuda_fail(cudaError_t e, const char *what) {
 	return fail(MBIK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-struct DeviceState {
-	int device = -1;
-	unsigned char *blob = nullptr;
-	cudaStream_t stream = nullptr; // used for MBIK_IO_HOST calls
+constexpr int kLanes = 3; // host-I/O pipeline depth: H2D(i+1) | solve(i) | D2H(i-1) on three streams
+
+// staging of one pipeline lane, grown on demand and reused (no allocation in steady state)
+struct Lane {
+	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
-	bool timed = false;
-	// staging for host-I/O calls, grown on demand and reused (no allocation in steady state)
 	float *d_targets = nullptr, *d_start = nullptr, *d_out = nullptr, *d_local = nullptr;
 	uint32_t *d_status = nullptr;
 	size_t cap_targets = 0, cap_start = 0, cap_out = 0, cap_local = 0, cap_status = 0;
+};
+
+struct DeviceState {
+	int device = -1;
+	int sm_count = 0;
+	unsigned char *blob = nullptr;
+	cudaEvent_t ev_start = nullptr, ev_stop = nullptr; // MBIK_IO_DEVICE launches (on the caller's stream)
+	bool timed = false;
+	float host_path_kernel_ms = -1.f; // sum over the chunks of the last MBIK_IO_HOST call
+	bool last_was_host = false;
+	Lane lanes[kLanes];
 };
 
 } // namespace
@@ -59,19 +70,27 @@ void free_device_state(DeviceState &ds) {
 	}
 	cudaSetDevice(ds.device);
 	cudaFree(ds.blob);
-	cudaFree(ds.d_targets);
-	cudaFree(ds.d_start);
-	cudaFree(ds.d_out);
-	cudaFree(ds.d_local);
-	cudaFree(ds.d_status);
 	if (ds.ev_start) {
 		cudaEventDestroy(ds.ev_start);
 	}
 	if (ds.ev_stop) {
 		cudaEventDestroy(ds.ev_stop);
 	}
-	if (ds.stream) {
-		cudaStreamDestroy(ds.stream);
+	for (Lane &ln : ds.lanes) {
+		cudaFree(ln.d_targets);
+		cudaFree(ln.d_start);
+		cudaFree(ln.d_out);
+		cudaFree(ln.d_local);
+		cudaFree(ln.d_status);
+		if (ln.ev_start) {
+			cudaEventDestroy(ln.ev_start);
+		}
+		if (ln.ev_stop) {
+			cudaEventDestroy(ln.ev_stop);
+		}
+		if (ln.stream) {
+			cudaStreamDestroy(ln.stream);
+		}
 	}
 }
 
@@ -94,12 +113,23 @@ int get_device_state(mbik_rig *rig, int device, DeviceState **out) {
 		cudaFree(ds.blob);
 		return cuda_fail(e, "cudaMemcpy(rig blob)");
 	}
-	e = cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking);
-	if (e == cudaSuccess) {
-		e = cudaEventCreate(&ds.ev_start);
-	}
+	e = cudaEventCreate(&ds.ev_start);
 	if (e == cudaSuccess) {
 		e = cudaEventCreate(&ds.ev_stop);
+	}
+	for (Lane &ln : ds.lanes) {
+		if (e == cudaSuccess) {
+			e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking);
+		}
+		if (e == cudaSuccess) {
+			e = cudaEventCreate(&ln.ev_start);
+		}
+		if (e == cudaSuccess) {
+			e = cudaEventCreate(&ln.ev_stop);
+		}
+	}
+	if (e == cudaSuccess) {
+		e = cudaDeviceGetAttribute(&ds.sm_count, cudaDevAttrMultiProcessorCount, device);
 	}
 	if (e != cudaSuccess) {
 		free_device_state(ds);
@@ -178,54 +208,102 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 		a.out_local = out_local;
 		a.out_status = out_status;
 		cudaEventRecord(ds->ev_start, user_stream);
-		e = mbik::launch_solve(a, rig->variant, user_stream);
+		e = mbik::launch_solve(a, rig->variant, ds->sm_count, user_stream);
 		cudaEventRecord(ds->ev_stop, user_stream);
 		ds->timed = true;
+		ds->last_was_host = false;
 		if (e != cudaSuccess) {
 			return cuda_fail(e, "kernel launch");
 		}
 		return MBIK_OK;
 	}
 
-	// host buffers: stage through device memory on this device's stream
-	const size_t bt = n_poses * np * 12 * sizeof(float), bs = n_poses * nb * 12 * sizeof(float);
-	const size_t bo = n_poses * nb * 10 * sizeof(float), bl = n_poses * nb * 12 * sizeof(float), bst = n_poses * sizeof(uint32_t);
-	if ((rc = ensure_capacity(&ds->d_targets, &ds->cap_targets, bt ? bt : 16)) != MBIK_OK ||
-			(rc = ensure_capacity(&ds->d_out, &ds->cap_out, bo)) != MBIK_OK ||
-			(start_pose && (rc = ensure_capacity(&ds->d_start, &ds->cap_start, bs)) != MBIK_OK) ||
-			(out_local && (rc = ensure_capacity(&ds->d_local, &ds->cap_local, bl)) != MBIK_OK) ||
-			(out_status && (rc = ensure_capacity(&ds->d_status, &ds->cap_status, bst)) != MBIK_OK)) {
-		return rc;
+	// Host buffers: the batch is cut into chunks of whole kernel waves and streamed through kLanes staging
+	// lanes, so the H2D copy of chunk i+1, the solve of chunk i and the D2H copy of chunk i-1 overlap.
+	const size_t wave = (size_t)(ds->sm_count > 0 ? ds->sm_count : 148) * mbik::kBlockThreads;
+	size_t chunk = 2 * wave;
+	if (const char *env = getenv("MBIK_CHUNK_POSES")) {
+		size_t v = (size_t)atoll(env);
+		if (v > 0) {
+			chunk = v;
+		}
 	}
-	cudaStream_t st = ds->stream;
-	if (bt) {
-		cudaMemcpyAsync(ds->d_targets, targets, bt, cudaMemcpyHostToDevice, st);
+	const size_t n_chunks = (n_poses + chunk - 1) / chunk;
+	std::vector<int> chunks_of_lane[kLanes];
+	for (size_t c = 0; c < n_chunks; c++) {
+		Lane &ln = ds->lanes[c % kLanes];
+		const size_t b0 = c * chunk, cn = (b0 + chunk <= n_poses) ? chunk : n_poses - b0;
+		const size_t bt = cn * np * 12 * sizeof(float), bs = cn * nb * 12 * sizeof(float);
+		const size_t bo = cn * nb * 10 * sizeof(float), bl = cn * nb * 12 * sizeof(float), bst = cn * sizeof(uint32_t);
+		if ((rc = ensure_capacity(&ln.d_targets, &ln.cap_targets, bt ? bt : 16)) != MBIK_OK ||
+				(rc = ensure_capacity(&ln.d_out, &ln.cap_out, bo)) != MBIK_OK ||
+				(start_pose && (rc = ensure_capacity(&ln.d_start, &ln.cap_start, bs)) != MBIK_OK) ||
+				(out_local && (rc = ensure_capacity(&ln.d_local, &ln.cap_local, bl)) != MBIK_OK) ||
+				(out_status && (rc = ensure_capacity(&ln.d_status, &ln.cap_status, bst)) != MBIK_OK)) {
+			for (Lane &l2 : ds->lanes) {
+				cudaStreamSynchronize(l2.stream);
+			}
+			return rc;
+		}
+		cudaStream_t st = ln.stream;
+		if (bt) {
+			cudaMemcpyAsync(ln.d_targets, targets + b0 * np * 12, bt, cudaMemcpyHostToDevice, st);
+		}
+		if (start_pose) {
+			cudaMemcpyAsync(ln.d_start, start_pose + b0 * nb * 12, bs, cudaMemcpyHostToDevice, st);
+		}
+		a.n_poses = cn;
+		a.targets = ln.d_targets;
+		a.start_pose = start_pose ? ln.d_start : nullptr;
+		a.out_pose = ln.d_out;
+		a.out_local = out_local ? ln.d_local : nullptr;
+		a.out_status = out_status ? ln.d_status : nullptr;
+		const bool last_of_lane = c + kLanes >= n_chunks;
+		if (last_of_lane) {
+			cudaEventRecord(ln.ev_start, st);
+		}
+		e = mbik::launch_solve(a, rig->variant, ds->sm_count, st);
+		if (last_of_lane) {
+			cudaEventRecord(ln.ev_stop, st);
+		}
+		if (e != cudaSuccess) {
+			for (Lane &l2 : ds->lanes) {
+				cudaStreamSynchronize(l2.stream);
+			}
+			return cuda_fail(e, "kernel launch");
+		}
+		cudaMemcpyAsync(out_pose + b0 * nb * 10, ln.d_out, bo, cudaMemcpyDeviceToHost, st);
+		if (out_local) {
+			cudaMemcpyAsync(out_local + b0 * nb * 12, ln.d_local, bl, cudaMemcpyDeviceToHost, st);
+		}
+		if (out_status) {
+			cudaMemcpyAsync(out_status + b0, ln.d_status, bst, cudaMemcpyDeviceToHost, st);
+		}
 	}
-	if (start_pose) {
-		cudaMemcpyAsync(ds->d_start, start_pose, bs, cudaMemcpyHostToDevice, st);
+	cudaError_t first_err = cudaSuccess;
+	for (Lane &ln : ds->lanes) {
+		cudaError_t e2 = cudaStreamSynchronize(ln.stream);
+		if (e2 != cudaSuccess && first_err == cudaSuccess) {
+			first_err = e2;
+		}
 	}
-	a.targets = ds->d_targets;
-	a.start_pose = start_pose ? ds->d_start : nullptr;
-	a.out_pose = ds->d_out;
-	a.out_local = out_local ? ds->d_local : nullptr;
-	a.out_status = out_status ? ds->d_status : nullptr;
-	cudaEventRecord(ds->ev_start, st);
-	e = mbik::launch_solve(a, rig->variant, st);
-	cudaEventRecord(ds->ev_stop, st);
-	ds->timed = true;
-	if (e != cudaSuccess) {
-		return cuda_fail(e, "kernel launch");
+	if (first_err != cudaSuccess) {
+		return cuda_fail(first_err, "solve (stream synchronize)");
 	}
-	cudaMemcpyAsync(out_pose, ds->d_out, bo, cudaMemcpyDeviceToHost, st);
-	if (out_local) {
-		cudaMemcpyAsync(out_local, ds->d_local, bl, cudaMemcpyDeviceToHost, st);
-	}
-	if (out_status) {
-		cudaMemcpyAsync(out_status, ds->d_status, bst, cudaMemcpyDeviceToHost, st);
-	}
-	e = cudaStreamSynchronize(st);
-	if (e != cudaSuccess) {
-		return cuda_fail(e, "solve (stream synchronize)");
+	// kernel time of this call = the last chunk of each lane that ran one (an estimate when n_chunks > kLanes)
+	{
+		float total = 0.f;
+		size_t timed_chunks = 0;
+		for (size_t c = (n_chunks > (size_t)kLanes ? n_chunks - kLanes : 0); c < n_chunks; c++) {
+			float ms = 0.f;
+			Lane &ln = ds->lanes[c % kLanes];
+			if (cudaEventElapsedTime(&ms, ln.ev_start, ln.ev_stop) == cudaSuccess) {
+				total += ms;
+				timed_chunks++;
+			}
+		}
+		ds->host_path_kernel_ms = timed_chunks ? total * (float)n_chunks / (float)timed_chunks : -1.f;
+		ds->last_was_host = true;
 	}
 	return MBIK_OK;
 }
@@ -488,6 +566,10 @@ int mbik_last_kernel_ms(mbik_rig *rig, int32_t device, float *out_ms) {
 	}
 	std::lock_guard<std::mutex> lock(rig->mu);
 	auto it = rig->devices.find(device);
+	if (it != rig->devices.end() && it->second.last_was_host && it->second.host_path_kernel_ms >= 0.f) {
+		*out_ms = it->second.host_path_kernel_ms;
+		return MBIK_OK;
+	}
 	if (it == rig->devices.end() || !it->second.timed) {
 		return fail(MBIK_ERR_INVALID_ARG, "no launch recorded on that device");
 	}

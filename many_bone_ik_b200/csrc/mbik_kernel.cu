@@ -27,6 +27,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 namespace mbik {
 
 // ---------------------------------------------------------------------------------------------------
@@ -419,8 +421,8 @@ __device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, boo
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int NB, int NSEG, int NSTK>
-__global__ void __launch_bounds__(kBlockThreads, 1) mbik_solve_kernel(SolveArgs a) {
+template <int NB, int NSEG, int NSTK, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel(SolveArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t bar;
 
@@ -649,15 +651,15 @@ __global__ void __launch_bounds__(kBlockThreads, 1) mbik_solve_kernel(SolveArgs 
 // ---------------------------------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------------------------------
-template <int NB, int NSEG, int NSTK>
+template <int NB, int NSEG, int NSTK, int THREADS>
 static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 	size_t smem = a.blob_bytes;
-	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel<NB, NSEG, NSTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel<NB, NSEG, NSTK, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) {
 		return e;
 	}
-	unsigned grid = (unsigned)((a.n_poses + kBlockThreads - 1) / kBlockThreads);
-	mbik_solve_kernel<NB, NSEG, NSTK><<<grid, kBlockThreads, smem, stream>>>(a);
+	unsigned grid = (unsigned)((a.n_poses + THREADS - 1) / THREADS);
+	mbik_solve_kernel<NB, NSEG, NSTK, THREADS><<<grid, THREADS, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 
@@ -675,14 +677,43 @@ int kernel_variant_for(int n_solved, int max_seg_len, int max_stack) {
 
 int kernel_capacity_of_variant(int v) { return (v >= 0 && v < 3) ? kVariants[v][0] : -1; }
 
-cudaError_t launch_solve(const SolveArgs &a, int variant, cudaStream_t stream) {
+cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStream_t stream) {
 	switch (variant) {
-		case 0:
-			return launch_variant<20, 8, 4>(a, stream);
+		case 0: {
+			// Small batches: one CTA per SM with as few warps as cover the batch (a 4096-pose batch runs as 128
+			// one-warp CTAs on 128 SMs instead of 11 twelve-warp CTAs on 11 SMs) -- latency, not throughput.
+			static const int forced = getenv("MBIK_THREADS") ? atoi(getenv("MBIK_THREADS")) : 0; // tuning knob
+			int threads = kBlockThreads;
+			if (forced > 0) {
+				threads = forced;
+			} else {
+				const int cands[] = { 32, 64, 128, 256 };
+				for (int c : cands) {
+					if ((a.n_poses + c - 1) / c <= (size_t)sm_count) {
+						threads = c;
+						break;
+					}
+				}
+			}
+			switch (threads) {
+				case 32:
+					return launch_variant<20, 8, 4, 32>(a, stream);
+				case 64:
+					return launch_variant<20, 8, 4, 64>(a, stream);
+				case 128:
+					return launch_variant<20, 8, 4, 128>(a, stream);
+				case 256:
+					return launch_variant<20, 8, 4, 256>(a, stream);
+				case 512:
+					return launch_variant<20, 8, 4, 512>(a, stream);
+				default:
+					return launch_variant<20, 8, 4, kBlockThreads>(a, stream);
+			}
+		}
 		case 1:
-			return launch_variant<64, 16, 8>(a, stream);
+			return launch_variant<64, 16, 8, kBlockThreads>(a, stream);
 		case 2:
-			return launch_variant<128, 128, 16>(a, stream);
+			return launch_variant<128, 128, 16, kBlockThreads>(a, stream);
 		default:
 			return cudaErrorInvalidValue;
 	}

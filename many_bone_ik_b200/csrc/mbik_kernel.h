@@ -23,6 +23,6 @@ struct SolveArgs {
 // index of the smallest kernel variant that fits the rig, or -1 if none does
 int kernel_variant_for(int n_solved, int max_seg_len, int max_stack);
 int kernel_capacity_of_variant(int variant);
-cudaError_t launch_solve(const SolveArgs &args, int variant, cudaStream_t stream);
+cudaError_t launch_solve(const SolveArgs &args, int variant, int sm_count, cudaStream_t stream);
 
 } // namespace mbik
