@@ -1,0 +1,105 @@
+"""Edge-case rigs for parity tests (beyond the three benchmark rigs)."""
+import numpy as np
+
+from many_bone_ik_b200 import rigs
+from many_bone_ik_b200.rigs import DEG, Rig, _add_constraints, _axis_angle, _xf
+
+
+def _chain(n, seg=0.1, curl=2.0):
+    parent = np.arange(-1, n - 1, dtype=np.int32)
+    rest = np.zeros((n, 12))
+    for i in range(n):
+        rest[i] = _xf(_axis_angle((0.2, 0.1, 1.0), (curl if i else 0.0) * DEG), (0.0, seg if i else 0.3, 0.01 * (i % 3)))
+    return parent, rest.astype(np.float32)
+
+
+def chain_multibone_root(n=12, iterations=3):
+    """Unpinned root: the translating root segment spans several bones.  The reference
+    diverges on this within ~7 iterations; 3 iterations stay finite."""
+    parent, rest = _chain(n)
+    r = Rig("chain_multibone_root", [f"b{i}" for i in range(n)], parent, rest, iterations=iterations, config_id=11)
+    r.pins = [dict(bone=5, weight=0.5, mpf=1.0, priorities=(0.2, 0.0, 0.2)), dict(bone=n - 1, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2))]
+    _add_constraints(r, {b: (1, 40, 0, -30, 60) for b in range(2, n, 3)})
+    return r
+
+
+def chain_diverging(n=12):
+    """Same rig, enough iterations to blow up to non-finite values: NaN propagation and the write-back reset
+    (reference src/ik_bone_3d.cpp:174-176) must match too."""
+    r = chain_multibone_root(n, iterations=60)
+    r.name = "chain_diverging"
+    r.config_id = 12
+    return r
+
+
+def two_roots():
+    """Two parentless bones: only the LAST root keeps an IKNode3D parent (ik_origin is re-instantiated per root,
+    reference src/many_bone_ik_3d.cpp:1022), so the first root never rotates."""
+    names = ["A0", "A1", "A2", "B0", "B1", "B2", "B3"]
+    parent = np.array([-1, 0, 1, -1, 3, 4, 5], np.int32)
+    rest = np.zeros((7, 12))
+    for i in range(7):
+        rest[i] = _xf(_axis_angle((1, 0.3, 0.2), (5.0 * (i % 3)) * DEG), (0.4 if i == 3 else 0.02 * i, 0.0 if parent[i] < 0 else 0.2, 0.0))
+    r = Rig("two_roots", names, parent, rest.astype(np.float32), iterations=6, config_id=13)
+    r.pins = [dict(bone=2, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2)), dict(bone=6, weight=0.7, mpf=1.0, priorities=(0.1, 0.3, 0.0))]
+    _add_constraints(r, {1: (2, 40, 25, -20, 50), 5: (1, 30, 0, -45, 90)})
+    return r
+
+
+def star_mixed_pins():
+    """Branching rig exercising: a pin with all priorities 0 that is alone in its list (QCP single-heading branch,
+    reference src/math/qcp.cpp:59-78), a 3-axis pin (7 headings), mpf = 0 cut-off, weight 0 pin, a constraint row
+    with zero cones, a constraint row on an unsolved bone, bone_damp shorter than the skeleton."""
+    names = ["Root", "S1", "S2", "L1", "L2", "L3", "R1", "R2", "R3", "T1", "T2", "T3", "T4", "Leaf"]
+    par = [-1, 0, 1, 2, 3, 4, 2, 6, 7, 0, 9, 10, 11, 8]
+    parent = np.array(par, np.int32)
+    rest = np.zeros((len(names), 12))
+    offs = [(0, 1, 0), (0, .2, 0), (0, .2, .02), (.15, .05, 0), (.2, 0, 0), (.2, 0, .01), (-.15, .05, 0), (-.2, 0, 0), (-.2, 0, 0),
+            (0, -.1, -.2), (0, 0, -.2), (0, .01, -.2), (0, 0, -.2), (-.05, 0, 0)]
+    for i in range(len(names)):
+        rest[i] = _xf(_axis_angle(((i % 3 == 0) * 1.0, (i % 3 == 1) * 1.0, (i % 3 == 2) * 1.0), ((i * 29) % 9 - 4) * DEG), offs[i])
+    r = Rig("star_mixed_pins", names, parent, rest.astype(np.float32), iterations=8, config_id=14)
+    r.pins = [
+        dict(bone=5, weight=1.0, mpf=1.0, priorities=(0.0, 0.0, 0.0)),   # L3: translation only -> 1 heading, alone in the L chain's list
+        dict(bone=8, weight=0.8, mpf=1.0, priorities=(0.3, 0.2, 0.3)),   # R3: 7 headings (has an unsolved child Leaf)
+        dict(bone=10, weight=0.6, mpf=0.0, priorities=(0.2, 0.0, 0.2)),  # T2: mpf 0 cuts T4 off from Root's list
+        dict(bone=12, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2)),  # T4
+        dict(bone=2, weight=0.0, mpf=0.5, priorities=(0.2, 0.0, 0.2)),   # S2: weight 0 (reference default)
+    ]
+    _add_constraints(r, {1: (1, 35, 0, -30, 60), 3: (2, 40, 30, -45, 90), 4: (3, 30, 25, 0, 45), 7: (4, 25, 20, -10, 20), 11: (1, 20, 0, -90, 180)})
+    r.constraints.append(dict(bone=9, twist_from=-0.3, twist_range=1.0, cones=[]))        # zero cones
+    r.constraints.append(dict(bone=13, twist_from=0.0, twist_range=1.0, cones=[(0, 1, 0, 0.5)]))  # unsolved bone: ignored
+    r.bone_damp = np.array([0.05, 0.02, 0.2, 0.01, 0.03], np.float32)  # indexed by bone id, shorter than the skeleton
+    return r
+
+
+def humanoid_no_constraints():
+    r = rigs.humanoid22()
+    r.constraints = []
+    r.name = "humanoid_no_constraints"
+    r.config_id = 15
+    return r
+
+
+def humanoid_constraint_mode():
+    r = rigs.humanoid22()
+    r.constraint_mode = True
+    r.name = "humanoid_constraint_mode"
+    r.config_id = 16
+    return r
+
+
+EDGE_RIGS = {f.__name__: f for f in [chain_multibone_root, chain_diverging, two_roots, star_mixed_pins, humanoid_no_constraints, humanoid_constraint_mode]}
+
+
+def perturbed_start_pose(rig, n, seed=7, angle_deg=12.0, offset=0.02):
+    """[n, n_bones, 12] start poses = rest pose with small random local rotations/offsets."""
+    rng = np.random.default_rng(seed)
+    out = np.repeat(rig.rest_local[None], n, axis=0).astype(np.float32).copy()
+    for k in range(n):
+        for b in range(rig.n_bones):
+            ax = rng.normal(size=3)
+            R = _axis_angle(ax, rng.uniform(0, angle_deg) * DEG) @ rig.rest_local[b, :9].astype(np.float64).reshape(3, 3)
+            out[k, b, :9] = R.reshape(9).astype(np.float32)
+            out[k, b, 9:] += rng.uniform(-offset, offset, 3).astype(np.float32)
+    return out
