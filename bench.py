@@ -5,9 +5,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[2], which also covers N=1): the `humanoid22` rig (22 bones, 5 pinned effectors,
-kusudama open-cone + twist limits on the 19 non-root solved bones, 10 iterations), 2^20 independent poses with
-seeded random effector targets, sharded contiguously over the N ranks (strong scaling, no collective in the
-solve).  One "step" = one pass of the hot path over the rank's shard.
+kusudama open-cone + twist limits on the 19 non-root solved bones, 10 iterations), 2^20 independent poses PER GPU
+with seeded random effector targets; rank g of N solves the contiguous pose range [g*2^20, (g+1)*2^20) of an
+N*2^20-pose batch (weak scaling, no collective in the solve).  One "step" = one pass of the hot path over the
+rank's shard.
 
   value : skeleton-solves/s with inputs already resident in HBM (device-resident I/O, CUDA-event timed)
   e2e   : the same through the C ABI with pinned HOST buffers, H2D + D2H inside the timed region
@@ -31,19 +32,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TOTAL_POSES = 1 << 20
+POSES_PER_GPU = 1 << 20
 LATENCY_BATCH = 4096
 METRIC = "ik_skeleton_solves_per_sec"
 UNIT = "solves/s"
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, per_gpu=POSES_PER_GPU):
     return {
-        "workload": "humanoid22 (22 bones, 5 effectors, 32 kusudama cones + twist, 10 iterations), 2^20 random-target poses "
-                    "(BASELINE configs[2]; the 1-GPU run solves all 2^20)",
-        "rig": "humanoid22", "iterations": 10, "total_poses": TOTAL_POSES, "poses_per_gpu": TOTAL_POSES // n_gpus,
+        "workload": "humanoid22 (22 bones, 5 effectors, 32 kusudama cones + twist, 10 iterations), 2^20 random-target poses per GPU "
+                    "(BASELINE configs[2]'s 1M-pose batch on every GPU: weak scaling)",
+        "rig": "humanoid22", "iterations": 10, "total_poses": per_gpu * n_gpus, "poses_per_gpu": per_gpu,
         "parallelism": f"dp{n_gpus} (contiguous pose shards, no collective)",
-        "cache": "inputs (252 MB targets) and outputs (923 MB) are larger than the 126 MB L2",
+        "cache": "per GPU the inputs (252 MB targets) and outputs (923 MB) are larger than the 126 MB L2",
     }
 
 
@@ -126,10 +127,10 @@ def run_reference_arm(args, rank, world):
         return
     from many_bone_ik_b200 import rigs
     rig = rigs.humanoid22()
-    cb, ms = time_cpu_reference(rig, budget_s=20.0, steps=max(args.steps, 1), warmup=max(min(args.warmup, 1), 0))
+    cb, ms = time_cpu_reference(rig, budget_s=args.budget_s, steps=max(args.steps, 1), warmup=max(min(args.warmup, 1), 0))
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -144,7 +145,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mbik", choices=["mbik", "reference"])
-    ap.add_argument("--poses", type=int, default=TOTAL_POSES, help="total poses (default 2^20); smaller values are for debugging only")
+    ap.add_argument("--poses", type=int, default=POSES_PER_GPU, help="poses per GPU (default 2^20); smaller values are for debugging only")
+    ap.add_argument("--budget-s", type=float, default=20.0, help="CPU seconds the reference arm may spend per run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -159,7 +161,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from many_bone_ik_b200 import BatchedIKRig, rigs
+    from many_bone_ik_b200 import BatchedIKRig, rigs, sharding
     from many_bone_ik_b200._capi import MBIK_IO_DEVICE, MBIK_IO_HOST
 
     if not torch.cuda.is_available():
@@ -187,8 +189,8 @@ def main():
 
     rig = rigs.humanoid22()
     R = BatchedIKRig(rig)
-    total = args.poses
-    lo, hi = total * rank // world, total * (rank + 1) // world
+    total = args.poses * world
+    lo, hi = sharding.shard_range(total, rank, world)
     n = hi - lo
     nb, npins = rig.n_bones, rig.n_pins
 
@@ -280,13 +282,21 @@ def main():
     tf = C.c_double(0)
     R.lib.mbik_measure_fp32_tflops(local_rank, 5, C.byref(tf))
     k_ms = float(np.mean(kernel_ms))
+    # DRAM traffic of the kernel from the committed ncu --set full capture (bytes per pose x poses of one launch)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic = float(tj["dram_bytes"]) / float(tj["poses"]) * n
+        traffic_src = tj.get("source")
+    except Exception:
+        pass
     flops = R.info["flops_per_solve"]
     bytes_per_solve = npins * 48 + nb * 40
     ach_tf = flops * n / (k_ms * 1e-3) / 1e12
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {
         "bound": "fp32", "kernel": "mbik_solve_kernel<24>", "achieved": ach_tf, "peak": float(tf.value), "unit": "TFLOP/s",
-        "frac": ach_tf / float(tf.value) if tf.value else None, "traffic": None,
+        "frac": ach_tf / float(tf.value) if tf.value else None, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": "FP32 FMA micro-benchmark run in this process (mbik_measure_fp32_tflops)",
         "flops_per_solve": flops, "kernel_ms": k_ms,
         "note": "algorithmic flop floor of SURVEY 8(d); the kernel issues separately rounded FMUL/FADD (bit-exact parity), so 50% of the FMA peak is its structural ceiling",
@@ -301,8 +311,8 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(world, args.poses),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * npins * 48) * world, "d2h_bytes_per_step": int(n * nb * 40) * world,
                 "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": args.steps * world,
