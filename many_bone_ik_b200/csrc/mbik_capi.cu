@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -50,6 +51,7 @@ struct DeviceState {
 	float host_path_kernel_ms = -1.f; // sum over the chunks of the last MBIK_IO_HOST call
 	bool last_was_host = false;
 	Lane lanes[kLanes];
+	std::mutex host_mu; // the staging lanes are per (rig, device): concurrent host-I/O calls on one device take turns
 };
 
 } // namespace
@@ -59,7 +61,7 @@ struct mbik_rig {
 	int n_solved = 0;
 	int variant = -1;
 	std::mutex mu;
-	std::map<int, DeviceState> devices;
+	std::map<int, std::unique_ptr<DeviceState>> devices;
 };
 
 namespace {
@@ -99,10 +101,11 @@ int get_device_state(mbik_rig *rig, int device, DeviceState **out) {
 	std::lock_guard<std::mutex> lock(rig->mu);
 	auto it = rig->devices.find(device);
 	if (it != rig->devices.end()) {
-		*out = &it->second;
+		*out = it->second.get();
 		return MBIK_OK;
 	}
-	DeviceState ds;
+	std::unique_ptr<DeviceState> owner(new DeviceState());
+	DeviceState &ds = *owner;
 	ds.device = device;
 	cudaError_t e = cudaMalloc((void **)&ds.blob, rig->flat.blob.size());
 	if (e != cudaSuccess) {
@@ -135,8 +138,8 @@ int get_device_state(mbik_rig *rig, int device, DeviceState **out) {
 		free_device_state(ds);
 		return cuda_fail(e, "stream/event creation");
 	}
-	auto ins = rig->devices.emplace(device, ds);
-	*out = &ins.first->second;
+	*out = owner.get();
+	rig->devices.emplace(device, std::move(owner));
 	return MBIK_OK;
 }
 
@@ -220,6 +223,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 
 	// Host buffers: the batch is cut into chunks of whole kernel waves and streamed through kLanes staging
 	// lanes, so the H2D copy of chunk i+1, the solve of chunk i and the D2H copy of chunk i-1 overlap.
+	std::lock_guard<std::mutex> host_lock(ds->host_mu);
 	const size_t wave = (size_t)(ds->sm_count > 0 ? ds->sm_count : 148) * mbik::kBlockThreads;
 	size_t chunk = 2 * wave;
 	if (const char *env = getenv("MBIK_CHUNK_POSES")) {
@@ -388,7 +392,7 @@ int mbik_rig_destroy(mbik_rig *rig) {
 		return MBIK_OK;
 	}
 	for (auto &kv : rig->devices) {
-		free_device_state(kv.second);
+		free_device_state(*kv.second);
 	}
 	delete rig;
 	return MBIK_OK;
@@ -566,17 +570,17 @@ int mbik_last_kernel_ms(mbik_rig *rig, int32_t device, float *out_ms) {
 	}
 	std::lock_guard<std::mutex> lock(rig->mu);
 	auto it = rig->devices.find(device);
-	if (it != rig->devices.end() && it->second.last_was_host && it->second.host_path_kernel_ms >= 0.f) {
-		*out_ms = it->second.host_path_kernel_ms;
+	if (it != rig->devices.end() && it->second->last_was_host && it->second->host_path_kernel_ms >= 0.f) {
+		*out_ms = it->second->host_path_kernel_ms;
 		return MBIK_OK;
 	}
-	if (it == rig->devices.end() || !it->second.timed) {
+	if (it == rig->devices.end() || !it->second->timed) {
 		return fail(MBIK_ERR_INVALID_ARG, "no launch recorded on that device");
 	}
 	cudaSetDevice(device);
-	cudaError_t e = cudaEventSynchronize(it->second.ev_stop);
+	cudaError_t e = cudaEventSynchronize(it->second->ev_stop);
 	if (e == cudaSuccess) {
-		e = cudaEventElapsedTime(out_ms, it->second.ev_start, it->second.ev_stop);
+		e = cudaEventElapsedTime(out_ms, it->second->ev_start, it->second->ev_stop);
 	}
 	if (e != cudaSuccess) {
 		return cuda_fail(e, "event timing");
