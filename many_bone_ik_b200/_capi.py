@@ -57,7 +57,7 @@ EXPORTED_SYMBOLS = [
     "mbik_device_count", "mbik_strerror", "mbik_last_error", "mbik_rig_create", "mbik_rig_destroy",
     "mbik_rig_get_info", "mbik_rig_get_bone_order", "mbik_rig_get_step_weights", "mbik_rig_get_bone_frames",
     "mbik_rig_get_cone_geometry", "mbik_solve_batch", "mbik_solve_batch_multi", "mbik_alloc_pinned",
-    "mbik_free_pinned", "mbik_last_kernel_ms", "mbik_measure_fp32_tflops",
+    "mbik_free_pinned", "mbik_last_kernel_ms", "mbik_measure_fp32_tflops", "mbik_selftest",
 ]
 
 
@@ -139,5 +139,6 @@ def load_library():
     lib.mbik_free_pinned.argtypes = [vp]
     lib.mbik_last_kernel_ms.argtypes = [vp, C.c_int32, fp]
     lib.mbik_measure_fp32_tflops.argtypes = [C.c_int32, C.c_int32, dp]
+    lib.mbik_selftest.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib

@@ -179,8 +179,10 @@ def test_invalid_device_ordinal():
 
 
 def _quat_angle(qa, qb):
-    d = np.abs(np.sum(qa.astype(np.float64) * qb.astype(np.float64), axis=-1))
-    return 2.0 * np.arccos(np.clip(d, 0.0, 1.0))
+    # angle between two unit quaternions (double cover aware); asin form is accurate near 0, unlike acos(dot)
+    a, b = qa.astype(np.float64), qb.astype(np.float64)
+    d = np.minimum(np.linalg.norm(a - b, axis=-1), np.linalg.norm(a + b, axis=-1))
+    return 4.0 * np.arcsin(np.clip(d / 2.0, 0.0, 1.0))
 
 
 @pytest.mark.parametrize("name", ["humanoid22", "chain64", "quad80"])
@@ -228,3 +230,16 @@ def test_large_batch_properties_at_bench_size():
     qn = np.linalg.norm(out[..., 3:7].astype(np.float64), axis=-1)
     assert np.all(np.abs(qn - 1.0) < 1e-5)
     assert not st.any()
+
+
+def test_guarded_sqrt_div_groups_are_correctly_rounded():
+    """The kernel's grouped sqrt/division sequences (mbik_math.cuh) == __fsqrt_rn/__fdiv_rn bit for bit: sqrt
+    exhaustively over [2^-80, 2^80), division over all 2^23 divisor mantissas x 4 rounds x 64 numerators,
+    plus random vectors (zeros, denormals, inf/NaN included) through vnorm / q_normalized / sqrt_then_div."""
+    import ctypes as C
+    lib = _capi.load_library()
+    n, bad = C.c_uint64(0), C.c_uint64(0)
+    rc = lib.mbik_selftest(0, 4, C.byref(n), C.byref(bad))
+    assert rc == 0
+    assert n.value > 3_000_000_000, n.value
+    assert bad.value == 0, f"{bad.value} mismatches out of {n.value}"
