@@ -372,3 +372,44 @@ def random_targets(rig: Rig, first_pose: int, n_poses: int, pos_range=0.3, max_a
         out[:, e, :9] = Rt.reshape(n_poses, 9).astype(np.float32)
         out[:, e, 9:] = (t0[None] + dpos).astype(np.float32)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# text forms consumed by the C++ host facade (many_bone_ik_b200/host/many_bone_ik_host.hpp)
+# ---------------------------------------------------------------------------------------------
+def _f(x):
+    return repr(float(np.float32(x)))  # shortest decimal that round-trips the float32 value via double
+
+
+def to_skeleton_text(rig: Rig) -> str:
+    """`n_bones`, then one line per bone: name parent 12 floats (Transform3D memory layout)."""
+    lines = [str(rig.n_bones)]
+    for b in range(rig.n_bones):
+        lines.append(" ".join([rig.bone_names[b], str(int(rig.parent[b]))] + [_f(v) for v in rig.rest_local[b]]))
+    return "\n".join(lines) + "\n"
+
+
+def to_property_text(rig: Rig) -> str:
+    """The rig's tables as the `key = value` property lines a Godot .tscn stores for a ManyBoneIK3D node
+    (property names of ManyBoneIK3D::_set, reference src/many_bone_ik_3d.cpp:296-375)."""
+    out = ['[node name="ManyBoneIK3D" type="ManyBoneIK3D" parent="."]',
+           f"iterations_per_frame = {float(rig.iterations)}", f"default_damp = {_f(rig.default_damp)}",
+           f"constraint_mode = {'true' if rig.constraint_mode else 'false'}", f"stabilization_passes = {int(rig.stabilization_passes)}",
+           f"pin_count = {len(rig.pins)}"]
+    for i, p in enumerate(rig.pins):
+        name = rig.bone_names[p["bone"]] if 0 <= p["bone"] < rig.n_bones else "NoSuchBone"
+        out += [f'pins/{i}/bone_name = &"{name}"', f'pins/{i}/target_node = NodePath("../Targets/{name}")',
+                f"pins/{i}/motion_propagation_factor = {_f(p['mpf'])}", f"pins/{i}/weight = {_f(p['weight'])}",
+                "pins/%d/direction_priorities = Vector3(%s, %s, %s)" % ((i,) + tuple(_f(v) for v in p["priorities"]))]
+    out.append(f"constraint_count = {len(rig.constraints)}")
+    for i, c in enumerate(rig.constraints):
+        out += [f'constraints/{i}/bone_name = &"{rig.bone_names[c["bone"]]}"', f"constraints/{i}/twist_from = {_f(c['twist_from'])}",
+                f"constraints/{i}/twist_range = {_f(c['twist_range'])}", f"constraints/{i}/kusudama_open_cone_count = {len(c['cones'])}"]
+        for j, (cx, cy, cz, r) in enumerate(c["cones"]):
+            out += [f"constraints/{i}/kusudama_open_cone/{j}/center = Vector3({_f(cx)}, {_f(cy)}, {_f(cz)})",
+                    f"constraints/{i}/kusudama_open_cone/{j}/radius = {_f(r)}"]
+        out.append(f"constraints/{i}/kusudama_twist = Transform3D(1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0)")
+    if len(rig.bone_damp):
+        out.append(f"bone_count = {len(rig.bone_damp)}")
+        out += [f"bone_damp/{i} = {_f(v)}" for i, v in enumerate(rig.bone_damp)]
+    return "\n".join(out) + "\n"

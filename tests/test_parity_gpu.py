@@ -243,3 +243,23 @@ def test_guarded_sqrt_div_groups_are_correctly_rounded():
     assert rc == 0
     assert n.value > 3_000_000_000, n.value
     assert bad.value == 0, f"{bad.value} mismatches out of {n.value}"
+
+
+@pytest.mark.parametrize("name", ["humanoid22", "chain64", "star_mixed_pins"])
+def test_cpp_facade_solve_equals_c_abi_solve(tmp_path, name):
+    """The reference-named C++ front end (ManyBoneIK3D setters / .tscn property paths ->
+    process_modification_batch) produces the same bits as the direct C-ABI path and the oracle."""
+    from test_host_facade_cpu import build_driver, run_driver
+    cases = dict(rigs.RIGS)
+    cases.update(rig_cases.EDGE_RIGS)
+    rig = cases[name]()
+    exe = build_driver(tmp_path)
+    n = 200
+    T = rigs.random_targets(rig, 0, n)
+    tb, ob = os.path.join(str(tmp_path), "t.bin"), os.path.join(str(tmp_path), "o.bin")
+    T.tofile(tb)
+    rc, facts, log = run_driver(exe, tmp_path, rig, [tb, ob, str(n)])
+    assert rc == 0 and int(facts["solve"]) == 0, log
+    got = np.fromfile(ob, np.float32).reshape(n, rig.n_bones, 10)
+    ref_out, ref_st = O.solve_batch(rig, T, threads=8)
+    assert np.array_equal(got, ref_out, equal_nan=True)
