@@ -203,6 +203,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 	a.blob_bytes = (uint32_t)F.blob.size();
 	a.iterations = iterations;
 	a.n_poses = n_poses;
+	a.stabilize = F.stabilization_passes > 0 ? 1 : 0;
 
 	if (flags & MBIK_IO_DEVICE) {
 		a.targets = targets;
@@ -376,8 +377,12 @@ int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
 		return fail(MBIK_ERR_UNSUPPORTED, "rig exceeds the largest kernel variant (128 solved bones, walk stack depth 16)");
 	}
 	if (desc->stabilization_passes > 0) {
-		delete rig;
-		return fail(MBIK_ERR_UNSUPPORTED, "stabilization_passes > 0 is not implemented yet (reference default is 0)");
+		for (int si : rig->flat.root_segments) {
+			if ((int)rig->flat.segments[si].effectors.size() > mbik::kMaxStabEffectors) {
+				delete rig;
+				return fail(MBIK_ERR_UNSUPPORTED, "stabilization_passes > 0 supports at most 32 effectors per root segment");
+			}
+		}
 	}
 	if (rig->flat.blob.size() > 200 * 1024) {
 		delete rig;

@@ -885,6 +885,7 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	hdr.iterations = R.iterations;
 	hdr.constraint_mode = d->constraint_mode;
 	hdr.stabilization_passes = d->stabilization_passes;
+	R.stabilization_passes = d->stabilization_passes;
 	hdr.n_chain = (int)R.chain.size();
 	hdr.max_seg_len = R.max_seg_len;
 	hdr.max_stack = R.max_stack;

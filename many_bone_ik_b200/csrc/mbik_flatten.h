@@ -53,6 +53,7 @@ struct FlatRig {
 	int n_effectors = 0;
 	int n_kept_segments = 0;
 	int iterations = 15;
+	int stabilization_passes = 0;
 	double flops_per_solve = 0;
 	std::string error;
 };

@@ -369,6 +369,7 @@ struct HeadingAcc {
 	V3 csum_m, csum_t;    // pass 0: weighted sums of the tip / target headings
 	V3 neg_mc, neg_tc;    // pass 1 when translating: -centroids
 	V3 last_t, last_m;    // the single heading of a 1-heading list
+	float msd, msd_wsum;  // pass 2 (stabilisation): _get_manual_msd accumulators (float, src/ik_bone_segment_3d.cpp:114-127)
 };
 
 __device__ __forceinline__ void heading_emit(HeadingAcc &A, int pass_i, bool translate, V3 th, V3 mh, double w) {
@@ -376,6 +377,11 @@ __device__ __forceinline__ void heading_emit(HeadingAcc &A, int pass_i, bool tra
 		A.total_w = r_add(A.total_w, w);
 		A.csum_m = vadd(A.csum_m, vmuls(mh, (float)w));
 		A.csum_t = vadd(A.csum_t, vmuls(th, (float)w));
+	} else if (pass_i == 2) { // IKBoneSegment3D::_get_manual_msd: float accumulators, double weight
+		float xd = r_sub(th.x, mh.x), yd = r_sub(th.y, mh.y), zd = r_sub(th.z, mh.z);
+		float d2 = r_add(r_add(r_mul(xd, xd), r_mul(yd, yd)), r_mul(zd, zd));
+		A.msd = r_add(A.msd, (float)r_mul(w, (double)d2));
+		A.msd_wsum = (float)r_add((double)A.msd_wsum, w);
 	} else {
 		if (translate) { // QCP::translate (:129-133) with -centroid
 			mh = vadd(mh, A.neg_mc);
@@ -388,13 +394,14 @@ __device__ __forceinline__ void heading_emit(HeadingAcc &A, int pass_i, bool tra
 }
 
 // Ge = global transform of the effector's bone, De = its bone-direction local basis, T = its target,
-// bo = origin of the SOLVED bone's bone-direction frame
+// bo = origin of the SOLVED bone's bone-direction frame, tgtO = effector-bone origin the TARGET headings are taken
+// from (= xform_zero(Ge), except in the stabilisation pass where target headings date from before the step)
 __device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, bool translate, const BlobEff &E, const X34 &Ge, const M3 &De,
-		const X34 &T, V3 bo) {
+		const X34 &T, V3 bo, V3 tgtO) {
 	const M3 tipB = m3_mul(Ge.b, De);
 	const V3 tipO = xform_zero(Ge);
 	// heading 0: origins.  Target heading is taken from the EFFECTOR's own bone (:97), tip heading from the solved bone (:125)
-	V3 th = vsub(T.o, tipO);
+	V3 th = vsub(T.o, tgtO);
 	V3 mh = vsub(tipO, bo);
 	float dist = vlen(vsub(bo, T.o));
 	float scale_by = dist < 1.0f ? dist : 1.0f; // MIN(distance, 1.0f)
@@ -405,9 +412,9 @@ __device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, boo
 			const double wd = E.w_axis[ax];
 			const float w = (float)wd;
 			V3 col = m3_col(T.b, ax);
-			V3 thp = vsub(vadd(col, T.o), tipO);
+			V3 thp = vsub(vadd(col, T.o), tgtO);
 			thp = v3(r_mul(thp.x, w), r_mul(thp.y, w), r_mul(thp.z, w));
-			V3 thm = vsub(vsub(T.o, col), tipO);
+			V3 thm = vsub(vsub(T.o, col), tgtO);
 			thm = v3(r_mul(thm.x, w), r_mul(thm.y, w), r_mul(thm.z, w));
 			V3 tcol = vmuls(m3_col(tipB, ax), E.prio[ax]);
 			V3 mhp = vmuls(vsub(vadd(tcol, tipO), bo), scale_by);
@@ -421,7 +428,7 @@ __device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, boo
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int NB, int NSEG, int NSTK, int THREADS>
+template <int NB, int NSEG, int NSTK, int THREADS, bool STAB>
 __global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel(SolveArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t bar;
@@ -472,6 +479,10 @@ __global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel(SolveArgs a) {
 	float Pseg[NSEG * 12]; // globals of the parents of the current segment's bones (ancestors do not move while a
 	                       // segment is being solved, so this replaces the reference's lazy global-transform cache)
 	float Gstk[NSTK * 12]; // globals of the branch points of the current downward walk
+	// stabilisation only (STAB variants): effector-bone origins from before the step (what the step's target
+	// headings were built from) and the segment's previous_deviation (src/ik_bone_segment_3d.h:63)
+	float TipO[STAB ? kMaxStabEffectors * 3 : 1];
+	double prev_dev = (double)INFINITY;
 
 	// seed: ManyBoneIK3D::_update_ik_bones_transform -> IKBone3D::set_initial_pose (src/ik_bone_3d.cpp:161-168)
 	for (int t = 0; t < ns; t++) {
@@ -538,7 +549,11 @@ __global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel(SolveArgs a) {
 					A.csum_m = A.csum_t = v3(0.0f, 0.0f, 0.0f);
 					if (flags & STEP_SELF_EFF) {
 						const BlobEff &E = effs[S.eff_off];
-						effector_headings(A, pass_i, translate, E, Gb, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo);
+						const V3 tO = xform_zero(Gb);
+						if (STAB) {
+							TipO[0] = tO.x; TipO[1] = tO.y; TipO[2] = tO.z;
+						}
+						effector_headings(A, pass_i, translate, E, Gb, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, tO);
 					}
 					// depth-first walk down to the effectors of this segment's list: the lazily re-derived global
 					// transforms of the reference (src/math/ik_node_3d.cpp:93-113) as explicit running products
@@ -554,7 +569,11 @@ __global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel(SolveArgs a) {
 						}
 						if (op.eff >= 0) {
 							const BlobEff &E = effs[S.eff_off + op.eff];
-							effector_headings(A, pass_i, translate, E, run, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo);
+							const V3 tO = xform_zero(run);
+							if (STAB) {
+								TipO[3 * op.eff] = tO.x; TipO[3 * op.eff + 1] = tO.y; TipO[3 * op.eff + 2] = tO.z;
+							}
+							effector_headings(A, pass_i, translate, E, run, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, tO);
 						}
 					}
 					if (pass_i == 0) {
@@ -591,6 +610,32 @@ __global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel(SolveArgs a) {
 				}
 			}
 
+			if (STAB && constraint_mode && (flags & STEP_STABILIZE)) {
+				// constraint mode skips the QCP passes, but the step's target headings still date from here (:135)
+				if (flags & STEP_SELF_EFF) {
+					const V3 tO = xform_zero(Gb);
+					TipO[0] = tO.x; TipO[1] = tO.y; TipO[2] = tO.z;
+				}
+				if (flags & STEP_PUSH_SELF) {
+					st_x34(Gstk, 0, Gb);
+				}
+				X34 run = Gb;
+				for (int k = 0; k < S.fk_cnt; k++) {
+					const BlobFk op = fk[S.fk_off + k];
+					if (op.src_slot >= 0) {
+						run = ld_x34(Gstk, op.src_slot);
+					}
+					run = x_mul(run, ld_x34(L, op.child));
+					if (op.push_slot >= 0) {
+						st_x34(Gstk, op.push_slot, run);
+					}
+					if (op.eff >= 0) {
+						const V3 tO = xform_zero(run);
+						TipO[3 * op.eff] = tO.x; TipO[3 * op.eff + 1] = tO.y; TipO[3 * op.eff + 2] = tO.z;
+					}
+				}
+			}
+
 			if (flags & STEP_IK_PARENT) {
 				if (flags & STEP_SWING) {
 					// constraint-orientation node: child of the parent's aligned node; its local origin tracks the
@@ -615,6 +660,52 @@ __global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel(SolveArgs a) {
 				}
 				if (flags & STEP_TWIST) {
 					Lb.b = twist_snap(P.b, Pinv, Lb.b, ld_m3(B.twist_basis), ld_m3(B.twist_center), B.twist_cos);
+				}
+			}
+			if (STAB) {
+				if (flags & STEP_STABILIZE) {
+					// stabilisation (:163-176): MSD between the step's target headings and the tip headings of the
+					// new pose; if it did not get closer the bone's local pose is reverted.  Further passes of the
+					// reference's do-while repeat the identical computation from the restored pose, so one attempt
+					// followed by accept/revert is the whole loop.
+					const X34 Gp = node_parent ? x_mul(P, Lb) : Lb;
+					const V3 bo2 = xform_zero(Gp);
+					HeadingAcc A;
+					A.msd = 0.0f;
+					A.msd_wsum = 0.0f;
+					if (flags & STEP_SELF_EFF) {
+						const BlobEff &E = effs[S.eff_off];
+						effector_headings(A, 2, false, E, Gp, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo2,
+								v3(TipO[0], TipO[1], TipO[2]));
+					}
+					if (flags & STEP_PUSH_SELF) {
+						st_x34(Gstk, 0, Gp);
+					}
+					X34 run = Gp;
+					for (int k = 0; k < S.fk_cnt; k++) {
+						const BlobFk op = fk[S.fk_off + k];
+						if (op.src_slot >= 0) {
+							run = ld_x34(Gstk, op.src_slot);
+						}
+						run = x_mul(run, ld_x34(L, op.child));
+						if (op.push_slot >= 0) {
+							st_x34(Gstk, op.push_slot, run);
+						}
+						if (op.eff >= 0) {
+							const BlobEff &E = effs[S.eff_off + op.eff];
+							effector_headings(A, 2, false, E, run, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo2,
+									v3(TipO[3 * op.eff], TipO[3 * op.eff + 1], TipO[3 * op.eff + 2]));
+						}
+					}
+					const double current_msd = (double)r_div(A.msd, r_mul(A.msd_wsum, A.msd_wsum));
+					if (current_msd <= r_mul(prev_dev, 1.0001)) {
+						prev_dev = current_msd;
+					} else {
+						Lb = ld_x34(L, b); // IKBone3D::set_pose(prev_transform)
+					}
+				}
+				if (flags & STEP_SEG_ROOT) {
+					prev_dev = (double)INFINITY; // :178-180
 				}
 			}
 			st_x34(L, b, Lb);
@@ -651,15 +742,15 @@ __global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel(SolveArgs a) {
 // ---------------------------------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------------------------------
-template <int NB, int NSEG, int NSTK, int THREADS>
+template <int NB, int NSEG, int NSTK, int THREADS, bool STAB = false>
 static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 	size_t smem = a.blob_bytes;
-	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel<NB, NSEG, NSTK, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel<NB, NSEG, NSTK, THREADS, STAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) {
 		return e;
 	}
 	unsigned grid = (unsigned)((a.n_poses + THREADS - 1) / THREADS);
-	mbik_solve_kernel<NB, NSEG, NSTK, THREADS><<<grid, THREADS, smem, stream>>>(a);
+	mbik_solve_kernel<NB, NSEG, NSTK, THREADS, STAB><<<grid, THREADS, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 
@@ -678,6 +769,18 @@ int kernel_variant_for(int n_solved, int max_seg_len, int max_stack) {
 int kernel_capacity_of_variant(int v) { return (v >= 0 && v < 3) ? kVariants[v][0] : -1; }
 
 cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStream_t stream) {
+	if (a.stabilize) { // stabilisation passes > 0: separate instantiations, the default path pays nothing for them
+		switch (variant) {
+			case 0:
+				return launch_variant<20, 8, 4, kStabBlockThreads, true>(a, stream);
+			case 1:
+				return launch_variant<64, 16, 8, kStabBlockThreads, true>(a, stream);
+			case 2:
+				return launch_variant<128, 128, 16, kStabBlockThreads, true>(a, stream);
+			default:
+				return cudaErrorInvalidValue;
+		}
+	}
 	switch (variant) {
 		case 0: {
 			// Small batches: one CTA per SM with as few warps as cover the batch (a 4096-pose batch runs as 128

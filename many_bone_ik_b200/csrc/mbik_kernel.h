@@ -7,6 +7,8 @@
 namespace mbik {
 
 constexpr int kBlockThreads = 384; // poses per CTA: one CTA per SM, all of its warps kept in lockstep
+constexpr int kStabBlockThreads = 256; // CTA size of the stabilisation variants
+constexpr int kMaxStabEffectors = 32;  // effectors per root-segment list the stabilisation variants can hold
 
 struct SolveArgs {
 	const unsigned char *blob; // device copy of the rig blob (16-byte aligned)
@@ -18,6 +20,7 @@ struct SolveArgs {
 	float *out_pose;         // [n_poses][n_bones][10]
 	float *out_local;        // [n_poses][n_bones][12] or nullptr
 	uint32_t *out_status;    // [n_poses] or nullptr
+	int32_t stabilize;       // rig has stabilization_passes > 0 (reference src/ik_bone_segment_3d.cpp:163-176)
 };
 
 // index of the smallest kernel variant that fits the rig, or -1 if none does

@@ -89,7 +89,55 @@ def humanoid_constraint_mode():
     return r
 
 
-EDGE_RIGS = {f.__name__: f for f in [chain_multibone_root, chain_diverging, two_roots, star_mixed_pins, humanoid_no_constraints, humanoid_constraint_mode]}
+def humanoid_stabilized():
+    """stabilization_passes = 2 (reference src/ik_bone_segment_3d.cpp:163-176): MSD accept / revert on the root segment."""
+    r = rigs.humanoid22()
+    r.stabilization_passes = 2
+    r.name = "humanoid_stabilized"
+    r.config_id = 17
+    return r
+
+
+def chain64_stabilized():
+    """Root segment of 8 translating bones with a 9-effector list, one stabilisation pass, fewer iterations."""
+    r = rigs.chain64()
+    r.stabilization_passes = 1
+    r.iterations = 6
+    r.name = "chain64_stabilized"
+    r.config_id = 18
+    return r
+
+
+def star_stabilized_constraint_mode():
+    """constraint_mode + stabilisation: no QCP, snaps only, MSD still evaluated against the step's target headings."""
+    r = star_mixed_pins()
+    r.stabilization_passes = 3
+    r.constraint_mode = True
+    r.name = "star_stabilized_constraint_mode"
+    r.config_id = 19
+    return r
+
+
+def chain_multibone_root_stabilized():
+    """Multi-bone translating root segment where stabilisation actually reverts steps."""
+    r = chain_multibone_root(12, iterations=5)
+    r.stabilization_passes = 2
+    r.name = "chain_multibone_root_stabilized"
+    r.config_id = 21
+    return r
+
+
+def two_roots_stabilized():
+    r = two_roots()
+    r.stabilization_passes = 1
+    r.name = "two_roots_stabilized"
+    r.config_id = 20
+    return r
+
+
+EDGE_RIGS = {f.__name__: f for f in [chain_multibone_root, chain_diverging, two_roots, star_mixed_pins, humanoid_no_constraints, humanoid_constraint_mode,
+                                     humanoid_stabilized, chain64_stabilized, star_stabilized_constraint_mode, two_roots_stabilized,
+                                     chain_multibone_root_stabilized]}
 
 
 def perturbed_start_pose(rig, n, seed=7, angle_deg=12.0, offset=0.02):
