@@ -153,6 +153,30 @@ int mbik_solve_batch_multi(mbik_rig *rig, const mbik_solve_params *params, size_
 		float *out_pose, float *out_local, uint32_t *out_status,
 		const int32_t *devices, int32_t n_devices);
 
+/*
+ * Warm-start streaming.  The reference re-seeds its IK bones from the skeleton after
+ * every frame (signal modification_processed -> _update_ik_bones_transform, reference src/many_bone_ik_3d.cpp:1084,
+ * :91-102), so frame f+1 starts from frame f's solution.  A stream keeps that state ON THE DEVICE: the raw local
+ * transforms of all `n_poses` skeletons live in a device-resident ping-pong pair, each submitted frame uploads only
+ * the targets, solves with start = previous frame's locals, and (optionally) downloads out_pose.  Frame f+1's
+ * target upload and frame f's pose download overlap the solves.  Results are bit-identical to calling
+ * mbik_solve_batch per frame with start_pose = the previous frame's out_local.
+ */
+typedef struct mbik_stream mbik_stream;
+/* initial_pose: host [n_poses][n_bones][12] or NULL (= the rig's rest pose for every skeleton) */
+int mbik_stream_create(mbik_rig *rig, int32_t device, size_t n_poses, const float *initial_pose, mbik_stream **out_stream);
+int mbik_stream_destroy(mbik_stream *stream);
+/* Enqueue one frame and return.  targets: host [n_poses][n_pins][12]; out_pose / out_status: host buffers or NULL
+ * (NULL = leave the result on the device).  All three must stay valid until mbik_stream_sync(); use pinned memory
+ * for true asynchrony.  iterations < 0 = the rig's iterations_per_frame. */
+int mbik_stream_submit(mbik_stream *stream, const float *targets, float *out_pose, uint32_t *out_status, int32_t iterations);
+int mbik_stream_sync(mbik_stream *stream); /* wait for every submitted frame; returns the first asynchronous error */
+/* Synchronous read-back of the current raw local transforms [n_poses][n_bones][12] (after all submitted frames). */
+int mbik_stream_read_local(mbik_stream *stream, float *out_local);
+/* Re-seed every skeleton (NULL = rest pose), like _bone_list_changed() -> _update_ik_bones_transform(). */
+int mbik_stream_reset(mbik_stream *stream, const float *initial_pose);
+int64_t mbik_stream_frames(const mbik_stream *stream); /* frames submitted so far */
+
 /* Pinned host allocation helpers (so a C caller can get full H2D/D2H bandwidth without linking CUDA). */
 void *mbik_alloc_pinned(size_t bytes);
 void mbik_free_pinned(void *p);

@@ -5,4 +5,4 @@ This package holds the sources (csrc/), the ctypes binding (solver.py, _capi.py)
 generators (rigs.py).  There is no CPU or Python fallback for the solve.
 """
 from . import rigs  # noqa: F401
-from .solver import BatchedIKRig, MbikError, device_count  # noqa: F401
+from .solver import BatchedIKRig, IKStream, MbikError, device_count  # noqa: F401

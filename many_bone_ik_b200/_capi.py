@@ -58,6 +58,8 @@ EXPORTED_SYMBOLS = [
     "mbik_rig_get_info", "mbik_rig_get_bone_order", "mbik_rig_get_step_weights", "mbik_rig_get_bone_frames",
     "mbik_rig_get_cone_geometry", "mbik_solve_batch", "mbik_solve_batch_multi", "mbik_alloc_pinned",
     "mbik_free_pinned", "mbik_last_kernel_ms", "mbik_measure_fp32_tflops", "mbik_selftest",
+    "mbik_stream_create", "mbik_stream_destroy", "mbik_stream_submit", "mbik_stream_sync", "mbik_stream_read_local",
+    "mbik_stream_reset", "mbik_stream_frames",
 ]
 
 
@@ -140,5 +142,13 @@ def load_library():
     lib.mbik_last_kernel_ms.argtypes = [vp, C.c_int32, fp]
     lib.mbik_measure_fp32_tflops.argtypes = [C.c_int32, C.c_int32, dp]
     lib.mbik_selftest.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.mbik_stream_create.argtypes = [vp, C.c_int32, C.c_size_t, vp, C.POINTER(vp)]
+    lib.mbik_stream_destroy.argtypes = [vp]
+    lib.mbik_stream_submit.argtypes = [vp, vp, vp, vp, C.c_int32]
+    lib.mbik_stream_sync.argtypes = [vp]
+    lib.mbik_stream_read_local.argtypes = [vp, vp]
+    lib.mbik_stream_reset.argtypes = [vp, vp]
+    lib.mbik_stream_frames.argtypes = [vp]
+    lib.mbik_stream_frames.restype = C.c_int64
     _lib = lib
     return lib

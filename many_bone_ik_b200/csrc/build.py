@@ -30,6 +30,14 @@ def nvcc_path():
     return "nvcc"
 
 
+OBJ_DIR = os.path.join(HERE, "_obj")
+COMPILE_FLAGS = [f for f in NVCC_FLAGS if f not in ("-shared",)]
+
+
+def _deps_mtime():
+    return max(os.path.getmtime(os.path.join(HERE, h)) for h in HEADERS + [os.path.basename(__file__)])
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
@@ -39,14 +47,35 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile each .cu to an object (only the stale ones, in parallel) and link libmbik.so."""
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_t = _deps_mtime()
+    procs = []
+    objs = []
+    for src in SOURCES:
+        sp = os.path.join(HERE, src)
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), hdr_t):
+            continue
+        cmd = [nvcc_path()] + [f for f in COMPILE_FLAGS if f != "-cudart" and f != "static"] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, sp]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if verbose or pr.returncode != 0:
+            sys.stderr.write(out)
+        failed = failed or pr.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed building libmbik.so")
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-o", OUT] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libmbik.so")
+        raise RuntimeError("nvcc failed linking libmbik.so")
     return OUT
 
 

@@ -64,6 +64,25 @@ struct mbik_rig {
 	std::map<int, std::unique_ptr<DeviceState>> devices;
 };
 
+struct mbik_stream {
+	mbik_rig *rig = nullptr;
+	int device = -1;
+	int sm_count = 148;
+	size_t n_poses = 0;
+	unsigned char *blob = nullptr;    // borrowed from the rig's DeviceState
+	float *local[2] = { nullptr, nullptr }; // ping-pong raw local transforms [n][n_bones][12]
+	int cur = 0;                      // local[cur] holds the latest state
+	float *d_targets[2] = { nullptr, nullptr };
+	float *d_out[2] = { nullptr, nullptr };
+	uint32_t *d_status[2] = { nullptr, nullptr };
+	cudaStream_t s_up = nullptr, s_solve = nullptr, s_down = nullptr;
+	cudaEvent_t ev_up[2] = { nullptr, nullptr };     // targets slot uploaded
+	cudaEvent_t ev_solved[2] = { nullptr, nullptr }; // solve reading/writing slot finished
+	cudaEvent_t ev_down[2] = { nullptr, nullptr };   // out slot downloaded (slot reusable)
+	bool slot_used[2] = { false, false };
+	int64_t frames = 0;
+};
+
 namespace {
 
 void free_device_state(DeviceState &ds) {
@@ -553,6 +572,253 @@ int mbik_solve_batch_multi(mbik_rig *rig, const mbik_solve_params *params, size_
 	}
 	return MBIK_OK;
 }
+
+int mbik_stream_destroy(mbik_stream *st) {
+	if (!st) {
+		return MBIK_OK;
+	}
+	if (st->device >= 0) {
+		cudaSetDevice(st->device);
+		if (st->s_solve) {
+			cudaStreamSynchronize(st->s_up);
+			cudaStreamSynchronize(st->s_solve);
+			cudaStreamSynchronize(st->s_down);
+		}
+		for (int i = 0; i < 2; i++) {
+			cudaFree(st->local[i]);
+			cudaFree(st->d_targets[i]);
+			cudaFree(st->d_out[i]);
+			cudaFree(st->d_status[i]);
+			if (st->ev_up[i]) {
+				cudaEventDestroy(st->ev_up[i]);
+			}
+			if (st->ev_solved[i]) {
+				cudaEventDestroy(st->ev_solved[i]);
+			}
+			if (st->ev_down[i]) {
+				cudaEventDestroy(st->ev_down[i]);
+			}
+		}
+		if (st->s_up) {
+			cudaStreamDestroy(st->s_up);
+		}
+		if (st->s_solve) {
+			cudaStreamDestroy(st->s_solve);
+		}
+		if (st->s_down) {
+			cudaStreamDestroy(st->s_down);
+		}
+	}
+	delete st;
+	return MBIK_OK;
+}
+
+int mbik_stream_reset(mbik_stream *st, const float *initial_pose) {
+	if (!st) {
+		return fail(MBIK_ERR_INVALID_ARG, "stream is NULL");
+	}
+	cudaError_t e = cudaSetDevice(st->device);
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "cudaSetDevice");
+	}
+	int rc = mbik_stream_sync(st);
+	if (rc != MBIK_OK) {
+		return rc;
+	}
+	const mbik::FlatRig &F = st->rig->flat;
+	const size_t row = (size_t)F.n_bones * 12, bytes = st->n_poses * row * sizeof(float);
+	if (initial_pose) {
+		e = cudaMemcpy(st->local[st->cur], initial_pose, bytes, cudaMemcpyHostToDevice);
+	} else {
+		// rest pose for every skeleton: replicate one row (rest_local is the tail section of the blob)
+		std::vector<float> rest(row);
+		for (int b = 0; b < F.n_bones; b++) {
+			memcpy(&rest[(size_t)b * 12], &F.rest_local[b], sizeof(float) * 12);
+		}
+		const size_t chunk = 4096;
+		std::vector<float> tile(chunk * row);
+		for (size_t k = 0; k < chunk; k++) {
+			memcpy(&tile[k * row], rest.data(), row * sizeof(float));
+		}
+		for (size_t k = 0; k < st->n_poses && e == cudaSuccess; k += chunk) {
+			size_t c = st->n_poses - k < chunk ? st->n_poses - k : chunk;
+			e = cudaMemcpy(st->local[st->cur] + k * row, tile.data(), c * row * sizeof(float), cudaMemcpyHostToDevice);
+		}
+	}
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "stream reset");
+	}
+	return MBIK_OK;
+}
+
+int mbik_stream_create(mbik_rig *rig, int32_t device, size_t n_poses, const float *initial_pose, mbik_stream **out_stream) {
+	if (!rig || !out_stream || n_poses == 0) {
+		return fail(MBIK_ERR_INVALID_ARG, "rig/out_stream is NULL or n_poses is 0");
+	}
+	*out_stream = nullptr;
+	mbik_solve_params p;
+	p.iterations = -1;
+	p.device = device;
+	p.flags = 0;
+	p.stream = nullptr;
+	int dev = -1;
+	int rc = resolve_device(&p, &dev);
+	if (rc != MBIK_OK) {
+		return rc;
+	}
+	cudaError_t e = cudaSetDevice(dev);
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "cudaSetDevice");
+	}
+	DeviceState *ds = nullptr;
+	if ((rc = get_device_state(rig, dev, &ds)) != MBIK_OK) {
+		return rc;
+	}
+	mbik_stream *st = new (std::nothrow) mbik_stream();
+	if (!st) {
+		return fail(MBIK_ERR_ALLOC, "out of memory");
+	}
+	st->rig = rig;
+	st->device = dev;
+	st->sm_count = ds->sm_count;
+	st->n_poses = n_poses;
+	st->blob = ds->blob;
+	const mbik::FlatRig &F = rig->flat;
+	const size_t nb = (size_t)F.n_bones, np = F.pins.size();
+	for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+		e = cudaMalloc((void **)&st->local[i], n_poses * nb * 12 * sizeof(float));
+		if (e == cudaSuccess) {
+			e = cudaMalloc((void **)&st->d_targets[i], (np ? n_poses * np * 12 : 4) * sizeof(float));
+		}
+		if (e == cudaSuccess) {
+			e = cudaMalloc((void **)&st->d_out[i], n_poses * nb * 10 * sizeof(float));
+		}
+		if (e == cudaSuccess) {
+			e = cudaMalloc((void **)&st->d_status[i], n_poses * sizeof(uint32_t));
+		}
+		if (e == cudaSuccess) {
+			e = cudaEventCreateWithFlags(&st->ev_up[i], cudaEventDisableTiming);
+		}
+		if (e == cudaSuccess) {
+			e = cudaEventCreateWithFlags(&st->ev_solved[i], cudaEventDisableTiming);
+		}
+		if (e == cudaSuccess) {
+			e = cudaEventCreateWithFlags(&st->ev_down[i], cudaEventDisableTiming);
+		}
+	}
+	if (e == cudaSuccess) {
+		e = cudaStreamCreateWithFlags(&st->s_up, cudaStreamNonBlocking);
+	}
+	if (e == cudaSuccess) {
+		e = cudaStreamCreateWithFlags(&st->s_solve, cudaStreamNonBlocking);
+	}
+	if (e == cudaSuccess) {
+		e = cudaStreamCreateWithFlags(&st->s_down, cudaStreamNonBlocking);
+	}
+	if (e != cudaSuccess) {
+		mbik_stream_destroy(st);
+		return cuda_fail(e, "stream allocation");
+	}
+	rc = mbik_stream_reset(st, initial_pose);
+	if (rc != MBIK_OK) {
+		mbik_stream_destroy(st);
+		return rc;
+	}
+	*out_stream = st;
+	return MBIK_OK;
+}
+
+int mbik_stream_submit(mbik_stream *st, const float *targets, float *out_pose, uint32_t *out_status, int32_t iterations) {
+	if (!st || (!targets && !st->rig->flat.pins.empty())) {
+		return fail(MBIK_ERR_INVALID_ARG, "stream/targets is NULL");
+	}
+	cudaError_t e = cudaSetDevice(st->device);
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "cudaSetDevice");
+	}
+	const mbik::FlatRig &F = st->rig->flat;
+	const size_t nb = (size_t)F.n_bones, np = F.pins.size(), n = st->n_poses;
+	const int slot = (int)(st->frames & 1);
+	// the slot's previous frame (f-2) must have finished downloading before its buffers are overwritten
+	if (st->slot_used[slot]) {
+		cudaStreamWaitEvent(st->s_up, st->ev_solved[slot], 0);   // targets[slot] no longer read
+		cudaStreamWaitEvent(st->s_solve, st->ev_down[slot], 0);  // out[slot] no longer being copied
+	}
+	if (np) {
+		cudaMemcpyAsync(st->d_targets[slot], targets, n * np * 12 * sizeof(float), cudaMemcpyHostToDevice, st->s_up);
+	}
+	cudaEventRecord(st->ev_up[slot], st->s_up);
+	cudaStreamWaitEvent(st->s_solve, st->ev_up[slot], 0);
+	mbik::SolveArgs a;
+	a.blob = st->blob;
+	a.blob_bytes = (uint32_t)F.blob.size();
+	a.iterations = iterations >= 0 ? iterations : F.iterations;
+	a.n_poses = n;
+	a.stabilize = F.stabilization_passes > 0 ? 1 : 0;
+	a.targets = st->d_targets[slot];
+	a.start_pose = st->local[st->cur];
+	a.out_pose = st->d_out[slot];
+	a.out_local = st->local[st->cur ^ 1];
+	a.out_status = st->d_status[slot];
+	e = mbik::launch_solve(a, st->rig->variant, st->sm_count, st->s_solve);
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "kernel launch");
+	}
+	cudaEventRecord(st->ev_solved[slot], st->s_solve);
+	st->cur ^= 1;
+	cudaStreamWaitEvent(st->s_down, st->ev_solved[slot], 0);
+	if (out_pose) {
+		cudaMemcpyAsync(out_pose, st->d_out[slot], n * nb * 10 * sizeof(float), cudaMemcpyDeviceToHost, st->s_down);
+	}
+	if (out_status) {
+		cudaMemcpyAsync(out_status, st->d_status[slot], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st->s_down);
+	}
+	cudaEventRecord(st->ev_down[slot], st->s_down);
+	st->slot_used[slot] = true;
+	st->frames++;
+	e = cudaGetLastError();
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "stream submit");
+	}
+	return MBIK_OK;
+}
+
+int mbik_stream_sync(mbik_stream *st) {
+	if (!st) {
+		return fail(MBIK_ERR_INVALID_ARG, "stream is NULL");
+	}
+	cudaError_t e = cudaSetDevice(st->device);
+	if (e == cudaSuccess) {
+		e = cudaStreamSynchronize(st->s_up);
+	}
+	if (e == cudaSuccess) {
+		e = cudaStreamSynchronize(st->s_solve);
+	}
+	if (e == cudaSuccess) {
+		e = cudaStreamSynchronize(st->s_down);
+	}
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "stream sync");
+	}
+	return MBIK_OK;
+}
+
+int mbik_stream_read_local(mbik_stream *st, float *out_local) {
+	if (!st || !out_local) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	int rc = mbik_stream_sync(st);
+	if (rc != MBIK_OK) {
+		return rc;
+	}
+	cudaError_t e = cudaMemcpy(out_local, st->local[st->cur], st->n_poses * (size_t)st->rig->flat.n_bones * 12 * sizeof(float), cudaMemcpyDeviceToHost);
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "read_local");
+	}
+	return MBIK_OK;
+}
+
+int64_t mbik_stream_frames(const mbik_stream *st) { return st ? st->frames : 0; }
 
 void *mbik_alloc_pinned(size_t bytes) {
 	void *p = nullptr;

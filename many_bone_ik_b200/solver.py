@@ -136,3 +136,71 @@ class BatchedIKRig:
         if rc != 0:
             raise MbikError(rc, "mbik_last_kernel_ms")
         return float(ms.value)
+
+
+class IKStream:
+    """Warm-start streaming (include/mbik.h, mbik_stream_*): the poses of `n_poses` skeletons stay resident on the
+    device; every frame uploads targets only and starts from the previous frame's solution, as the reference
+    re-seeds its IK bones from the skeleton after each frame (src/many_bone_ik_3d.cpp:1084, :91-102)."""
+
+    def __init__(self, rig: BatchedIKRig, n_poses, device=0, initial_pose=None):
+        self.lib = rig.lib
+        self.rig = rig
+        self.n = int(n_poses)
+        if initial_pose is not None:
+            initial_pose = np.ascontiguousarray(initial_pose, np.float32)
+            if initial_pose.shape != (self.n, rig.n_bones, 12):
+                raise ValueError(f"initial_pose must be [{self.n}, {rig.n_bones}, 12]")
+        h = C.c_void_p()
+        rc = self.lib.mbik_stream_create(rig.handle, int(device), self.n, _ptr(initial_pose), C.byref(h))
+        if rc != 0:
+            raise MbikError(rc, "mbik_stream_create")
+        self.handle = h
+        self._keep = []
+
+    def submit(self, targets, out_pose=None, out_status=None, iterations=-1):
+        """Asynchronous: buffers must stay alive until sync() (they are kept referenced here)."""
+        if isinstance(targets, np.ndarray):
+            targets = np.ascontiguousarray(targets, np.float32)
+            if targets.shape != (self.n, self.rig.n_pins, 12):
+                raise ValueError(f"targets must be [{self.n}, {self.rig.n_pins}, 12]")
+        self._keep.append((targets, out_pose, out_status))
+        rc = self.lib.mbik_stream_submit(self.handle, _ptr(targets), _ptr(out_pose), _ptr(out_status), int(iterations))
+        if rc != 0:
+            raise MbikError(rc, "mbik_stream_submit")
+
+    def sync(self):
+        rc = self.lib.mbik_stream_sync(self.handle)
+        self._keep.clear()
+        if rc != 0:
+            raise MbikError(rc, "mbik_stream_sync")
+
+    def read_local(self):
+        out = np.empty((self.n, self.rig.n_bones, 12), np.float32)
+        rc = self.lib.mbik_stream_read_local(self.handle, _ptr(out))
+        self._keep.clear()
+        if rc != 0:
+            raise MbikError(rc, "mbik_stream_read_local")
+        return out
+
+    def reset(self, initial_pose=None):
+        if initial_pose is not None:
+            initial_pose = np.ascontiguousarray(initial_pose, np.float32)
+        rc = self.lib.mbik_stream_reset(self.handle, _ptr(initial_pose))
+        if rc != 0:
+            raise MbikError(rc, "mbik_stream_reset")
+
+    @property
+    def frames(self):
+        return int(self.lib.mbik_stream_frames(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mbik_stream_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

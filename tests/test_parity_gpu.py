@@ -263,3 +263,40 @@ def test_cpp_facade_solve_equals_c_abi_solve(tmp_path, name):
     got = np.fromfile(ob, np.float32).reshape(n, rig.n_bones, 10)
     ref_out, ref_st = O.solve_batch(rig, T, threads=8)
     assert np.array_equal(got, ref_out, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["humanoid22", "quad80"])
+def test_warm_start_stream_equals_per_frame_calls(name):
+    """mbik_stream_*: device-resident frame-to-frame warm start == per-frame mbik_solve_batch with
+    start_pose = previous out_local == the oracle re-seeded from the previous frame (5 frames, pipelined)."""
+    from many_bone_ik_b200 import IKStream
+    rig = rigs.RIGS[name]()
+    R = BatchedIKRig(rig)
+    n, frames = 300, 5
+    S = IKStream(R, n, device=0)
+    Ts = [rigs.random_targets(rig, 777 * f, n) for f in range(frames)]
+    outs = [np.empty((n, rig.n_bones, 10), np.float32) for _ in range(frames)]
+    sts = [np.empty(n, np.uint32) for _ in range(frames)]
+    for f in range(frames):  # all frames in flight before the first sync
+        S.submit(Ts[f], outs[f], sts[f])
+    S.sync()
+    assert S.frames == frames
+    final_local = S.read_local()
+    start = None
+    for f in range(frames):
+        ref_out, ref_loc, ref_st = O.solve_batch(rig, Ts[f], start_pose=start, want_local=True, threads=8)
+        assert np.array_equal(outs[f], ref_out, equal_nan=True), f"frame {f}"
+        assert np.array_equal(sts[f], ref_st)
+        start = ref_loc
+    assert np.array_equal(final_local, start, equal_nan=True)
+    # reset -> rest pose again; and a caller-supplied initial pose
+    S.reset()
+    S.submit(Ts[0], outs[1], None)
+    S.sync()
+    assert np.array_equal(outs[1], outs[0], equal_nan=True)
+    sp = rig_cases.perturbed_start_pose(rig, n)
+    S2 = IKStream(R, n, device=0, initial_pose=sp)
+    S2.submit(Ts[1], outs[2], None)
+    S2.sync()
+    ref_out, _ = O.solve_batch(rig, Ts[1], start_pose=sp, threads=8)
+    assert np.array_equal(outs[2], ref_out, equal_nan=True)
