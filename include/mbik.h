@@ -113,6 +113,8 @@ typedef struct mbik_rig_info {
 	int32_t kernel_capacity;  /* solved-bone capacity of the kernel variant that will run */
 	int64_t rig_blob_bytes;   /* constants staged to shared memory per CTA */
 	double flops_per_solve;   /* algorithmic flop floor, SURVEY.md section 8(d) convention */
+	int32_t max_segment_len;  /* bones in the longest kept segment */
+	int32_t max_walk_stack;   /* branch-point stack depth of the deepest effector walk */
 } mbik_rig_info;
 
 int mbik_device_count(void);

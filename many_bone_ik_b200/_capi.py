@@ -46,7 +46,7 @@ class RigInfo(C.Structure):
     _fields_ = [("n_bones", C.c_int32), ("n_solved", C.c_int32), ("n_segments", C.c_int32), ("n_steps", C.c_int32),
                 ("n_effectors", C.c_int32), ("n_pins", C.c_int32), ("max_headings", C.c_int32), ("n_cones", C.c_int32),
                 ("iterations", C.c_int32), ("kernel_capacity", C.c_int32), ("rig_blob_bytes", C.c_int64),
-                ("flops_per_solve", C.c_double)]
+                ("flops_per_solve", C.c_double), ("max_segment_len", C.c_int32), ("max_walk_stack", C.c_int32)]
 
 
 MBIK_IO_HOST = 0

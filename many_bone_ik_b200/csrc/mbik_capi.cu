@@ -439,6 +439,8 @@ int mbik_rig_get_info(const mbik_rig *rig, mbik_rig_info *o) {
 	o->kernel_capacity = mbik::kernel_capacity_of_variant(rig->variant);
 	o->rig_blob_bytes = (int64_t)F.blob.size();
 	o->flops_per_solve = F.flops_per_solve;
+	o->max_segment_len = F.max_seg_len;
+	o->max_walk_stack = F.max_stack;
 	return MBIK_OK;
 }
 

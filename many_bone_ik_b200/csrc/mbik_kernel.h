@@ -1,4 +1,4 @@
-// mbik_kernel.h -- launch interface of the solve kernel (mbik_kernel.cu).
+// mbik_kernel.h -- launch interface of the solve kernel (mbik_kernel_body.cuh, instantiated in mbik_kernel_v*.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -23,9 +23,21 @@ struct SolveArgs {
 	int32_t stabilize;       // rig has stabilization_passes > 0 (reference src/ik_bone_segment_3d.cpp:163-176)
 };
 
+// Compiled size variants {solved-bone capacity, longest segment, walk-stack depth}; per-pose thread-local state is
+// NB*12 + NSEG*12 + NSTK*12 floats, so tight variants keep more of it in L1/L2.
+constexpr int kNumVariants = 5;
+constexpr int kVariants[kNumVariants][3] = { { 20, 4, 2 }, { 32, 8, 4 }, { 64, 8, 1 }, { 64, 16, 8 }, { 128, 128, 16 } };
+
 // index of the smallest kernel variant that fits the rig, or -1 if none does
 int kernel_variant_for(int n_solved, int max_seg_len, int max_stack);
 int kernel_capacity_of_variant(int variant);
 cudaError_t launch_solve(const SolveArgs &args, int variant, int sm_count, cudaStream_t stream);
+
+// one translation unit per variant (parallel compilation); threads == 0 selects the stabilisation instantiation
+cudaError_t launch_v0(const SolveArgs &a, int threads, cudaStream_t stream);
+cudaError_t launch_v1(const SolveArgs &a, int threads, cudaStream_t stream);
+cudaError_t launch_v2(const SolveArgs &a, int threads, cudaStream_t stream);
+cudaError_t launch_v3(const SolveArgs &a, int threads, cudaStream_t stream);
+cudaError_t launch_v4(const SolveArgs &a, int threads, cudaStream_t stream);
 
 } // namespace mbik
