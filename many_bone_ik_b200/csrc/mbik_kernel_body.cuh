@@ -369,7 +369,7 @@ struct HeadingAcc {
 	double total_w;       // pass 0: sum of weights
 	V3 csum_m, csum_t;    // pass 0: weighted sums of the tip / target headings
 	V3 neg_mc, neg_tc;    // pass 1 when translating: -centroids
-	V3 last_t, last_m;    // the single heading of a 1-heading list
+	                      // (pass 1 reuses csum_m / csum_t for the latest heading: the operands of the 1-heading QCP branch)
 	float msd, msd_wsum;  // pass 2 (stabilisation): _get_manual_msd accumulators (float, src/ik_bone_segment_3d.cpp:114-127)
 };
 
@@ -389,8 +389,8 @@ __device__ __forceinline__ void heading_emit(HeadingAcc &A, int pass_i, bool tra
 			th = vadd(th, A.neg_tc);
 		}
 		qcp_accumulate(A.sums, th, mh, w);
-		A.last_t = th;
-		A.last_m = mh;
+		A.csum_t = th;
+		A.csum_m = mh;
 	}
 }
 
@@ -526,21 +526,24 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				}
 			}
 
-			const X34 P = S.parent >= 0 ? ld_x34(Pseg, S.pslot) : x_identity();
-			X34 Lb = ld_x34(L, b);
-			const X34 Gb = node_parent ? x_mul(P, Lb) : Lb;
-			M3 Pinv = m3_identity();
-			if (node_parent) {
-				Pinv = m3_inverse(P.b);
+			// Gb = global transform of the bone before the step.  P and the local pose are re-read after the heading
+			// walk instead of being carried through it (register pressure: the walk keeps 11 double accumulators,
+			// the running transform, a target and a tip frame live).
+			X34 Gb;
+			{
+				const X34 P0 = S.parent >= 0 ? ld_x34(Pseg, S.pslot) : x_identity();
+				const X34 L0 = ld_x34(L, b);
+				Gb = node_parent ? x_mul(P0, L0) : L0;
 			}
+			Q4 q = q4(0.0f, 0.0f, 0.0f, 1.0f);
+			V3 translation = v3(0.0f, 0.0f, 0.0f);
 
 			if (!constraint_mode) {
 				const V3 bo = xform_zero(Gb); // origin of the solved bone's bone-direction frame
 				const bool translate = (flags & STEP_TRANSLATE) != 0;
-				V3 moved_center = v3(0.0f, 0.0f, 0.0f), target_center = v3(0.0f, 0.0f, 0.0f);
 				HeadingAcc A;
 				qcp_zero(A.sums);
-				A.neg_mc = A.neg_tc = A.last_t = A.last_m = v3(0.0f, 0.0f, 0.0f);
+				A.neg_mc = A.neg_tc = v3(0.0f, 0.0f, 0.0f);
 				if (flags & STEP_PUSH_SELF) {
 					st_x34(Gstk, 0, Gb);
 				}
@@ -578,6 +581,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						}
 					}
 					if (pass_i == 0) {
+						V3 moved_center, target_center;
 						if (A.total_w > 0.0) {
 							moved_center = vdivs(A.csum_m, (float)A.total_w);
 							target_center = vdivs(A.csum_t, (float)A.total_w);
@@ -589,9 +593,24 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						A.neg_tc = vmuls(target_center, -1.0f);
 					}
 				}
-				Q4 q = (S.n_headings == 1) ? qcp_rotation_single(A.last_m, A.last_t) : qcp_rotation(A.sums);
-				V3 translation = vsub(target_center, moved_center);
+				q = (S.n_headings == 1) ? qcp_rotation_single(A.csum_m, A.csum_t) : qcp_rotation(A.sums);
+				// translation = target_center - moved_center (src/math/qcp.cpp:135-137); the centres are the exact
+				// negations of neg_tc / neg_mc (zero when the segment does not translate)
+				translation = vsub(vneg(A.neg_tc), vneg(A.neg_mc));
+			}
 
+			// re-read the parent global and the local pose (same values as above; the index is laundered so that the
+			// compiler reloads instead of keeping 24 registers alive across the walk)
+			int b_reload = b, pslot_reload = S.pslot;
+			asm volatile("" : "+r"(b_reload), "+r"(pslot_reload));
+			const X34 P = S.parent >= 0 ? ld_x34(Pseg, pslot_reload) : x_identity();
+			X34 Lb = ld_x34(L, b_reload);
+			M3 Pinv = m3_identity();
+			if (node_parent) {
+				Pinv = m3_inverse(P.b);
+			}
+
+			if (!constraint_mode) {
 				M3 R2 = damp_and_slerp0(q, S.cos_half_damp, Gb.b);
 				if (node_parent) {
 					Lb.b = rotate_local_with_global(Pinv, R2, P.b, Lb.b);

@@ -15,8 +15,6 @@ cudaError_t launch_v0(const SolveArgs &a, int threads, cudaStream_t stream) {
 			return launch_variant<20, 4, 2, 128>(a, stream);
 		case 256:
 			return launch_variant<20, 4, 2, 256>(a, stream);
-		case 384:
-			return launch_variant<20, 4, 2, 384>(a, stream);
 		case 512:
 			return launch_variant<20, 4, 2, 512>(a, stream);
 		default:
