@@ -122,7 +122,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, emit):
     if rank != 0:
         return
     from many_bone_ik_b200 import rigs
@@ -136,7 +136,7 @@ def run_reference_arm(args, rank, world):
         "gpu_launches": 0,
         "note": "reference = line-cited CPU restatement of the reference solver (oracle/); the Godot module itself cannot be built here",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -153,9 +153,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: anything libraries print (NCCL's version banner, ...) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+    def emit(line):
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, emit)
         return 0
 
     import torch
@@ -295,7 +303,7 @@ def main():
     ach_tf = flops * n / (k_ms * 1e-3) / 1e12
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {
-        "bound": "fp32", "kernel": "mbik_solve_kernel<24>", "achieved": ach_tf, "peak": float(tf.value), "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": "mbik_solve_kernel<20,4,2,512> (one launch = all iterations of one batch)", "achieved": ach_tf, "peak": float(tf.value), "unit": "TFLOP/s",
         "frac": ach_tf / float(tf.value) if tf.value else None, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": "FP32 FMA micro-benchmark run in this process (mbik_measure_fp32_tflops)",
         "flops_per_solve": flops, "kernel_ms": k_ms,
@@ -322,7 +330,7 @@ def main():
         "clocks": clocks,
         "device_equals_host_path": same,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
