@@ -390,7 +390,7 @@ int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
 		return fail(rc, msg);
 	}
 	rig->n_solved = (int)rig->flat.bone_order.size();
-	rig->variant = mbik::kernel_variant_for(rig->n_solved, rig->flat.max_seg_len, rig->flat.max_stack);
+	rig->variant = mbik::kernel_variant_for(rig->n_solved, rig->flat.max_seg_len, rig->flat.max_stack, rig->flat.blob.size());
 	if (rig->variant < 0) {
 		delete rig;
 		return fail(MBIK_ERR_UNSUPPORTED, "rig exceeds the largest kernel variant (128 solved bones, walk stack depth 16)");

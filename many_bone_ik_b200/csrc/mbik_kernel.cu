@@ -5,8 +5,12 @@
 
 namespace mbik {
 
-int kernel_variant_for(int n_solved, int max_seg_len, int max_stack) {
+int kernel_variant_for(int n_solved, int max_seg_len, int max_stack, size_t blob_bytes) {
 	for (int v = 0; v < kNumVariants; v++) {
+		// the small variants keep their scratch transforms in shared memory (up to 150 KiB) next to the rig blob
+		if (v <= 2 && blob_bytes > 72 * 1024) {
+			continue;
+		}
 		if (n_solved <= kVariants[v][0] && max_seg_len <= kVariants[v][1] && max_stack <= kVariants[v][2]) {
 			return v;
 		}

@@ -29,7 +29,7 @@ constexpr int kNumVariants = 5;
 constexpr int kVariants[kNumVariants][3] = { { 20, 4, 2 }, { 32, 8, 4 }, { 64, 8, 1 }, { 64, 16, 8 }, { 128, 128, 16 } };
 
 // index of the smallest kernel variant that fits the rig, or -1 if none does
-int kernel_variant_for(int n_solved, int max_seg_len, int max_stack);
+int kernel_variant_for(int n_solved, int max_seg_len, int max_stack, size_t blob_bytes);
 int kernel_capacity_of_variant(int variant);
 cudaError_t launch_solve(const SolveArgs &args, int variant, int sm_count, cudaStream_t stream);
 

@@ -86,6 +86,33 @@ __device__ __forceinline__ void st_x34(float *A, int i, const X34 &t) {
 	p[10] = t.o.y;
 	p[11] = t.o.z;
 }
+// Per-pose scratch transforms (segment parent-global chain, walk stack): either a thread-local array or, when
+// STRIDE > 0, a column of a [word][thread] shared-memory matrix (conflict-free: consecutive lanes, consecutive words).
+template <int STRIDE>
+struct Scratch {
+	float *p;
+	__device__ __forceinline__ X34 ld(int i) const {
+		X34 t;
+		const float *q = p + i * 12 * (STRIDE > 0 ? STRIDE : 1);
+#pragma unroll
+		for (int k = 0; k < 9; k++) {
+			t.b.m[k] = q[k * (STRIDE > 0 ? STRIDE : 1)];
+		}
+		t.o = v3(q[9 * (STRIDE > 0 ? STRIDE : 1)], q[10 * (STRIDE > 0 ? STRIDE : 1)], q[11 * (STRIDE > 0 ? STRIDE : 1)]);
+		return t;
+	}
+	__device__ __forceinline__ void st(int i, const X34 &t) const {
+		float *q = p + i * 12 * (STRIDE > 0 ? STRIDE : 1);
+#pragma unroll
+		for (int k = 0; k < 9; k++) {
+			q[k * (STRIDE > 0 ? STRIDE : 1)] = t.b.m[k];
+		}
+		q[9 * (STRIDE > 0 ? STRIDE : 1)] = t.o.x;
+		q[10 * (STRIDE > 0 ? STRIDE : 1)] = t.o.y;
+		q[11 * (STRIDE > 0 ? STRIDE : 1)] = t.o.z;
+	}
+};
+
 __device__ __forceinline__ M3 ld_m3(const float *p) {
 	M3 r;
 #pragma unroll
@@ -429,7 +456,8 @@ __device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, boo
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int NB, int NSEG, int NSTK, bool STAB>
+// SCR_STRIDE > 0: the scratch transforms live in shared memory behind the rig blob (SCR_STRIDE = CTA size)
+template <int NB, int NSEG, int NSTK, bool STAB, int SCR_STRIDE>
 __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t bar;
@@ -477,9 +505,13 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 
 	// Per-pose state (thread-local, lane-interleaved):
 	float L[NB * 12];      // local transform of every solved bone (t order) -- the only state carried between steps
-	float Pseg[NSEG * 12]; // globals of the parents of the current segment's bones (ancestors do not move while a
-	                       // segment is being solved, so this replaces the reference's lazy global-transform cache)
-	float Gstk[NSTK * 12]; // globals of the branch points of the current downward walk
+	// globals of the parents of the current segment's bones (ancestors do not move while a segment is being solved,
+	// so this replaces the reference's lazy global-transform cache) and of the branch points of the current walk
+	float Pseg_local[SCR_STRIDE > 0 ? 1 : NSEG * 12];
+	float Gstk_local[SCR_STRIDE > 0 ? 1 : NSTK * 12];
+	float *scr = reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + threadIdx.x;
+	const Scratch<SCR_STRIDE> Pseg{ SCR_STRIDE > 0 ? scr : Pseg_local };
+	const Scratch<SCR_STRIDE> Gstk{ SCR_STRIDE > 0 ? scr + NSEG * 12 * SCR_STRIDE : Gstk_local };
 	// stabilisation only (STAB variants): effector-bone origins from before the step (what the step's target
 	// headings were built from) and the segment's previous_deviation (src/ik_bone_segment_3d.h:63)
 	float TipO[STAB ? kMaxStabEffectors * 3 : 1];
@@ -509,7 +541,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				// parents of this segment's bones (slot 0 = parent of the segment root)
 				const int off = S.chain_cnt - S.seg_len; // -1 for a root segment: its root has no IK parent
 				if (off < 0) {
-					st_x34(Pseg, 0, x_identity());
+					Pseg.st(0, x_identity());
 				}
 				X34 g = x_identity();
 				for (int k = 0; k < S.chain_cnt; k++) {
@@ -521,7 +553,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						g = x_mul(g, l);
 					}
 					if (k - off >= 0) {
-						st_x34(Pseg, k - off, g);
+						Pseg.st(k - off, g);
 					}
 				}
 			}
@@ -531,7 +563,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			// the running transform, a target and a tip frame live).
 			X34 Gb;
 			{
-				const X34 P0 = S.parent >= 0 ? ld_x34(Pseg, S.pslot) : x_identity();
+				const X34 P0 = S.parent >= 0 ? Pseg.ld(S.pslot) : x_identity();
 				const X34 L0 = ld_x34(L, b);
 				Gb = node_parent ? x_mul(P0, L0) : L0;
 			}
@@ -545,7 +577,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				qcp_zero(A.sums);
 				A.neg_mc = A.neg_tc = v3(0.0f, 0.0f, 0.0f);
 				if (flags & STEP_PUSH_SELF) {
-					st_x34(Gstk, 0, Gb);
+					Gstk.st(0, Gb);
 				}
 				// pass 0 (translating root segment only): weighted centroids; pass 1: inner product (:225-248)
 				for (int pass_i = translate ? 0 : 1; pass_i < 2; pass_i++) {
@@ -565,11 +597,11 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					for (int k = 0; k < S.fk_cnt; k++) {
 						const BlobFk op = fk[S.fk_off + k];
 						if (op.src_slot >= 0) {
-							run = ld_x34(Gstk, op.src_slot);
+							run = Gstk.ld(op.src_slot);
 						}
 						run = x_mul(run, ld_x34(L, op.child));
 						if (op.push_slot >= 0) {
-							st_x34(Gstk, op.push_slot, run);
+							Gstk.st(op.push_slot, run);
 						}
 						if (op.eff >= 0) {
 							const BlobEff &E = effs[S.eff_off + op.eff];
@@ -603,7 +635,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			// compiler reloads instead of keeping 24 registers alive across the walk)
 			int b_reload = b, pslot_reload = S.pslot;
 			asm volatile("" : "+r"(b_reload), "+r"(pslot_reload));
-			const X34 P = S.parent >= 0 ? ld_x34(Pseg, pslot_reload) : x_identity();
+			const X34 P = S.parent >= 0 ? Pseg.ld(pslot_reload) : x_identity();
 			X34 Lb = ld_x34(L, b_reload);
 			M3 Pinv = m3_identity();
 			if (node_parent) {
@@ -637,17 +669,17 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					TipO[0] = tO.x; TipO[1] = tO.y; TipO[2] = tO.z;
 				}
 				if (flags & STEP_PUSH_SELF) {
-					st_x34(Gstk, 0, Gb);
+					Gstk.st(0, Gb);
 				}
 				X34 run = Gb;
 				for (int k = 0; k < S.fk_cnt; k++) {
 					const BlobFk op = fk[S.fk_off + k];
 					if (op.src_slot >= 0) {
-						run = ld_x34(Gstk, op.src_slot);
+						run = Gstk.ld(op.src_slot);
 					}
 					run = x_mul(run, ld_x34(L, op.child));
 					if (op.push_slot >= 0) {
-						st_x34(Gstk, op.push_slot, run);
+						Gstk.st(op.push_slot, run);
 					}
 					if (op.eff >= 0) {
 						const V3 tO = xform_zero(run);
@@ -699,17 +731,17 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 								v3(TipO[0], TipO[1], TipO[2]));
 					}
 					if (flags & STEP_PUSH_SELF) {
-						st_x34(Gstk, 0, Gp);
+						Gstk.st(0, Gp);
 					}
 					X34 run = Gp;
 					for (int k = 0; k < S.fk_cnt; k++) {
 						const BlobFk op = fk[S.fk_off + k];
 						if (op.src_slot >= 0) {
-							run = ld_x34(Gstk, op.src_slot);
+							run = Gstk.ld(op.src_slot);
 						}
 						run = x_mul(run, ld_x34(L, op.child));
 						if (op.push_slot >= 0) {
-							st_x34(Gstk, op.push_slot, run);
+							Gstk.st(op.push_slot, run);
 						}
 						if (op.eff >= 0) {
 							const BlobEff &E = effs[S.eff_off + op.eff];
@@ -759,9 +791,14 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	}
 }
 
+// shared-memory scratch is used when it fits beside the largest rig blob (200 KiB budget checked at rig creation)
+template <int NSEG, int NSTK, int THREADS>
+struct ScratchStride {
+	static constexpr int value = ((NSEG + NSTK) * 12 * THREADS * 4 <= 150 * 1024) ? THREADS : 0;
+};
 template <int NB, int NSEG, int NSTK, int THREADS, bool STAB, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) mbik_solve_kernel(SolveArgs a) {
-	solve_body<NB, NSEG, NSTK, STAB>(a);
+	solve_body<NB, NSEG, NSTK, STAB, ScratchStride<NSEG, NSTK, THREADS>::value>(a);
 }
 // ---------------------------------------------------------------------------------------------------
 // host-side launcher
@@ -769,6 +806,12 @@ __global__ void __launch_bounds__(THREADS, MINB) mbik_solve_kernel(SolveArgs a) 
 template <int NB, int NSEG, int NSTK, int THREADS, bool STAB = false, int MINB = 1>
 static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 	size_t smem = a.blob_bytes;
+	if (ScratchStride<NSEG, NSTK, THREADS>::value > 0) {
+		smem = ((smem + 127) & ~(size_t)127) + (size_t)(NSEG + NSTK) * 12 * THREADS * sizeof(float);
+		if (smem > 227 * 1024) {
+			return cudaErrorInvalidValue; // cannot happen: blob <= 64 KiB for these variants (checked at rig creation)
+		}
+	}
 	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel<NB, NSEG, NSTK, THREADS, STAB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) {
 		return e;

@@ -37,7 +37,8 @@ def function_table(path):
     return out
 
 
-FT = {f: function_table(os.path.join(CSRC, f)) for f in ("mbik_kernel.cu", "mbik_math.cuh")}
+BODY = "mbik_kernel_body.cuh"
+FT = {f: function_table(os.path.join(CSRC, f)) for f in (BODY, "mbik_math.cuh")}
 
 
 def func_of(fname, line):
@@ -53,8 +54,13 @@ def func_of(fname, line):
 # ---- address -> inline chain from nvdisasm -gi
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if "mbik_kernel" in f and f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+dis = ""
+for f in sorted(os.listdir(tmp)):
+    if "mbik_kernel" in f and f.endswith(".cubin"):
+        d = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if kname in d:
+            dis = d
+            break
 addr_chain = {}
 chain = []
 in_kernel = False
@@ -96,7 +102,8 @@ inner_s = collections.Counter()
 stage_s = collections.Counter()
 stmt_s = collections.Counter()
 tot = tots = 0
-kernel_start = [s for s, n in FT["mbik_kernel.cu"] if n == "mbik_solve_kernel"][0]
+kernel_start = [s for s, n in FT[BODY] if n == "solve_body"][0]
+kernel_end = min(s for s, n in FT[BODY] if s > kernel_start)
 for r in data:
     try:
         ie = int(r[idx["Instructions Executed"]])
@@ -115,7 +122,7 @@ for r in data:
     inner[fi] += ie
     inner_s[fi] += sm
     # the chain is innermost first; the last entry is the kernel body statement
-    body = [(f, l) for f, l in ours if f == "mbik_kernel.cu" and l >= kernel_start]
+    body = [(f, l) for f, l in ours if f == BODY and kernel_start <= l < kernel_end]
     if body:
         stmt[body[-1][1]] += ie
         stmt_s[body[-1][1]] += sm
@@ -131,7 +138,7 @@ for k, v in stage.most_common(top):
 print("\nby innermost function:")
 for k, v in inner.most_common(top):
     print(f"  {k:28s} {100.0 * v / tot:6.2f}%  {100.0 * inner_s[k] / max(tots, 1):6.2f}%")
-print("\nby kernel-body statement (mbik_kernel.cu line):")
-src = open(os.path.join(CSRC, "mbik_kernel.cu")).read().splitlines()
+print("\nby kernel-body statement (mbik_kernel_body.cuh line):")
+src = open(os.path.join(CSRC, BODY)).read().splitlines()
 for k, v in stmt.most_common(top):
     print(f"  {k:5d} {100.0 * v / tot:6.2f}%  {100.0 * stmt_s[k] / max(tots, 1):6.2f}%  {src[k - 1].strip()[:90]}")
