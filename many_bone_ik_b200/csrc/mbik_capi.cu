@@ -395,6 +395,13 @@ int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
 		delete rig;
 		return fail(MBIK_ERR_UNSUPPORTED, "rig exceeds the largest kernel variant (128 solved bones, walk stack depth 16)");
 	}
+	{
+		std::string verr;
+		if (!mbik::validate_schedule(rig->flat, mbik::kVariants[rig->variant][0], mbik::kVariants[rig->variant][1], mbik::kVariants[rig->variant][2], verr)) {
+			delete rig;
+			return fail(MBIK_ERR_UNSUPPORTED, verr);
+		}
+	}
 	if (desc->stabilization_passes > 0) {
 		for (int si : rig->flat.root_segments) {
 			if ((int)rig->flat.segments[si].effectors.size() > mbik::kMaxStabEffectors) {

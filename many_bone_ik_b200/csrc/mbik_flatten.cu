@@ -909,4 +909,71 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	return MBIK_OK;
 }
 
+bool validate_schedule(const FlatRig &R, int cap_bones, int cap_seg, int cap_stack, std::string &error) {
+	const int ns = (int)R.bones.size(), n_fk = (int)R.fk.size(), n_effs = (int)R.effs.size(), n_cones = (int)R.cones.size();
+	const int n_chain = (int)R.chain.size(), n_pins = (int)R.pins.size();
+	auto bad = [&](const char *what, int step) {
+		error = std::string("inconsistent schedule: ") + what + " (step " + std::to_string(step) + ")";
+		return false;
+	};
+	if (ns > cap_bones || (int)R.steps.size() != ns) {
+		return bad("solved-bone count", -1);
+	}
+	for (int t = 0; t < ns; t++) {
+		if (R.bones[t].skel_bone < 0 || R.bones[t].skel_bone >= R.n_bones || R.bones[t].parent < -1 || R.bones[t].parent >= ns) {
+			return bad("bone table", t);
+		}
+	}
+	for (const BlobPass &p : R.pass) {
+		if (p.skel_bone < 0 || p.skel_bone >= R.n_bones) {
+			return bad("pass-through table", -1);
+		}
+	}
+	for (const BlobEff &e : R.effs) {
+		if (e.bone < 0 || e.bone >= ns || e.pin < 0 || e.pin >= n_pins) {
+			return bad("effector table", -1);
+		}
+	}
+	for (int s = 0; s < (int)R.steps.size(); s++) {
+		const BlobStep &S = R.steps[s];
+		if (S.bone < 0 || S.bone >= ns || S.parent < -1 || S.parent >= ns) {
+			return bad("bone index", s);
+		}
+		if (S.seg_len < 1 || S.seg_len > cap_seg || S.pslot < 0 || S.pslot >= S.seg_len) {
+			return bad("segment slot", s);
+		}
+		if (S.eff_off < 0 || S.eff_cnt < 0 || S.eff_off + S.eff_cnt > n_effs || S.fk_off < 0 || S.fk_cnt < 0 || S.fk_off + S.fk_cnt > n_fk) {
+			return bad("effector / walk range", s);
+		}
+		if (S.cone_off < 0 || S.cone_cnt < 0 || S.cone_off + S.cone_cnt > n_cones) {
+			return bad("cone range", s);
+		}
+		if (S.flags & STEP_SEG_FIRST) {
+			if (S.chain_off < 0 || S.chain_cnt < 0 || S.chain_off + S.chain_cnt > n_chain || S.chain_cnt - S.seg_len < -1) {
+				return bad("ancestor chain", s);
+			}
+			for (int k = 0; k < S.chain_cnt; k++) {
+				int t = R.chain[S.chain_off + k];
+				if (t < 0 || t >= ns) {
+					return bad("ancestor chain entry", s);
+				}
+			}
+		}
+		if ((S.flags & STEP_SELF_EFF) && S.eff_cnt < 1) {
+			return bad("self effector", s);
+		}
+		if ((S.flags & STEP_PUSH_SELF) && cap_stack < 1) {
+			return bad("walk stack", s);
+		}
+		for (int k = 0; k < S.fk_cnt; k++) {
+			const BlobFk &op = R.fk[S.fk_off + k];
+			if (op.child < 0 || op.child >= ns || op.src_slot < -1 || op.src_slot >= cap_stack || op.push_slot < -1 || op.push_slot >= cap_stack ||
+					op.eff < -1 || op.eff >= S.eff_cnt) {
+				return bad("walk op", s);
+			}
+		}
+	}
+	return true;
+}
+
 } // namespace mbik

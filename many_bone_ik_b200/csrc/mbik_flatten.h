@@ -61,4 +61,8 @@ struct FlatRig {
 // Returns MBIK_OK or a negative error code (message in out.error).
 int flatten_rig(const mbik_rig_desc *desc, FlatRig &out);
 
+// Range-checks every index of the schedule against the capacities {solved bones, segment slots, stack slots} of the
+// kernel variant that will run it (the kernel itself does no bounds checking).  Returns true if consistent.
+bool validate_schedule(const FlatRig &rig, int cap_bones, int cap_seg, int cap_stack, std::string &error);
+
 } // namespace mbik

@@ -151,3 +151,52 @@ def perturbed_start_pose(rig, n, seed=7, angle_deg=12.0, offset=0.02):
             out[k, b, :9] = R.reshape(9).astype(np.float32)
             out[k, b, 9:] += rng.uniform(-offset, offset, 3).astype(np.float32)
     return out
+
+
+def random_rig(seed):
+    """Random skeleton tree with random pins / kusudama rows / damping: fuzzes the flattener (segment building,
+    dropped segments, effector lists, mpf cut-offs, weights) and every kernel stage against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(3, 41))
+    parent = np.full(n, -1, np.int32)
+    for b in range(1, n):
+        # mostly chains with occasional branching; a second root now and then
+        r = rng.random()
+        if r < 0.04:
+            parent[b] = -1
+        elif r < 0.7:
+            parent[b] = b - 1
+        else:
+            parent[b] = int(rng.integers(0, b))
+    rest = np.zeros((n, 12))
+    for b in range(n):
+        ax = rng.normal(size=3)
+        ang = rng.uniform(0, 40) * DEG if rng.random() < 0.8 else 0.0
+        off = rng.normal(size=3) * 0.15 if parent[b] >= 0 else rng.normal(size=3) * 0.5
+        if rng.random() < 0.1:
+            off[:] = 0.0  # coincident joints
+        rest[b] = _xf(_axis_angle(ax, ang), off)
+    r = Rig(f"random{seed}", [f"b{i}" for i in range(n)], parent, rest.astype(np.float32), iterations=int(rng.integers(1, 6)), config_id=100 + seed)
+    n_pins = int(rng.integers(1, min(n, 7) + 1))
+    bones = rng.choice(n, size=n_pins, replace=False)
+    for b in bones:
+        pr = tuple(float(x) for x in np.where(rng.random(3) < 0.6, rng.uniform(0.05, 0.6, 3), 0.0))
+        r.pins.append(dict(bone=int(b), weight=float(rng.choice([0.0, 0.3, 1.0, 0.75])) if rng.random() < 0.9 else 0.0,
+                           mpf=float(rng.choice([0.0, 0.5, 1.0, 1.0])), priorities=pr))
+    for b in range(n):
+        if rng.random() < 0.6:
+            nc = int(rng.integers(0, 5))
+            cones = []
+            for _ in range(nc):
+                c = rng.normal(size=3)
+                c = c / np.linalg.norm(c) if rng.random() < 0.95 else np.zeros(3)
+                cones.append((float(c[0]), float(c[1]), float(c[2]), float(rng.uniform(0.05, 1.4))))
+            r.constraints.append(dict(bone=b, twist_from=float(rng.uniform(-2, 2)), twist_range=float(rng.uniform(0.05, 6.0)), cones=cones))
+    if rng.random() < 0.5:
+        r.bone_damp = rng.uniform(0.01, 0.3, size=int(rng.integers(1, n + 1))).astype(np.float32)
+    r.default_damp = float(np.float32(rng.uniform(0.02, 0.5)))
+    if rng.random() < 0.3:
+        r.stabilization_passes = int(rng.integers(1, 3))
+    if rng.random() < 0.1:
+        r.constraint_mode = True
+    return r

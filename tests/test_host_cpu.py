@@ -74,6 +74,22 @@ def test_flattener_matches_reference_setup(name):
     R.close()
 
 
+@pytest.mark.parametrize("seed", range(40))
+def test_flattener_matches_reference_setup_random_rigs(seed):
+    """Fuzz: random skeleton trees / pins / kusudama rows (tests/rig_cases.py::random_rig)."""
+    rig = rig_cases.random_rig(seed)
+    R = BatchedIKRig(rig)
+    F = O.rig_facts(rig)
+    assert np.array_equal(R.bone_order(), F["bone_order"])
+    assert R.info["n_segments"] == F["n_segments"]
+    d, t = R.bone_frames()
+    assert np.array_equal(d, F["dir_basis"], equal_nan=True)
+    assert np.array_equal(t, F["twist_basis"], equal_nan=True)
+    for s in range(R.info["n_steps"]):
+        assert np.array_equal(R.step_weights(s), O.step_weights(rig, s)), f"step {s}"
+    assert np.array_equal(R.cone_geometry(), O.cone_geometry(rig), equal_nan=True)
+
+
 def test_schedule_facts_of_the_benchmark_rigs():
     """The segment structure SURVEY.md section 8(d) states for the canonical rigs."""
     h = BatchedIKRig(rigs.humanoid22())

@@ -56,6 +56,13 @@ def test_bit_exact_edge_rigs(name):
         assert st.any(), "this rig is meant to exercise the non-finite reset path"
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_bit_exact_random_rigs(seed):
+    """Fuzz: random trees, pins (zero weights, mpf cut-offs, 0-3 priority axes), 0-4 cones per row, per-bone damping,
+    stabilisation, constraint mode -- solve == oracle bit for bit."""
+    _compare(rig_cases.random_rig(seed), 96)
+
+
 @pytest.mark.parametrize("name", ["humanoid22", "quad80", "star_mixed_pins"])
 def test_bit_exact_with_start_pose(name):
     """Warm start: seeding from caller-supplied local poses (IKBone3D::set_initial_pose, src/ik_bone_3d.cpp:161)."""
