@@ -76,6 +76,13 @@ __device__ __forceinline__ X34 ld_x34(const float *A, int i) {
 	t.o = v3(p[9], p[10], p[11]);
 	return t;
 }
+// raw local transform to global memory (48-byte records, 16-byte aligned), streaming stores
+__device__ __forceinline__ void stg_x34(float *p, const X34 &t) {
+	float4 *q = reinterpret_cast<float4 *>(p);
+	__stcs(q + 0, make_float4(t.b.m[0], t.b.m[1], t.b.m[2], t.b.m[3]));
+	__stcs(q + 1, make_float4(t.b.m[4], t.b.m[5], t.b.m[6], t.b.m[7]));
+	__stcs(q + 2, make_float4(t.b.m[8], t.o.x, t.o.y, t.o.z));
+}
 __device__ __forceinline__ void st_x34(float *A, int i, const X34 &t) {
 	float *p = A + i * 12;
 #pragma unroll
@@ -382,9 +389,14 @@ __device__ __forceinline__ uint32_t write_bone_pose(const X34 &local, float *out
 	float sgn = det > 0.0f ? 1.0f : (det < 0.0f ? -1.0f : 0.0f);
 	V3 sc = v3(vlen(m3_col(b, 0)), vlen(m3_col(b, 1)), vlen(m3_col(b, 2)));
 	sc = vmuls(sc, sgn);
-	out10[0] = local.o.x; out10[1] = local.o.y; out10[2] = local.o.z;
-	out10[3] = q.x; out10[4] = q.y; out10[5] = q.z; out10[6] = q.w;
-	out10[7] = sc.x; out10[8] = sc.y; out10[9] = sc.z;
+	// streaming (evict-first) stores: the results are not read again, and must not push the per-pose state that
+	// lives in thread-local memory out of L2.  40-byte records are 8-byte aligned -> float2 stores.
+	float2 *o2 = reinterpret_cast<float2 *>(out10);
+	__stcs(o2 + 0, make_float2(local.o.x, local.o.y));
+	__stcs(o2 + 1, make_float2(local.o.z, q.x));
+	__stcs(o2 + 2, make_float2(q.y, q.z));
+	__stcs(o2 + 3, make_float2(q.w, sc.x));
+	__stcs(o2 + 4, make_float2(sc.y, sc.z));
 	return st;
 }
 
@@ -774,7 +786,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			X34 l = ld_x34(L, t);
 			status |= write_bone_pose(l, my_out + (size_t)sb * 10);
 			if (my_loc) {
-				st_x34(my_loc, sb, l);
+				stg_x34(my_loc + (size_t)sb * 12, l);
 			}
 		}
 		for (int k = 0; k < H.n_pass; k++) {
@@ -782,7 +794,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			X34 l = my_start ? ldg_x34(my_start + (size_t)sb * 12) : ld_x34(rest, sb);
 			status |= write_bone_pose(l, my_out + (size_t)sb * 10);
 			if (my_loc) {
-				st_x34(my_loc, sb, l);
+				stg_x34(my_loc + (size_t)sb * 12, l);
 			}
 		}
 	}
