@@ -48,15 +48,16 @@ struct BlobStep { // 64 bytes
 	int32_t seg_len;
 };
 
-struct BlobBone { // per solved bone, t order; 160 bytes
+struct BlobBone { // per solved bone, t order; 208 bytes; every 3x3 is padded to 12 floats so that it starts on a
+                  // 16-byte boundary and is read from shared memory with three 128-bit loads
 	int32_t skel_bone;
 	int32_t parent;          // t index or -1
 	uint32_t flags;          // STEP_NODE_PARENT only
 	float twist_cos;         // twist_half_range_half_cos = cos(range / 4)
-	float dir_basis[9];      // bone-direction node local basis (origin is zero)
-	float orient_basis[9];   // constraint-orientation node local basis (identity after a rebuild)
-	float twist_basis[9];    // constraint-twist node local basis (after _update_constraint)
-	float twist_center[9];   // Basis(twist_center_rot)
+	float dir_basis[12];     // bone-direction node local basis (origin is zero)
+	float orient_basis[12];  // constraint-orientation node local basis (identity after a rebuild)
+	float twist_basis[12];   // constraint-twist node local basis (after _update_constraint)
+	float twist_center[12];  // Basis(twist_center_rot)
 };
 
 struct BlobEff { // one entry per (segment, effector); 64 bytes
@@ -103,7 +104,7 @@ struct BlobPass { // skeleton bones outside bone_list: copied through to the out
 
 static_assert(sizeof(BlobStep) == 64, "BlobStep layout");
 static_assert(sizeof(BlobFk) == 8, "BlobFk layout");
-static_assert(sizeof(BlobBone) == 160, "BlobBone layout");
+static_assert(sizeof(BlobBone) == 208, "BlobBone layout");
 static_assert(sizeof(BlobEff) == 64, "BlobEff layout");
 static_assert(sizeof(BlobCone) == 160, "BlobCone layout");
 

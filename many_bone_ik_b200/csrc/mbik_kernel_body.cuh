@@ -120,6 +120,16 @@ struct Scratch {
 	}
 };
 
+// 3x3 from a 16-byte aligned, 12-float padded record (BlobBone matrices): three 128-bit loads
+__device__ __forceinline__ M3 ld_m3v(const float *p) {
+	const float4 *q = reinterpret_cast<const float4 *>(p);
+	float4 a = q[0], b = q[1], c = q[2];
+	M3 r;
+	r.m[0] = a.x; r.m[1] = a.y; r.m[2] = a.z; r.m[3] = a.w;
+	r.m[4] = b.x; r.m[5] = b.y; r.m[6] = b.z; r.m[7] = b.w;
+	r.m[8] = c.x;
+	return r;
+}
 __device__ __forceinline__ M3 ld_m3(const float *p) {
 	M3 r;
 #pragma unroll
@@ -601,7 +611,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						if (STAB) {
 							TipO[0] = tO.x; TipO[1] = tO.y; TipO[2] = tO.z;
 						}
-						effector_headings(A, pass_i, translate, E, Gb, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, tO);
+						effector_headings(A, pass_i, translate, E, Gb, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, tO);
 					}
 					// depth-first walk down to the effectors of this segment's list: the lazily re-derived global
 					// transforms of the reference (src/math/ik_node_3d.cpp:93-113) as explicit running products
@@ -621,7 +631,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 							if (STAB) {
 								TipO[3 * op.eff] = tO.x; TipO[3 * op.eff + 1] = tO.y; TipO[3 * op.eff + 2] = tO.z;
 							}
-							effector_headings(A, pass_i, translate, E, run, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, tO);
+							effector_headings(A, pass_i, translate, E, run, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, tO);
 						}
 					}
 					if (pass_i == 0) {
@@ -705,12 +715,12 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					// constraint-orientation node: child of the parent's aligned node; its local origin tracks the
 					// bone's local origin after set_global_pose (src/ik_bone_3d.cpp:145-151); never set in constraint mode
 					X34 Lor;
-					Lor.b = ld_m3(B.orient_basis);
+					Lor.b = ld_m3v(B.orient_basis);
 					Lor.o = constraint_mode ? v3(0.0f, 0.0f, 0.0f) : Lb.o;
 					const X34 Cor = x_mul(P, Lor);
 					const X34 Gcur = x_mul(P, Lb);
 					X34 Gd;
-					Gd.b = m3_mul(Gcur.b, ld_m3(B.dir_basis));
+					Gd.b = m3_mul(Gcur.b, ld_m3v(B.dir_basis));
 					Gd.o = xform_zero(Gcur);
 					const V3 bone_dir = x_xform(Gd, v3(0.0f, 1.0f, 0.0f));
 					const V3 bone_tip = x_xform(x_affine_inverse(Cor), bone_dir);
@@ -723,7 +733,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					}
 				}
 				if (flags & STEP_TWIST) {
-					Lb.b = twist_snap(P.b, Pinv, Lb.b, ld_m3(B.twist_basis), ld_m3(B.twist_center), B.twist_cos);
+					Lb.b = twist_snap(P.b, Pinv, Lb.b, ld_m3v(B.twist_basis), ld_m3v(B.twist_center), B.twist_cos);
 				}
 			}
 			if (STAB) {
@@ -739,7 +749,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					A.msd_wsum = 0.0f;
 					if (flags & STEP_SELF_EFF) {
 						const BlobEff &E = effs[S.eff_off];
-						effector_headings(A, 2, false, E, Gp, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo2,
+						effector_headings(A, 2, false, E, Gp, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo2,
 								v3(TipO[0], TipO[1], TipO[2]));
 					}
 					if (flags & STEP_PUSH_SELF) {
@@ -757,7 +767,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						}
 						if (op.eff >= 0) {
 							const BlobEff &E = effs[S.eff_off + op.eff];
-							effector_headings(A, 2, false, E, run, ld_m3(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo2,
+							effector_headings(A, 2, false, E, run, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo2,
 									v3(TipO[3 * op.eff], TipO[3 * op.eff + 1], TipO[3 * op.eff + 2]));
 						}
 					}
