@@ -60,13 +60,15 @@ struct BlobBone { // per solved bone, t order; 208 bytes; every 3x3 is padded to
 	float twist_center[12];  // Basis(twist_center_rot)
 };
 
-struct BlobEff { // one entry per (segment, effector); 64 bytes
+struct BlobEff { // one entry per (segment, effector); 80 bytes
 	int32_t bone;            // t index of the effector's bone
 	int32_t pin;             // row of the pins table = target slot
 	float prio[3];           // direction priorities (axis used iff > 0)
 	int32_t n_headings;      // 1 + 2 * (#priorities > 0)
 	double w_origin;         // heading weight of the origin heading
 	double w_axis[3];        // heading weight of each axis pair (0 when unused)
+	float w_origin_f;        // (float)w_origin, (float)w_axis[i]: the narrowed weights the reference multiplies
+	float w_axis_f[3];       // headings by (real_t w = p_weights->get(index), src/ik_effector_3d.cpp:103)
 	int32_t pad[2];
 };
 
@@ -105,7 +107,7 @@ struct BlobPass { // skeleton bones outside bone_list: copied through to the out
 static_assert(sizeof(BlobStep) == 64, "BlobStep layout");
 static_assert(sizeof(BlobFk) == 8, "BlobFk layout");
 static_assert(sizeof(BlobBone) == 208, "BlobBone layout");
-static_assert(sizeof(BlobEff) == 64, "BlobEff layout");
+static_assert(sizeof(BlobEff) == 80, "BlobEff layout");
 static_assert(sizeof(BlobCone) == 160, "BlobCone layout");
 
 } // namespace mbik

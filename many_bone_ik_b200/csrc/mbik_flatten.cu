@@ -698,11 +698,13 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 			E.bone = R.t_of_bone[e];
 			E.pin = pin_of_bone[e];
 			E.w_origin = S.weights[h++];
+			E.w_origin_f = (float)E.w_origin;
 			E.n_headings = 1;
 			for (int a = 0; a < 3; a++) {
 				E.prio[a] = pin.direction_priorities[a];
 				if (pin.direction_priorities[a] > 0.0) {
 					E.w_axis[a] = S.weights[h];
+					E.w_axis_f[a] = (float)E.w_axis[a];
 					h += 2;
 					E.n_headings += 2;
 				}

@@ -170,8 +170,8 @@ __device__ __forceinline__ void qcp_zero(QcpSums &s) {
 	s.xx = s.xy = s.xz = s.yx = s.yy = s.yz = s.zx = s.zy = s.zz = s.ss1 = s.ss2 = 0.0;
 }
 // inner_product body (:177-202): coords1 = target, coords2 = moved
-__device__ __forceinline__ void qcp_accumulate(QcpSums &s, V3 target, V3 moved, double w) {
-	V3 wc1 = vmuls(target, (float)w);
+__device__ __forceinline__ void qcp_accumulate(QcpSums &s, V3 target, V3 moved, double w, float wf /* == (float)w */) {
+	V3 wc1 = vmuls(target, wf);
 	s.ss1 = r_add(s.ss1, (double)vdot(wc1, target));
 	s.ss2 = r_add(s.ss2, r_mul(w, (double)vdot(moved, moved)));
 	s.xx = r_add(s.xx, (double)r_mul(wc1.x, moved.x));
@@ -422,11 +422,11 @@ struct HeadingAcc {
 	float msd, msd_wsum;  // pass 2 (stabilisation): _get_manual_msd accumulators (float, src/ik_bone_segment_3d.cpp:114-127)
 };
 
-__device__ __forceinline__ void heading_emit(HeadingAcc &A, int pass_i, bool translate, V3 th, V3 mh, double w) {
+__device__ __forceinline__ void heading_emit(HeadingAcc &A, int pass_i, bool translate, V3 th, V3 mh, double w, float wf /* == (float)w */) {
 	if (pass_i == 0) { // QCP::move_to_weighted_center (:139-160)
 		A.total_w = r_add(A.total_w, w);
-		A.csum_m = vadd(A.csum_m, vmuls(mh, (float)w));
-		A.csum_t = vadd(A.csum_t, vmuls(th, (float)w));
+		A.csum_m = vadd(A.csum_m, vmuls(mh, wf));
+		A.csum_t = vadd(A.csum_t, vmuls(th, wf));
 	} else if (pass_i == 2) { // IKBoneSegment3D::_get_manual_msd: float accumulators, double weight
 		float xd = r_sub(th.x, mh.x), yd = r_sub(th.y, mh.y), zd = r_sub(th.z, mh.z);
 		float d2 = r_add(r_add(r_mul(xd, xd), r_mul(yd, yd)), r_mul(zd, zd));
@@ -437,7 +437,7 @@ __device__ __forceinline__ void heading_emit(HeadingAcc &A, int pass_i, bool tra
 			mh = vadd(mh, A.neg_mc);
 			th = vadd(th, A.neg_tc);
 		}
-		qcp_accumulate(A.sums, th, mh, w);
+		qcp_accumulate(A.sums, th, mh, w, wf);
 		A.csum_t = th;
 		A.csum_m = mh;
 	}
@@ -448,29 +448,29 @@ __device__ __forceinline__ void heading_emit(HeadingAcc &A, int pass_i, bool tra
 // from (= xform_zero(Ge), except in the stabilisation pass where target headings date from before the step)
 __device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, bool translate, const BlobEff &E, const X34 &Ge, const M3 &De,
 		const X34 &T, V3 bo, V3 tgtO) {
-	const M3 tipB = m3_mul(Ge.b, De);
 	const V3 tipO = xform_zero(Ge);
 	// heading 0: origins.  Target heading is taken from the EFFECTOR's own bone (:97), tip heading from the solved bone (:125)
 	V3 th = vsub(T.o, tgtO);
 	V3 mh = vsub(tipO, bo);
 	float dist = vlen(vsub(bo, T.o));
 	float scale_by = dist < 1.0f ? dist : 1.0f; // MIN(distance, 1.0f)
-	heading_emit(A, pass_i, translate, th, mh, E.w_origin);
+	heading_emit(A, pass_i, translate, th, mh, E.w_origin, E.w_origin_f);
 #pragma unroll
 	for (int ax = 0; ax < 3; ax++) {
 		if (E.prio[ax] > 0.0f) {
 			const double wd = E.w_axis[ax];
-			const float w = (float)wd;
+			const float w = E.w_axis_f[ax];
 			V3 col = m3_col(T.b, ax);
 			V3 thp = vsub(vadd(col, T.o), tgtO);
 			thp = v3(r_mul(thp.x, w), r_mul(thp.y, w), r_mul(thp.z, w));
 			V3 thm = vsub(vsub(T.o, col), tgtO);
 			thm = v3(r_mul(thm.x, w), r_mul(thm.y, w), r_mul(thm.z, w));
-			V3 tcol = vmuls(m3_col(tipB, ax), E.prio[ax]);
+			// column `ax` of the tip basis Ge.b * De (Basis::operator*: element (i, ax) = De.col(ax) . Ge.b.row(i))
+			V3 tcol = vmuls(m3_xform(Ge.b, m3_col(De, ax)), E.prio[ax]);
 			V3 mhp = vmuls(vsub(vadd(tcol, tipO), bo), scale_by);
 			V3 mhm = vmuls(vsub(vsub(tipO, tcol), bo), scale_by);
-			heading_emit(A, pass_i, translate, thp, mhp, wd);
-			heading_emit(A, pass_i, translate, thm, mhm, wd);
+			heading_emit(A, pass_i, translate, thp, mhp, wd, w);
+			heading_emit(A, pass_i, translate, thm, mhm, wd, w);
 		}
 	}
 }
