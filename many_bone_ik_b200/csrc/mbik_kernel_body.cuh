@@ -551,7 +551,12 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			// Keep the CTA's warps in lockstep at bone-step granularity: the step body is ~75 KB of straight-line
 			// SASS, far more than the instruction cache holds, so warps that drift apart each stream it from L2
 			// on their own (ncu: 60% of stall samples were stall_no_inst before this barrier).
-			__syncthreads();
+#ifndef MBIK_SYNC_EVERY
+#define MBIK_SYNC_EVERY 1
+#endif
+			if (MBIK_SYNC_EVERY == 1 || (s % MBIK_SYNC_EVERY) == 0) {
+				__syncthreads();
+			}
 			const BlobStep &S = steps[s];
 			const int b = S.bone;
 			const uint32_t flags = S.flags;
