@@ -343,6 +343,15 @@ int check_solve_args(mbik_rig *rig, const mbik_solve_params *params, size_t n_po
 	if (it < 0) {
 		it = 0;
 	}
+	// early-outs of ManyBoneIK3D::_process_modification (reference src/many_bone_ik_3d.cpp:649-651, :671-680): no pins,
+	// or no pin with a non-empty bone name (bone < 0) -> nothing is solved, every bone passes through
+	bool has_pins = false;
+	for (const mbik_pin_desc &p : rig->flat.pins) {
+		has_pins = has_pins || p.bone >= 0;
+	}
+	if (!has_pins) {
+		it = 0;
+	}
 	*iterations = it;
 	return MBIK_OK;
 }
@@ -762,6 +771,15 @@ int mbik_stream_submit(mbik_stream *st, const float *targets, float *out_pose, u
 	a.blob = st->blob;
 	a.blob_bytes = (uint32_t)F.blob.size();
 	a.iterations = iterations >= 0 ? iterations : F.iterations;
+	{
+		bool has_pins = false; // same early-out as mbik_solve_batch (reference src/many_bone_ik_3d.cpp:649-651, :671-680)
+		for (const mbik_pin_desc &p : F.pins) {
+			has_pins = has_pins || p.bone >= 0;
+		}
+		if (!has_pins) {
+			a.iterations = 0;
+		}
+	}
 	a.n_poses = n;
 	a.stabilize = F.stabilization_passes > 0 ? 1 : 0;
 	a.targets = st->d_targets[slot];

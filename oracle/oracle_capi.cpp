@@ -116,7 +116,15 @@ void solve_range(const mbik_rig_desc *d, size_t begin, size_t end, const float *
 			sk.pose[b] = load_xform(start_pose ? start_pose + (k * d->n_bones + b) * 12 : d->rest_local + 12 * b);
 		}
 		ik->_update_ik_bones_transform(); // the modification_processed re-seed (many_bone_ik_3d.cpp:1084, :91-102)
-		ik->solve_iterations();
+		// early-outs of _process_modification (many_bone_ik_3d.cpp:649-651, :671-680): no pins at all, or no pin
+		// with a non-empty bone name (bone < 0 stands for the empty name) -> the skeleton is left untouched
+		bool has_pins = false;
+		for (int p = 0; p < d->n_pins; p++) {
+			has_pins = has_pins || d->pins[p].bone >= 0;
+		}
+		if (d->n_pins > 0 && has_pins) {
+			ik->solve_iterations();
+		}
 		ik->write_skeleton_pose(out_pose + k * d->n_bones * 10, out_local ? out_local + k * d->n_bones * 12 : nullptr,
 				out_status ? out_status + k : nullptr);
 	}

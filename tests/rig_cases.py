@@ -200,3 +200,31 @@ def random_rig(seed):
     if rng.random() < 0.1:
         r.constraint_mode = True
     return r
+
+
+def no_pins():
+    """No pins at all: nothing is solved; every bone passes through (reference early-out, many_bone_ik_3d.cpp:649)."""
+    r = rigs.humanoid22()
+    r.pins = []
+    r.name = "no_pins"
+    r.config_id = 30
+    return r
+
+
+def scaled_bones():
+    """Non-unit and negative bone scales in the rest pose (det < 0 flips in get_rotation_quaternion, get_scale sign)."""
+    n = 8
+    parent = np.arange(-1, n - 1, dtype=np.int32)
+    rest = np.zeros((n, 12))
+    scales = [(1, 1, 1), (1.5, 1.5, 1.5), (1, 2, 0.5), (-1, 1, 1), (1, 1, 1), (0.7, 0.7, 0.7), (1, -1, 1), (1, 1, 1)]
+    for i in range(n):
+        R = _axis_angle((0.3, 1.0, 0.2), (7.0 * i) * DEG) @ np.diag(scales[i])
+        rest[i] = _xf(R, (0.02 * i, 0.0 if i == 0 else 0.2, 0.0))
+    r = Rig("scaled_bones", [f"b{i}" for i in range(n)], parent, rest.astype(np.float32), iterations=4, config_id=31)
+    r.pins = [dict(bone=0, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2)), dict(bone=4, weight=0.6, mpf=1.0, priorities=(0.2, 0.1, 0.2)),
+              dict(bone=7, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2))]
+    _add_constraints(r, {2: (2, 40, 25, -20, 50), 5: (1, 30, 0, -45, 90), 6: (3, 25, 20, -10, 40)})
+    return r
+
+
+EDGE_RIGS.update({f.__name__: f for f in [no_pins, scaled_bones]})

@@ -307,3 +307,23 @@ def test_warm_start_stream_equals_per_frame_calls(name):
     S2.sync()
     ref_out, _ = O.solve_batch(rig, Ts[1], start_pose=sp, threads=8)
     assert np.array_equal(outs[2], ref_out, equal_nan=True)
+
+
+def test_non_finite_targets_propagate_like_the_reference():
+    """NaN / Inf / huge targets: the kernel's guarded fast paths must fall back exactly where IEEE semantics matter."""
+    rig = rigs.humanoid22()
+    n = 64
+    T = rigs.random_targets(rig, 0, n)
+    T[0, 0, 9] = np.nan
+    T[1, 1, :9] = np.inf
+    T[2, 2, 9:] = 3.0e38
+    T[3, 3, 9:] = 1.0e-30
+    T[4, :, :] = 0.0
+    T[5, 4, 0] = -np.inf
+    T[6, 0, 9:] = (1e20, -1e20, 1e-20)
+    _assert_same(rig, BatchedIKRig(rig).solve(T, want_local=True), O.solve_batch(rig, T, want_local=True, threads=8))
+    q = rigs.quad80()
+    Tq = rigs.random_targets(q, 0, 32)
+    Tq[::3, ::2, 9:] *= np.float32(1e19)
+    Tq[1::3, 1::2, :9] = 0.0
+    _assert_same(q, BatchedIKRig(q).solve(Tq, want_local=True), O.solve_batch(q, Tq, want_local=True, threads=8))
