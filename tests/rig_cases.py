@@ -228,3 +228,33 @@ def scaled_bones():
 
 
 EDGE_RIGS.update({f.__name__: f for f in [no_pins, scaled_bones]})
+
+
+def chain100():
+    """100-bone single chain, one pin at the tip: ONE 100-bone translating root segment (largest kernel variant)."""
+    n = 100
+    parent, rest = _chain(n, seg=0.03, curl=1.0)
+    r = Rig("chain100", [f"b{i}" for i in range(n)], parent, rest, iterations=2, config_id=32)
+    r.pins = [dict(bone=n - 1, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2))]
+    _add_constraints(r, {b: (1 + b % 3, 35, 20, -40, 80) for b in range(1, n, 2)})
+    return r
+
+
+def big_tree120():
+    """120-bone branching rig with 12 pins (deep effector walks, many segments): largest kernel variant."""
+    rng = np.random.default_rng(77)
+    n = 120
+    parent = np.full(n, -1, np.int32)
+    for b in range(1, n):
+        parent[b] = b - 1 if rng.random() < 0.8 else int(rng.integers(max(0, b - 30), b))
+    rest = np.zeros((n, 12))
+    for b in range(n):
+        rest[b] = _xf(_axis_angle(rng.normal(size=3), rng.uniform(0, 25) * DEG), rng.normal(size=3) * 0.08 + (0, 0.1, 0))
+    r = Rig("big_tree120", [f"b{i}" for i in range(n)], parent, rest.astype(np.float32), iterations=3, config_id=33)
+    for b in sorted(rng.choice(np.arange(5, n), size=12, replace=False)):
+        r.pins.append(dict(bone=int(b), weight=float(rng.uniform(0.3, 1.0)), mpf=float(rng.choice([0.5, 1.0])), priorities=(0.2, 0.0, 0.2)))
+    _add_constraints(r, {int(b): (int(rng.integers(1, 4)), 40, 25, -30, 60) for b in range(1, n, 3)})
+    return r
+
+
+EDGE_RIGS.update({f.__name__: f for f in [chain100, big_tree120]})
