@@ -23,6 +23,8 @@ enum : uint32_t {
 	STEP_SEG_FIRST = 128u,  // first step of its segment (the tip): (re)build the segment's parent-global chain
 	STEP_SELF_EFF = 256u,   // the solved bone is itself the first effector of the list (pinned segment tip)
 	STEP_PUSH_SELF = 512u,  // the solved bone is a branch point of its walk: its global goes to stack slot 0
+	STEP_PLAIN_FRAMES = 1024u, // orientation-axes basis is exactly the identity and the bone-direction basis is finite with
+	                           // |entries| <= 2: enables the finite-operand shortcuts of the swing snap (mbik_kernel_body.cuh)
 };
 
 struct BlobHeader {

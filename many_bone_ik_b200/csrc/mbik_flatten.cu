@@ -729,6 +729,17 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 		bool translate = S.parent_seg < 0;
 		st.flags = (translate ? STEP_TRANSLATE : 0) | (node_has_parent[b] ? STEP_NODE_PARENT : 0) | (ik_parent[b] >= 0 ? STEP_IK_PARENT : 0) |
 				(cons[b].present ? (STEP_SWING | STEP_TWIST) : 0) | (b == S.root_bone ? STEP_SEG_ROOT : 0) | (S.stabilize > 0 ? STEP_STABILIZE : 0);
+		{
+			const BlobBone &BB = R.bones[R.t_of_bone[b]];
+			const M3 ident = m3_identity();
+			bool plain = true;
+			for (int k = 0; k < 9; k++) {
+				plain = plain && BB.orient_basis[k] == ident.m[k] && fabsf(BB.dir_basis[k]) <= 2.0f; // NaN fails the <=
+			}
+			if (plain) {
+				st.flags |= STEP_PLAIN_FRAMES;
+			}
+		}
 		st.eff_off = seg_eff_off[R.seg_of_bone[b]];
 		st.eff_cnt = (int)S.effectors.size();
 		st.cone_off = cone_off[b];

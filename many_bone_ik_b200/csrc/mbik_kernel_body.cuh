@@ -155,6 +155,21 @@ __device__ __forceinline__ X34 ldg_x34(const float *p) {
 // evaluated like Transform3D::xform so that non-finite bases poison it exactly as in the reference
 __device__ __forceinline__ V3 xform_zero(const X34 &t) { return x_xform(t, v3(0.0f, 0.0f, 0.0f)); }
 
+// max |entry| of a 3x3 with NaN propagation (4 x FMNMX3.NAN): `m3_absmax(M) < kFiniteBound` is false as soon as one
+// entry is NaN, Inf or huge.  Where it holds, multiplications by the exact constants 0 and 1 that the reference
+// performs (Transform3D::xform of a zero vector or a unit axis, products with an identity basis, lerp / slerp with
+// weight 0) cannot poison or overflow, so they are skipped: same values, fewer instructions (signs of exact zeros
+// aside).  Lanes for which it does not hold take the literal formulation.
+__device__ __forceinline__ float max3_abs_nan(float a, float b, float c) {
+	float d;
+	asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)));
+	return d;
+}
+__device__ __forceinline__ float m3_absmax(const M3 &a) {
+	return max3_abs_nan(max3_abs_nan(a.m[0], a.m[1], a.m[2]), max3_abs_nan(a.m[3], a.m[4], a.m[5]), max3_abs_nan(a.m[6], a.m[7], a.m[8]));
+}
+static constexpr float kFiniteBound = 1.0e18f;
+
 // IKNode3D::rotate_local_with_global (src/math/ik_node_3d.cpp:56-67): L.basis = ((P^-1 * R) * P) * L.basis
 __device__ __forceinline__ M3 rotate_local_with_global(const M3 &Pinv, const M3 &R, const M3 &P, const M3 &Lb) {
 	return m3_mul(m3_mul(m3_mul(Pinv, R), P), Lb);
@@ -359,7 +374,7 @@ __device__ __forceinline__ M3 twist_snap(const M3 &Pb, const M3 &Pinv, const M3 
 
 // damping clamp + the (numerically no-op) slerp toward the current global basis with weight 0
 // (src/ik_bone_segment_3d.cpp:143-151)
-__device__ __forceinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const M3 &Gb) {
+__device__ __forceinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const M3 &Gb, bool gb_bounded) {
 	M3 rot = m3_from_quat(q);
 	Q4 cq = clamp_to_cos_half_angle(m3_get_rotation_quat(rot), cos_half_damp);
 	M3 R1 = m3_from_quat(cq);
@@ -368,17 +383,23 @@ __device__ __forceinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const 
 	// non-finite global basis poisons the result exactly as it does in the reference.
 	Q4 from = m3_get_quat(R1);
 	Q4 to = m3_get_quat(Gb);
-	float cosom = q_dot(from, to);
-	if (cosom < 0.0f) {
-		to = q4(-to.x, -to.y, -to.z, -to.w);
+	Q4 sl = from;
+	// finite `to`: from * 1 + to * 0 == from
+	if (!(max3_abs_nan(max3_abs_nan(to.x, to.y, to.z), to.w, 0.0f) < kFiniteBound)) {
+		float cosom = q_dot(from, to);
+		if (cosom < 0.0f) {
+			to = q4(-to.x, -to.y, -to.z, -to.w);
+		}
+		sl = q4(r_add(r_mul(1.0f, from.x), r_mul(0.0f, to.x)), r_add(r_mul(1.0f, from.y), r_mul(0.0f, to.y)),
+				r_add(r_mul(1.0f, from.z), r_mul(0.0f, to.z)), r_add(r_mul(1.0f, from.w), r_mul(0.0f, to.w)));
 	}
-	Q4 sl = q4(r_add(r_mul(1.0f, from.x), r_mul(0.0f, to.x)), r_add(r_mul(1.0f, from.y), r_mul(0.0f, to.y)),
-			r_add(r_mul(1.0f, from.z), r_mul(0.0f, to.z)), r_add(r_mul(1.0f, from.w), r_mul(0.0f, to.w)));
 	M3 b = m3_from_quat(sl);
 #pragma unroll
 	for (int i = 0; i < 3; i++) {
-		float la = vlen(m3_row(R1, i)), lb = vlen(m3_row(Gb, i));
-		float f = r_add(la, r_mul(r_sub(lb, la), 0.0f)); // Math::lerp(la, lb, 0)
+		float la = vlen(m3_row(R1, i));
+		// Math::lerp(la, lb, 0) = la + (lb - la) * 0 with lb = |row i of Gb|: for bounded Gb, lb is finite, so the
+		// second term is 0 for finite la and NaN otherwise -- exactly la * 0
+		float f = gb_bounded ? r_add(la, r_mul(la, 0.0f)) : r_add(la, r_mul(r_sub(vlen(m3_row(Gb, i)), la), 0.0f));
 		b.m[3 * i] = r_mul(b.m[3 * i], f);
 		b.m[3 * i + 1] = r_mul(b.m[3 * i + 1], f);
 		b.m[3 * i + 2] = r_mul(b.m[3 * i + 2], f);
@@ -596,9 +617,10 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			}
 			Q4 q = q4(0.0f, 0.0f, 0.0f, 1.0f);
 			V3 translation = v3(0.0f, 0.0f, 0.0f);
+			const bool gb_bounded = m3_absmax(Gb.b) < kFiniteBound;
 
 			if (!constraint_mode) {
-				const V3 bo = xform_zero(Gb); // origin of the solved bone's bone-direction frame
+				const V3 bo = gb_bounded ? Gb.o : xform_zero(Gb); // origin of the solved bone's bone-direction frame
 				const bool translate = (flags & STEP_TRANSLATE) != 0;
 				HeadingAcc A;
 				qcp_zero(A.sums);
@@ -670,7 +692,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			}
 
 			if (!constraint_mode) {
-				M3 R2 = damp_and_slerp0(q, S.cos_half_damp, Gb.b);
+				M3 R2 = damp_and_slerp0(q, S.cos_half_damp, Gb.b, gb_bounded);
 				if (node_parent) {
 					Lb.b = rotate_local_with_global(Pinv, R2, P.b, Lb.b);
 				}
@@ -719,16 +741,31 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				if (flags & STEP_SWING) {
 					// constraint-orientation node: child of the parent's aligned node; its local origin tracks the
 					// bone's local origin after set_global_pose (src/ik_bone_3d.cpp:145-151); never set in constraint mode
-					X34 Lor;
-					Lor.b = ld_m3v(B.orient_basis);
-					Lor.o = constraint_mode ? v3(0.0f, 0.0f, 0.0f) : Lb.o;
-					const X34 Cor = x_mul(P, Lor);
+					const V3 Lor_o = constraint_mode ? v3(0.0f, 0.0f, 0.0f) : Lb.o;
 					const X34 Gcur = x_mul(P, Lb);
-					X34 Gd;
-					Gd.b = m3_mul(Gcur.b, ld_m3v(B.dir_basis));
-					Gd.o = xform_zero(Gcur);
-					const V3 bone_dir = x_xform(Gd, v3(0.0f, 1.0f, 0.0f));
-					const V3 bone_tip = x_xform(x_affine_inverse(Cor), bone_dir);
+					X34 Cor, CorInv;
+					V3 bone_dir;
+					if ((flags & STEP_PLAIN_FRAMES) && m3_absmax(P.b) < kFiniteBound && m3_absmax(Gcur.b) < kFiniteBound) {
+						// identity orientation-axes basis: Cor.basis = P.basis * I = P.basis, so its inverse is Pinv;
+						// bone_dir = (Gcur.basis * dir_basis).xform((0,1,0)) + Gcur.origin needs column 1 only
+						Cor.b = P.b;
+						Cor.o = x_xform(P, Lor_o);
+						CorInv.b = Pinv;
+						const V3 dcol = m3_xform(Gcur.b, m3_col(ld_m3v(B.dir_basis), 1));
+						bone_dir = vadd(dcol, Gcur.o);
+					} else {
+						X34 Lor;
+						Lor.b = ld_m3v(B.orient_basis);
+						Lor.o = Lor_o;
+						Cor = x_mul(P, Lor);
+						CorInv.b = m3_inverse(Cor.b);
+						X34 Gd;
+						Gd.b = m3_mul(Gcur.b, ld_m3v(B.dir_basis));
+						Gd.o = xform_zero(Gcur);
+						bone_dir = x_xform(Gd, v3(0.0f, 1.0f, 0.0f));
+					}
+					CorInv.o = m3_xform(CorInv.b, vneg(Cor.o)); // Transform3D::affine_inverse
+					const V3 bone_tip = x_xform(CorInv, bone_dir);
 					float in_bounds;
 					V3 in_limits = point_in_limits(bone_tip, cones + S.cone_off, S.cone_cnt, in_bounds);
 					if (in_bounds < 0.0f) {
