@@ -69,8 +69,14 @@ def time_cpu_reference(rig, budget_s=12.0, steps=1, warmup=0):
     for _ in range(steps):
         O.solve_batch(rig, T, threads=cores)
     dt = time.perf_counter() - t0
+    # single-thread figure (SURVEY 8(d) CPU reference timing (i)): one pose stream on one core, ~2 s
+    n1 = int(max(64, min(rate / max(cores, 1) * 2.0, 1 << 14)))
+    t1 = time.perf_counter()
+    O.solve_batch(rig, T[:n1], threads=1)
+    dt1 = time.perf_counter() - t1
     return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} poses x {steps} pass(es) of the same workload, oracle restatement, all {cores} host threads, {dt:.1f} s"}, dt / steps * 1e3
+            "sample": f"{n} poses x {steps} pass(es) of the same workload, oracle restatement, all {cores} host threads, {dt:.1f} s",
+            "single_thread_value": n1 / dt1, "single_thread_us_per_solve": dt1 / n1 * 1e6}, dt / steps * 1e3
 
 
 # --------------------------------------------------------------------------------------------------
@@ -318,6 +324,31 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"},
     }
 
+    # ---- the other BASELINE configs (4: chain64, 30 iterations; 5: quad80, 15 iterations), device-resident, brief ----
+    other = {}
+    for name in ("chain64", "quad80"):
+        try:
+            rg = rigs.RIGS[name]()
+            Rg = BatchedIKRig(rg)
+            m = 148 * 512
+            tg = torch.from_numpy(rigs.random_targets(rg, 0, m)).to(dev)
+            og = torch.empty((m, rg.n_bones, 10), dtype=torch.float32, device=dev)
+            for _ in range(2):
+                Rg.solve_raw(m, tg, og, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(3):
+                Rg.solve_raw(m, tg, og, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+            b_.record()
+            torch.cuda.synchronize()
+            ms = a_.elapsed_time(b_) / 3
+            other[name] = {"solves_per_s": m / (ms * 1e-3), "poses": m, "iterations": rg.iterations, "ms_per_launch": ms,
+                           "flops_per_solve": Rg.info["flops_per_solve"],
+                           "fp32_roofline_frac": Rg.info["flops_per_solve"] * m / (ms * 1e-3) / 1e12 / float(tf.value) if tf.value else None}
+            del Rg, tg, og
+        except Exception as e:  # never let the side measurements break the headline line
+            other[name] = {"error": str(e)}
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         cpu_baseline, _ = time_cpu_reference(rig, budget_s=12.0)
@@ -332,6 +363,7 @@ def main():
         "latency_p50_ms_4096": p50,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "other_rigs_device_resident": other,
         "clocks": clocks,
         "device_equals_host_path": same,
     }
