@@ -245,7 +245,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 	// lanes, so the H2D copy of chunk i+1, the solve of chunk i and the D2H copy of chunk i-1 overlap.
 	std::lock_guard<std::mutex> host_lock(ds->host_mu);
 	const size_t wave = (size_t)(ds->sm_count > 0 ? ds->sm_count : 148) * mbik::kBlockThreads;
-	size_t chunk = 2 * wave;
+	size_t chunk = wave; // one kernel wave per chunk: shortest pipeline fill / drain (measured: 28.8 vs 27.7 M solves/s at two waves)
 	if (const char *env = getenv("MBIK_CHUNK_POSES")) {
 		size_t v = (size_t)atoll(env);
 		if (v > 0) {
