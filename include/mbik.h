@@ -196,6 +196,20 @@ int mbik_measure_fp32_tflops(int32_t device, int32_t reps, double *out_tflops);
  * 2^23 divisor mantissas x rounds x 64 numerators).  *out_mismatches must come back 0. */
 int mbik_selftest(int32_t device, int32_t rounds, uint64_t *out_checked, uint64_t *out_mismatches);
 
+/*
+ * Stage probes (not on the solve path): run ONE stage of the kernel's device code on caller-supplied inputs, so that
+ * the reference's own unit-test vectors (tests/test_qcp.h, tests/test_ik_kusudama_3d.h) and per-stage differential
+ * tests can be checked against the CUDA implementation directly, not only through whole solves.
+ *   mbik_stage_qcp              QCP::weighted_superpose (reference src/math/qcp.cpp:220-248): n headings (moved = tip,
+ *                               target, double weights) -> out7 = rotation quaternion xyzw + translation xyz
+ *   mbik_stage_clamp            IKBoneSegment3D::clamp_to_cos_half_angle (src/ik_bone_segment_3d.cpp:97-112), n quaternions
+ *   mbik_stage_point_in_limits  IKKusudama3D::get_local_point_in_limits (src/ik_kusudama_3d.cpp:273-332) with the cones of
+ *                               the constraint on skeleton bone `bone` of `rig`; out[n][4] = point xyz + in_bounds
+ */
+int mbik_stage_qcp(int32_t device, int32_t n, const float *moved, const float *target, const double *weight, int32_t translate, float *out7);
+int mbik_stage_clamp(int32_t device, int32_t n, const float *quats, const double *cos_half, float *out);
+int mbik_stage_point_in_limits(mbik_rig *rig, int32_t device, int32_t bone, int32_t n, const float *points, float *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,7 +59,7 @@ EXPORTED_SYMBOLS = [
     "mbik_rig_get_cone_geometry", "mbik_solve_batch", "mbik_solve_batch_multi", "mbik_alloc_pinned",
     "mbik_free_pinned", "mbik_last_kernel_ms", "mbik_measure_fp32_tflops", "mbik_selftest",
     "mbik_stream_create", "mbik_stream_destroy", "mbik_stream_submit", "mbik_stream_sync", "mbik_stream_read_local",
-    "mbik_stream_reset", "mbik_stream_frames",
+    "mbik_stream_reset", "mbik_stream_frames", "mbik_stage_qcp", "mbik_stage_clamp", "mbik_stage_point_in_limits",
 ]
 
 
@@ -150,5 +150,8 @@ def load_library():
     lib.mbik_stream_reset.argtypes = [vp, vp]
     lib.mbik_stream_frames.argtypes = [vp]
     lib.mbik_stream_frames.restype = C.c_int64
+    lib.mbik_stage_qcp.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp]
+    lib.mbik_stage_clamp.argtypes = [C.c_int32, C.c_int32, vp, vp, vp]
+    lib.mbik_stage_point_in_limits.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
     _lib = lib
     return lib

@@ -847,6 +847,93 @@ int mbik_stream_read_local(mbik_stream *st, float *out_local) {
 
 int64_t mbik_stream_frames(const mbik_stream *st) { return st ? st->frames : 0; }
 
+namespace {
+// tiny RAII device buffer for the stage probes
+struct DevBuf {
+	void *p = nullptr;
+	cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+	~DevBuf() { cudaFree(p); }
+};
+} // namespace
+
+int mbik_stage_qcp(int32_t device, int32_t n, const float *moved, const float *target, const double *weight, int32_t translate, float *out7) {
+	if (n < 0 || !out7 || (n > 0 && (!moved || !target || !weight))) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	if (mbik_device_count() <= 0) {
+		return fail(MBIK_ERR_NO_DEVICE, "no CUDA device: mbik has no CPU fallback");
+	}
+	cudaError_t e = cudaSetDevice(device);
+	DevBuf dm, dt, dw, dout;
+	if (e == cudaSuccess) e = dm.alloc(sizeof(float) * 3 * n);
+	if (e == cudaSuccess) e = dt.alloc(sizeof(float) * 3 * n);
+	if (e == cudaSuccess) e = dw.alloc(sizeof(double) * n);
+	if (e == cudaSuccess) e = dout.alloc(sizeof(float) * 7);
+	if (e == cudaSuccess && n) e = cudaMemcpy(dm.p, moved, sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess && n) e = cudaMemcpy(dt.p, target, sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess && n) e = cudaMemcpy(dw.p, weight, sizeof(double) * n, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = mbik::launch_stage_qcp(n, (const float *)dm.p, (const float *)dt.p, (const double *)dw.p, translate, (float *)dout.p);
+	if (e == cudaSuccess) e = cudaMemcpy(out7, dout.p, sizeof(float) * 7, cudaMemcpyDeviceToHost);
+	return e == cudaSuccess ? MBIK_OK : cuda_fail(e, "mbik_stage_qcp");
+}
+
+int mbik_stage_clamp(int32_t device, int32_t n, const float *quats, const double *cos_half, float *out) {
+	if (n < 0 || (n > 0 && (!quats || !cos_half || !out))) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	if (n == 0) {
+		return MBIK_OK;
+	}
+	if (mbik_device_count() <= 0) {
+		return fail(MBIK_ERR_NO_DEVICE, "no CUDA device: mbik has no CPU fallback");
+	}
+	cudaError_t e = cudaSetDevice(device);
+	DevBuf dq, dc, dout;
+	if (e == cudaSuccess) e = dq.alloc(sizeof(float) * 4 * n);
+	if (e == cudaSuccess) e = dc.alloc(sizeof(double) * n);
+	if (e == cudaSuccess) e = dout.alloc(sizeof(float) * 4 * n);
+	if (e == cudaSuccess) e = cudaMemcpy(dq.p, quats, sizeof(float) * 4 * n, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dc.p, cos_half, sizeof(double) * n, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = mbik::launch_stage_clamp(n, (const float *)dq.p, (const double *)dc.p, (float *)dout.p);
+	if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost);
+	return e == cudaSuccess ? MBIK_OK : cuda_fail(e, "mbik_stage_clamp");
+}
+
+int mbik_stage_point_in_limits(mbik_rig *rig, int32_t device, int32_t bone, int32_t n, const float *points, float *out) {
+	if (!rig || n < 0 || (n > 0 && (!points || !out))) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	const mbik::FlatRig &F = rig->flat;
+	if (bone < 0 || bone >= F.n_bones || F.t_of_bone[bone] < 0) {
+		return fail(MBIK_ERR_INVALID_ARG, "bone is not a solved bone of this rig");
+	}
+	const mbik::BlobStep *S = nullptr;
+	for (const mbik::BlobStep &st : F.steps) {
+		if (st.bone == F.t_of_bone[bone]) {
+			S = &st;
+		}
+	}
+	if (!S) {
+		return fail(MBIK_ERR_INVALID_ARG, "bone has no step");
+	}
+	if (n == 0) {
+		return MBIK_OK;
+	}
+	if (mbik_device_count() <= 0) {
+		return fail(MBIK_ERR_NO_DEVICE, "no CUDA device: mbik has no CPU fallback");
+	}
+	cudaError_t e = cudaSetDevice(device);
+	DevBuf dc, dp, dout;
+	if (e == cudaSuccess) e = dc.alloc(sizeof(mbik::BlobCone) * S->cone_cnt);
+	if (e == cudaSuccess) e = dp.alloc(sizeof(float) * 3 * n);
+	if (e == cudaSuccess) e = dout.alloc(sizeof(float) * 4 * n);
+	if (e == cudaSuccess && S->cone_cnt) e = cudaMemcpy(dc.p, F.cones.data() + S->cone_off, sizeof(mbik::BlobCone) * S->cone_cnt, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dp.p, points, sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = mbik::launch_stage_point_in_limits((const mbik::BlobCone *)dc.p, S->cone_cnt, n, (const float *)dp.p, (float *)dout.p);
+	if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost);
+	return e == cudaSuccess ? MBIK_OK : cuda_fail(e, "mbik_stage_point_in_limits");
+}
+
 void *mbik_alloc_pinned(size_t bytes) {
 	void *p = nullptr;
 	if (cudaMallocHost(&p, bytes) != cudaSuccess) {

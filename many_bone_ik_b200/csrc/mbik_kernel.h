@@ -40,4 +40,10 @@ cudaError_t launch_v2(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v3(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v4(const SolveArgs &a, int threads, cudaStream_t stream);
 
+// stage probes (mbik_selftest.cu): device pointers in, device pointers out
+struct BlobCone;
+cudaError_t launch_stage_qcp(int n, const float *d_moved, const float *d_target, const double *d_weight, int translate, float *d_out7);
+cudaError_t launch_stage_clamp(int n, const float *d_quats, const double *d_cos_half, float *d_out);
+cudaError_t launch_stage_point_in_limits(const BlobCone *d_cones, int n_cones, int n, const float *d_points, float *d_out);
+
 } // namespace mbik

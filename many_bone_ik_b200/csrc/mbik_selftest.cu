@@ -5,6 +5,7 @@
 //   vnorm / q_normalized / Basis::get_quaternion helpers: random vectors incl. zero, tiny and huge components,
 //          against the unguarded formulation
 #include "../../include/mbik.h"
+#include "mbik_kernel_body.cuh"
 #include "mbik_math.cuh"
 
 #include <cuda_runtime.h>
@@ -103,7 +104,76 @@ __global__ void vector_cases(unsigned long long *bad, unsigned long long *n, uin
 	atomicAdd(n, cnt);
 }
 
+// ---- stage probes: the kernel's own device functions on caller-supplied inputs ----
+__global__ void stage_qcp_kernel(int n, const float *moved, const float *target, const double *weight, int translate, float *out7) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) {
+		return;
+	}
+	HeadingAcc A;
+	qcp_zero(A.sums);
+	A.neg_mc = A.neg_tc = v3(0.0f, 0.0f, 0.0f);
+	for (int pass_i = translate ? 0 : 1; pass_i < 2; pass_i++) {
+		A.total_w = 0.0;
+		A.csum_m = A.csum_t = v3(0.0f, 0.0f, 0.0f);
+		for (int i = 0; i < n; i++) {
+			V3 mh = v3(moved[3 * i], moved[3 * i + 1], moved[3 * i + 2]);
+			V3 th = v3(target[3 * i], target[3 * i + 1], target[3 * i + 2]);
+			heading_emit(A, pass_i, translate != 0, th, mh, weight[i], (float)weight[i]);
+		}
+		if (pass_i == 0) { // same centroid code as solve_body
+			V3 moved_center, target_center;
+			if (A.total_w > 0.0) {
+				moved_center = vdivs(A.csum_m, (float)A.total_w);
+				target_center = vdivs(A.csum_t, (float)A.total_w);
+			} else {
+				moved_center = A.csum_m;
+				target_center = A.csum_t;
+			}
+			A.neg_mc = vmuls(moved_center, -1.0f);
+			A.neg_tc = vmuls(target_center, -1.0f);
+		}
+	}
+	Q4 q = (n == 1) ? qcp_rotation_single(A.csum_m, A.csum_t) : qcp_rotation(A.sums);
+	V3 t = vsub(vneg(A.neg_tc), vneg(A.neg_mc));
+	out7[0] = q.x; out7[1] = q.y; out7[2] = q.z; out7[3] = q.w;
+	out7[4] = t.x; out7[5] = t.y; out7[6] = t.z;
+}
+
+__global__ void stage_clamp_kernel(int n, const float *quats, const double *cos_half, float *out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) {
+		return;
+	}
+	Q4 q = clamp_to_cos_half_angle(q4(quats[4 * i], quats[4 * i + 1], quats[4 * i + 2], quats[4 * i + 3]), cos_half[i]);
+	out[4 * i] = q.x; out[4 * i + 1] = q.y; out[4 * i + 2] = q.z; out[4 * i + 3] = q.w;
+}
+
+__global__ void stage_point_in_limits_kernel(const BlobCone *cones, int n_cones, int n, const float *points, float *out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) {
+		return;
+	}
+	float in_bounds;
+	V3 p = point_in_limits(v3(points[3 * i], points[3 * i + 1], points[3 * i + 2]), cones, n_cones, in_bounds);
+	out[4 * i] = p.x; out[4 * i + 1] = p.y; out[4 * i + 2] = p.z; out[4 * i + 3] = in_bounds;
+}
+
 } // namespace
+
+namespace mbik {
+cudaError_t launch_stage_qcp(int n, const float *d_moved, const float *d_target, const double *d_weight, int translate, float *d_out7) {
+	stage_qcp_kernel<<<1, 32>>>(n, d_moved, d_target, d_weight, translate, d_out7);
+	return cudaGetLastError();
+}
+cudaError_t launch_stage_clamp(int n, const float *d_quats, const double *d_cos_half, float *d_out) {
+	stage_clamp_kernel<<<(n + 127) / 128, 128>>>(n, d_quats, d_cos_half, d_out);
+	return cudaGetLastError();
+}
+cudaError_t launch_stage_point_in_limits(const BlobCone *d_cones, int n_cones, int n, const float *d_points, float *d_out) {
+	stage_point_in_limits_kernel<<<(n + 127) / 128, 128>>>(d_cones, n_cones, n, d_points, d_out);
+	return cudaGetLastError();
+}
+} // namespace mbik
 
 extern "C" {
 #pragma GCC visibility push(default)
