@@ -327,3 +327,69 @@ def test_non_finite_targets_propagate_like_the_reference():
     Tq[::3, ::2, 9:] *= np.float32(1e19)
     Tq[1::3, 1::2, :9] = 0.0
     _assert_same(q, BatchedIKRig(q).solve(Tq, want_local=True), O.solve_batch(q, Tq, want_local=True, threads=8))
+
+
+def test_concurrent_host_calls_on_one_rig():
+    """mbik_rig is shareable across threads: concurrent host-buffer solves on one (rig, device) take turns on the
+    staging lanes; concurrent device-buffer solves on separate streams overlap.  Every result equals the serial one."""
+    import threading
+    import torch
+    rig = rigs.humanoid22()
+    R = BatchedIKRig(rig)
+    n = 20000
+    Ts = [rigs.random_targets(rig, 50000 * k, n) for k in range(4)]
+    serial = [R.solve(T)[0] for T in Ts]
+    got = [None] * 4
+
+    def work(k):
+        got[k] = R.solve(Ts[k])[0]
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for k in range(4):
+        assert np.array_equal(got[k], serial[k], equal_nan=True), k
+    # device path, one stream per thread
+    dev = torch.device("cuda", 0)
+    outs = [torch.empty((n, rig.n_bones, 10), dtype=torch.float32, device=dev) for _ in range(4)]
+    tds = [torch.from_numpy(T).to(dev) for T in Ts]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+
+    def work_dev(k):
+        R.solve_raw(n, tds[k], outs[k], device=0, flags=_capi.MBIK_IO_DEVICE, stream=streams[k].cuda_stream)
+
+    th = [threading.Thread(target=work_dev, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    torch.cuda.synchronize()
+    for k in range(4):
+        assert np.array_equal(outs[k].cpu().numpy(), serial[k], equal_nan=True), k
+
+
+def test_rig_and_stream_lifecycle_does_not_leak_device_memory():
+    import torch
+    from many_bone_ik_b200 import IKStream
+    rig = rigs.quad80()
+    T = rigs.random_targets(rig, 0, 2048)
+
+    def cycle():
+        R = BatchedIKRig(rig)
+        R.solve(T)
+        S = IKStream(R, 2048)
+        S.submit(T, None, None)
+        S.sync()
+        S.close()
+        R.close()
+
+    cycle()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    for _ in range(20):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free0 - free1 < 8 * 1024 * 1024, (free0, free1)
