@@ -1,10 +1,10 @@
-// mbik_kernel_body.cuh -- the fused sm_100a solve kernel (included by the mbik_kernel_*.cu variant units): ALL iterations of the ManyBoneIK solve loop for a
-// batch of independent skeleton poses in one launch.
+// mbik_kernel_body.cuh -- the fused sm_100a solve kernel (instantiated per size variant in mbik_kernel_v*.cu):
+// ALL iterations of the ManyBoneIK solve loop for a batch of independent skeleton poses in one launch.
 //
 // Replaces (reference, /root/reference):
 //   ManyBoneIK3D::_process_modification iteration loop      src/many_bone_ik_3d.cpp:685-692
 //   IKBoneSegment3D::segment_solver / _qcp_solver           src/ik_bone_segment_3d.cpp:210-240
-//   _update_optimal_rotation / _set_optimal_rotation        src/ik_bone_segment_3d.cpp:90-181
+//   _update_optimal_rotation / _set_optimal_rotation        src/ik_bone_segment_3d.cpp:90-181 (incl. stabilisation :163-176)
 //   IKEffector3D::update_effector_{target,tip}_headings     src/ik_effector_3d.cpp:90-149
 //   QCP::weighted_superpose                                 src/math/qcp.cpp:56-248
 //   IKKusudama3D::snap_to_orientation_limit / twist         src/ik_kusudama_3d.cpp:117-158, 273-376
@@ -12,15 +12,16 @@
 //   IKNode3D lazy global-transform cache                    src/math/ik_node_3d.cpp (explicit FK here)
 //   IKBone3D::set_skeleton_bone_pose write-back             src/ik_bone_3d.cpp:170-179
 //
-// Mapping: one THREAD per pose (the poses of a batch are independent and the per-pose work is a long
-// serial chain of tiny 3x3 ops, so lanes-over-poses is the only mapping that keeps all 32 lanes busy).
-// Rig constants (mbik_blob.h) are staged once per CTA into shared memory by a single TMA bulk copy
-// (cp.async.bulk + mbarrier) and read as warp-wide broadcasts.  Per-pose state -- the local transform of
-// every solved bone and a cache of global transforms -- lives in thread-local arrays (lane-interleaved,
-// L1-resident).  FP32 CUDA cores (+ FP64 where the reference computes in double); no tensor cores: no
-// stage is a dense contraction.  All arithmetic is individually rounded (mbik_math.cuh), which makes the
-// result bit-identical to the reference arithmetic -- required, because in float32 the reference's
-// constraint snaps amplify rounding differences by O(chain length) per iteration.
+// Mapping: one THREAD per pose (the poses of a batch are independent and the per-pose work is a long serial chain of
+// tiny 3x3 ops, so lanes-over-poses is the only mapping that keeps all 32 lanes busy); 512-thread CTAs, one per SM,
+// kept in lockstep per bone-step because the step body (~70 KB of SASS) streams through the instruction cache.
+// Rig constants (mbik_blob.h) are staged once per CTA into shared memory by a single TMA bulk copy (cp.async.bulk +
+// mbarrier) and read as warp-wide broadcasts.  Per-pose state: the local transform of every solved bone in a
+// thread-local array (lane-interleaved, L1/L2 resident); the current segment's parent-global chain and the walk stack
+// in [word][thread] shared-memory columns when they fit (else thread-local).  FP32 CUDA cores (+ FP64 where the
+// reference computes in double); no tensor cores: no stage is a dense contraction.  All arithmetic is individually
+// rounded (mbik_math.cuh), which makes the result bit-identical to the reference arithmetic -- required, because in
+// float32 the reference's constraint snaps amplify rounding differences by O(chain length) per iteration.
 #pragma once
 #include "mbik_blob.h"
 #include "mbik_kernel.h"
