@@ -264,6 +264,25 @@ def main():
     barrier()
     e2e_value = total * args.steps / e2e_s
 
+    # ---- side measurement: BASELINE configs[2] read literally = ONE 2^20-pose batch sharded over the N GPUs (strong
+    # scaling; each rank solves the first 2^20/N poses of its buffer), device-resident ----
+    strong = None
+    if world > 1:
+        ns = min(n, (1 << 20) // world)
+        for _ in range(2):
+            R.solve_raw(ns, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            R.solve_raw(ns, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+        s1.record()
+        torch.cuda.synchronize()
+        strong_ms = max_over_ranks(s0.elapsed_time(s1))
+        barrier()
+        strong = {"total_poses": ns * world, "poses_per_gpu": ns, "value": ns * world * args.steps / (strong_ms * 1e-3), "unit": UNIT,
+                  "ms_per_step": strong_ms / args.steps}
+
     # correctness guard on a small sample of what was just computed (device path == host path, finite)
     chk = min(n, 1024)
     same = bool(torch.equal(o_dev[:chk].cpu(), o_host[:chk]))
@@ -364,6 +383,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "other_rigs_device_resident": other,
+        "strong_scaling_1M_batch": strong,
         "clocks": clocks,
         "device_equals_host_path": same,
     }
