@@ -143,3 +143,18 @@ def test_point_in_limits_stage_equals_oracle(n_cones):
             o_pt, o_ib = O.kusudama_point_in_limits(np.array(cones, np.float32), pts[i])
             assert np.array_equal(g_pt[i], o_pt, equal_nan=True), (trial, i, g_pt[i], o_pt)
             assert g_ib[i] == o_ib, (trial, i, g_ib[i], o_ib)
+
+
+def test_reference_cases_in_cpp_through_the_c_abi(tmp_path):
+    """tests/cpp/reference_cases_gpu.cpp: the reference's doctest cases, same names / inputs / CHECKs, in C++ against
+    libmbik.so (stage probes + the ManyBoneIK3D facade for the kusudama set-up)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "many_bone_ik_b200")
+    exe = os.path.join(str(tmp_path), "refcases")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(root, "tests", "cpp", "reference_cases_gpu.cpp"),
+                           "-L" + pkg, "-l:libmbik.so", "-Wl,-rpath," + pkg, "-ldl", "-lpthread", "-lrt"])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failed" in r.stdout
