@@ -393,3 +393,22 @@ def test_rig_and_stream_lifecycle_does_not_leak_device_memory():
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info(0)
     assert free0 - free1 < 8 * 1024 * 1024, (free0, free1)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_overflow_fuzz_random_rigs(seed):
+    """Targets scaled by 1e5 ... 1e37 (and 1e-30) on random rigs, 12 iterations: poses overflow to Inf / NaN part-way.
+    Every guarded fast path and finite-operand shortcut of the kernel must hand over to the literal IEEE formulation
+    exactly where it matters: raw locals equal the oracle NaN-for-NaN, status words equal."""
+    rig = rig_cases.random_rig(seed)
+    rig.iterations = 12
+    rng = np.random.default_rng(seed)
+    n = 64
+    T = rigs.random_targets(rig, 0, n)
+    T[:, :, 9:] *= np.float32(10.0) ** rng.integers(5, 38, size=(n, 1, 1)).astype(np.float32)
+    if seed % 3 == 0:
+        T[:, :, :9] *= np.float32(10.0) ** rng.integers(0, 20, size=(n, 1, 1)).astype(np.float32)
+    if seed % 4 == 0:
+        T[::5] = np.float32(1e-30) * T[::5]
+    R = BatchedIKRig(rig)
+    _assert_same(rig, R.solve(T, want_local=True), O.solve_batch(rig, T, want_local=True, threads=8))
