@@ -569,6 +569,11 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	// stabilisation only (STAB variants): effector-bone origins from before the step (what the step's target
 	// headings were built from) and the segment's previous_deviation (src/ik_bone_segment_3d.h:63)
 	float TipO[STAB ? kMaxStabEffectors * 3 : 1];
+	// translating (root) segments build every heading twice (centroid pass, inner-product pass): on the large-rig
+	// variants the effector frames of the first pass are kept, so the second pass needs no walk (chain64: 8 steps x
+	// 56-bone walks per iteration)
+	constexpr int ECACHE = NB >= 64 ? 16 : 0;
+	float Efr[ECACHE > 0 ? ECACHE * 12 : 1];
 	double prev_dev = (double)INFINITY;
 
 	// seed: ManyBoneIK3D::_update_ik_bones_transform -> IKBone3D::set_initial_pose (src/ik_bone_3d.cpp:161-168)
@@ -647,9 +652,23 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					Gstk.st(0, Gb);
 				}
 				// pass 0 (translating root segment only): weighted centroids; pass 1: inner product (:225-248)
+				const bool cache_frames = ECACHE > 0 && translate && S.eff_cnt <= ECACHE;
 				for (int pass_i = translate ? 0 : 1; pass_i < 2; pass_i++) {
 					A.total_w = 0.0;
 					A.csum_m = A.csum_t = v3(0.0f, 0.0f, 0.0f);
+					if (ECACHE > 0 && cache_frames && pass_i == 1) {
+						// second pass of a translating step from the cached effector frames (same frames, same order)
+						for (int e = 0; e < S.eff_cnt; e++) {
+							const BlobEff &E = effs[S.eff_off + e];
+							const X34 Ge = (e == 0 && (flags & STEP_SELF_EFF)) ? Gb : ld_x34(Efr, e);
+							const V3 tO = xform_zero(Ge);
+							if (STAB) {
+								TipO[3 * e] = tO.x; TipO[3 * e + 1] = tO.y; TipO[3 * e + 2] = tO.z;
+							}
+							effector_headings(A, 1, true, E, Ge, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, tO);
+						}
+						continue;
+					}
 					if (flags & STEP_SELF_EFF) {
 						const BlobEff &E = effs[S.eff_off];
 						const V3 tO = xform_zero(Gb);
@@ -696,6 +715,9 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 							}
 							if (!MBIK_PIPE_T) {
 								T = ldg_x34(my_targets + (size_t)E.pin * 12);
+							}
+							if (ECACHE > 0 && cache_frames && pass_i == 0) {
+								st_x34(Efr, op.eff, run);
 							}
 							effector_headings(A, pass_i, translate, E, run, ld_m3v(bones[E.bone].dir_basis), T, bo, tO);
 						}
