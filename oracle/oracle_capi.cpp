@@ -328,6 +328,70 @@ void orc_swing_twist_y(const float *q4, float *out8) {
 	out8[4] = t.x; out8[5] = t.y; out8[6] = t.z; out8[7] = t.w;
 }
 
+// Engine-math shim probes (oracle/godot_math.h): the Godot core/math functions the solve path calls, exposed so that
+// tests can check their mathematical properties independently (the engine source is not in the reference tree).
+//   op 0: Basis(Quaternion in[0..3])                         -> out[0..8]
+//   op 1: Basis(in[0..8]).get_quaternion()                   -> out[0..3]
+//   op 2: Basis(in[0..8]).get_rotation_quaternion()          -> out[0..3]
+//   op 3: Basis(in[0..8]).orthonormalized()                  -> out[0..8]
+//   op 4: Basis(in[0..8]).inverse()                          -> out[0..8]
+//   op 5: Quaternion(Vector3 in[0..2], Vector3 in[3..5])     -> out[0..3]   (shortest arc)
+//   op 6: Quaternion(in[0..3]).xform(Vector3 in[4..6])       -> out[0..2]
+//   op 7: Basis(in[0..8]).slerp(Basis(in[9..17]), in[18])    -> out[0..8]
+//   op 8: Quaternion(Vector3 axis in[0..2], angle in[3])     -> out[0..3]
+//   op 9: Transform3D(in[0..11]).affine_inverse()            -> out[0..11]
+//   op 10: Basis(in[0..8]) * Basis(in[9..17])                -> out[0..8]
+//   op 11: Basis(in[0..8]).get_scale()                       -> out[0..2]
+int orc_math_probe(int op, const float *in, float *out) {
+	auto load_b = [](const float *p) {
+		Basis b;
+		for (int r = 0; r < 3; r++) {
+			for (int c = 0; c < 3; c++) {
+				b.rows[r][c] = p[r * 3 + c];
+			}
+		}
+		return b;
+	};
+	auto store_b = [](const Basis &b, float *p) {
+		for (int r = 0; r < 3; r++) {
+			for (int c = 0; c < 3; c++) {
+				p[r * 3 + c] = b.rows[r][c];
+			}
+		}
+	};
+	auto store_q = [](const Quaternion &q, float *p) {
+		p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
+	};
+	switch (op) {
+		case 0: store_b(Basis(Quaternion(in[0], in[1], in[2], in[3])), out); return 0;
+		case 1: store_q(load_b(in).get_quaternion(), out); return 0;
+		case 2: store_q(load_b(in).get_rotation_quaternion(), out); return 0;
+		case 3: store_b(load_b(in).orthonormalized(), out); return 0;
+		case 4: store_b(load_b(in).inverse(), out); return 0;
+		case 5: store_q(Quaternion(Vector3(in[0], in[1], in[2]), Vector3(in[3], in[4], in[5])), out); return 0;
+		case 6: {
+			Vector3 v = Quaternion(in[0], in[1], in[2], in[3]).xform(Vector3(in[4], in[5], in[6]));
+			out[0] = v.x; out[1] = v.y; out[2] = v.z;
+			return 0;
+		}
+		case 7: store_b(load_b(in).slerp(load_b(in + 9), in[18]), out); return 0;
+		case 8: store_q(Quaternion(Vector3(in[0], in[1], in[2]), in[3]), out); return 0;
+		case 9: {
+			Transform3D t = load_xform(in).affine_inverse();
+			store_b(t.basis, out);
+			out[9] = t.origin.x; out[10] = t.origin.y; out[11] = t.origin.z;
+			return 0;
+		}
+		case 10: store_b(load_b(in) * load_b(in + 9), out); return 0;
+		case 11: {
+			Vector3 v = load_b(in).get_scale();
+			out[0] = v.x; out[1] = v.y; out[2] = v.z;
+			return 0;
+		}
+		default: return -1;
+	}
+}
+
 int orc_hardware_threads(void) {
 	unsigned n = std::thread::hardware_concurrency();
 	return n ? (int)n : 1;

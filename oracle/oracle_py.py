@@ -39,6 +39,7 @@ def lib():
         L.orc_kusudama_point_in_limits.argtypes = [vp, C.c_int, vp, vp]
         L.orc_clamp_to_cos_half_angle.argtypes = [vp, C.c_double, vp]
         L.orc_swing_twist_y.argtypes = [vp, vp]
+        L.orc_math_probe.argtypes = [C.c_int, vp, vp]
         L.orc_hardware_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -140,6 +141,21 @@ def swing_twist_y(q):
     out = np.zeros(8, np.float32)
     L.orc_swing_twist_y(_p(q), _p(out))
     return out[:4].copy(), out[4:].copy()
+
+
+MATH_OPS = dict(basis_from_quat=0, get_quaternion=1, get_rotation_quaternion=2, orthonormalized=3, inverse=4, shortest_arc=5,
+                quat_xform=6, basis_slerp=7, quat_axis_angle=8, affine_inverse=9, basis_mul=10, get_scale=11)
+_MATH_OUT = {0: 9, 1: 4, 2: 4, 3: 9, 4: 9, 5: 4, 6: 3, 7: 9, 8: 4, 9: 12, 10: 9, 11: 3}
+
+
+def math_probe(op, *args):
+    """One function of the Godot core/math shim (oracle/godot_math.h) on float32 inputs."""
+    L = lib()
+    code = MATH_OPS[op]
+    inp = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float32).reshape(-1) for a in args]), np.float32)
+    out = np.zeros(_MATH_OUT[code], np.float32)
+    assert L.orc_math_probe(code, _p(inp), _p(out)) == 0
+    return out
 
 
 def run_kat():
