@@ -360,40 +360,53 @@ __device__ __forceinline__ V3 point_in_limits(V3 in_point, const BlobCone *cones
 
 // IKKusudama3D::get_swing_twist about +Y followed by the twist clamp and recomposition
 // (src/ik_kusudama_3d.cpp:117-158); returns the new LOCAL basis of the bone
-__device__ __forceinline__ M3 twist_snap(const M3 &Pb, const M3 &Pinv, const M3 &Lb, const M3 &twist_basis, const M3 &twist_center, float twist_cos) {
+template <class Ops>
+__device__ __forceinline__ M3 twist_snap_t(const M3 &Pb, const M3 &Pinv, const M3 &Lb, const M3 &twist_basis, const M3 &twist_center, float twist_cos, Ops &ops) {
 	M3 ctw = m3_mul(Pb, twist_basis); // global basis of the twist-axes node
 	M3 gts = m3_mul(Pb, Lb);          // global basis of the bone
 	M3 gtc = m3_mul(ctw, twist_center);
-	M3 align = m3_orthonormalized(m3_mul(m3_inverse(gtc), gts));
-	Q4 rot = m3_get_rotation_quat(align);
+	M3 align = m3_orthonormalized_t(m3_mul(m3_inverse_t(gtc, ops), gts), ops);
+	Q4 rot = m3_get_rotation_quat_t(align, ops);
 	if (rot.w < 0.0f) {
 		rot = q_muls(rot, -1.0f);
 	}
 	const V3 axis = v3(0.0f, 1.0f, 0.0f);
 	float pd = r_add(r_add(r_mul(rot.x, axis.x), r_mul(rot.y, axis.y)), r_mul(rot.z, axis.z));
 	V3 p = vmuls(axis, pd);
-	Q4 tw = q_normalized(q4(p.x, p.y, p.z, rot.w));
+	Q4 tw = q_normalized_t(q4(p.x, p.y, p.z, rot.w), ops);
 	float dd = vdot(v3(tw.x, tw.y, tw.z), axis);
 	if (dd < 0.0f) {
 		tw = q_muls(tw, -1.0f);
 	}
-	Q4 sw = q_normalized(q_mul(rot, q4(-tw.x, -tw.y, -tw.z, tw.w)));
+	Q4 sw = q_normalized_t(q_mul(rot, q4(-tw.x, -tw.y, -tw.z, tw.w)), ops);
 	tw = clamp_to_cos_half_angle(tw, (double)twist_cos);
-	M3 recomposition = m3_orthonormalized(m3_mul(gtc, m3_from_quat(q_mul(sw, tw))));
+	M3 recomposition = m3_orthonormalized_t(m3_mul(gtc, m3_from_quat_t(q_mul(sw, tw), ops)), ops);
 	return m3_mul(Pinv, recomposition);
+}
+// guarded straight-line evaluation; lanes whose evaluation reported an operand out of range redo the stage with the
+// literal formulation (cold code, same registers: no call, no arguments through memory)
+__device__ __forceinline__ M3 twist_snap(const M3 &Pb, const M3 &Pinv, const M3 &Lb, const M3 &twist_basis, const M3 &twist_center, float twist_cos) {
+	CheckedOps ops;
+	M3 r = twist_snap_t(Pb, Pinv, Lb, twist_basis, twist_center, twist_cos, ops);
+	if (!ops.ok) {
+		ExactOps exact;
+		r = twist_snap_t(Pb, Pinv, Lb, twist_basis, twist_center, twist_cos, exact);
+	}
+	return r;
 }
 
 // damping clamp + the (numerically no-op) slerp toward the current global basis with weight 0
 // (src/ik_bone_segment_3d.cpp:143-151)
-__device__ __forceinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const M3 &Gb, bool gb_bounded) {
-	M3 rot = m3_from_quat(q);
-	Q4 cq = clamp_to_cos_half_angle(m3_get_rotation_quat(rot), cos_half_damp);
-	M3 R1 = m3_from_quat(cq);
+template <class Ops>
+__device__ __forceinline__ M3 damp_and_slerp0_t(Q4 q, double cos_half_damp, const M3 &Gb, bool gb_bounded, Ops &ops) {
+	M3 rot = m3_from_quat_t(q, ops);
+	Q4 cq = clamp_to_cos_half_angle(m3_get_rotation_quat_t(rot, ops), cos_half_damp);
+	M3 R1 = m3_from_quat_t(cq, ops);
 	// Basis::slerp(to, 0): Quaternion(from).slerp(Quaternion(to), 0) is scale0 = 1, scale1 = 0 on every
 	// branch of Quaternion::slerp (sin(w)/sin(w) == 1 exactly); the 0 * to terms are kept so that a
 	// non-finite global basis poisons the result exactly as it does in the reference.
-	Q4 from = m3_get_quat(R1);
-	Q4 to = m3_get_quat(Gb);
+	Q4 from = m3_get_quat_t(R1, ops);
+	Q4 to = m3_get_quat_t(Gb, ops);
 	Q4 sl = from;
 	// finite `to`: from * 1 + to * 0 == from
 	if (!(max3_abs_nan(max3_abs_nan(to.x, to.y, to.z), to.w, 0.0f) < kFiniteBound)) {
@@ -404,10 +417,10 @@ __device__ __forceinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const 
 		sl = q4(r_add(r_mul(1.0f, from.x), r_mul(0.0f, to.x)), r_add(r_mul(1.0f, from.y), r_mul(0.0f, to.y)),
 				r_add(r_mul(1.0f, from.z), r_mul(0.0f, to.z)), r_add(r_mul(1.0f, from.w), r_mul(0.0f, to.w)));
 	}
-	M3 b = m3_from_quat(sl);
+	M3 b = m3_from_quat_t(sl, ops);
 #pragma unroll
 	for (int i = 0; i < 3; i++) {
-		float la = vlen(m3_row(R1, i));
+		float la = ops.sqrt(vlen2(m3_row(R1, i)));
 		// Math::lerp(la, lb, 0) = la + (lb - la) * 0 with lb = |row i of Gb|: for bounded Gb, lb is finite, so the
 		// second term is 0 for finite la and NaN otherwise -- exactly la * 0
 		float f = gb_bounded ? r_add(la, r_mul(la, 0.0f)) : r_add(la, r_mul(r_sub(vlen(m3_row(Gb, i)), la), 0.0f));
@@ -416,6 +429,15 @@ __device__ __forceinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const 
 		b.m[3 * i + 2] = r_mul(b.m[3 * i + 2], f);
 	}
 	return b;
+}
+__device__ __forceinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const M3 &Gb, bool gb_bounded) {
+	CheckedOps ops;
+	M3 r = damp_and_slerp0_t(q, cos_half_damp, Gb, gb_bounded, ops);
+	if (!ops.ok) {
+		ExactOps exact;
+		r = damp_and_slerp0_t(q, cos_half_damp, Gb, gb_bounded, exact);
+	}
+	return r;
 }
 
 // IKBone3D::set_skeleton_bone_pose (src/ik_bone_3d.cpp:170-179): position, rotation quaternion, scale

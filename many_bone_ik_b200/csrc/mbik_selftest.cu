@@ -69,6 +69,15 @@ __device__ V3 vnorm_plain(V3 a) {
 }
 __device__ bool same(float a, float b) { return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b); }
 
+__device__ bool mode_all_ordinary(const float *c) {
+	bool ok = true;
+	for (int i = 0; i < 4; i++) {
+		float a = fabsf(c[i]);
+		ok = ok && a >= 0.0625f && a <= 16.0f;
+	}
+	return ok;
+}
+
 __global__ void vector_cases(unsigned long long *bad, unsigned long long *n, uint32_t round) {
 	uint64_t h = splitmix(((uint64_t)round << 40) ^ ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x));
 	unsigned long long cnt = 0, bd = 0;
@@ -98,7 +107,35 @@ __global__ void vector_cases(unsigned long long *bad, unsigned long long *n, uin
 		sqrt_then_div(c[3], 0.5f, s, d);
 		float s2 = __fsqrt_rn(c[3]);
 		bd += !(same(s, s2) && same(d, __fdiv_rn(0.5f, s2)));
-		cnt += 3;
+		// CheckedOps: wherever it reports ok, its values equal the literal IEEE formulation
+		{
+			CheckedOps co;
+			V3 g = co.normalized(a);
+			if (co.ok) {
+				bd += !(same(g.x, p.x) && same(g.y, p.y) && same(g.z, p.z));
+			}
+			CheckedOps c2;
+			float s3, d3;
+			c2.sqrt_then_div(c[3], 0.5f, s3, d3);
+			if (c2.ok) {
+				bd += !(same(s3, s2) && same(d3, __fdiv_rn(0.5f, s2)));
+			}
+			CheckedOps c3;
+			float q3 = c3.div_const(2.0f, c[2]);
+			if (c3.ok) {
+				bd += !same(q3, __fdiv_rn(2.0f, c[2]));
+			}
+			CheckedOps c4;
+			float r4 = c4.sqrt(c[1]);
+			if (c4.ok) {
+				bd += !same(r4, __fsqrt_rn(c[1]));
+			}
+			// and it must report ok for ordinary operands (otherwise the fast path would never be taken)
+			if (mode_all_ordinary(c)) {
+				bd += !(co.ok && c3.ok);
+			}
+		}
+		cnt += 7;
 	}
 	atomicAdd(bad, bd);
 	atomicAdd(n, cnt);
