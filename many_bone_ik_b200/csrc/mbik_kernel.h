@@ -7,7 +7,7 @@
 namespace mbik {
 
 constexpr int kBlockThreads = 512; // poses per CTA: one CTA per SM (128 registers per thread), all of its warps kept in lockstep
-constexpr int kStabBlockThreads = 256; // CTA size of the stabilisation variants
+constexpr int kStabBlockThreads = 512; // CTA size of the stabilisation variants
 constexpr int kMaxStabEffectors = 32;  // effectors per root-segment list the stabilisation variants can hold
 
 struct SolveArgs {
