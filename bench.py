@@ -176,7 +176,7 @@ def main():
     import torch.distributed as dist
 
     from many_bone_ik_b200 import BatchedIKRig, rigs, sharding
-    from many_bone_ik_b200._capi import MBIK_IO_DEVICE, MBIK_IO_HOST
+    from many_bone_ik_b200._capi import MBIK_IO_DEVICE, MBIK_IO_HOST, MBIK_SCHED_THROUGHPUT
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: many_bone_ik_b200 has no CPU fallback")
@@ -295,16 +295,21 @@ def main():
     # ---- p50 latency of a 4096-pose batch, device-resident (BASELINE configs[1]) ----
     lt = t_dev[:LATENCY_BATCH].contiguous()
     lo_ = torch.empty((LATENCY_BATCH, nb, 10), dtype=torch.float32, device=dev)
-    lat = []
-    for i in range(220):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        R.solve_raw(LATENCY_BATCH, lt, lo_, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
-        b.record()
-        torch.cuda.synchronize()
-        if i >= 20:
-            lat.append(a.elapsed_time(b))
-    p50 = float(np.median(lat))
+    # the library picks the segment-parallel mapping for a batch this small (32 poses per CTA, one warp per concurrently
+    # solvable segment); the one-thread-per-pose mapping is timed next to it for comparison
+    def _p50(extra_flags):
+        lat = []
+        for i in range(220):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            R.solve_raw(LATENCY_BATCH, lt, lo_, device=local_rank, flags=MBIK_IO_DEVICE | extra_flags, stream=stream)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 20:
+                lat.append(a.elapsed_time(b))
+        return float(np.median(lat))
+    p50 = _p50(0)
+    p50_thread_per_pose = _p50(MBIK_SCHED_THROUGHPUT)
 
     # ---- roofline of the one kernel (FP32 CUDA cores; HBM shown as the sanity figure) ----
     import ctypes as C
@@ -380,6 +385,7 @@ def main():
                 "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": args.steps * world,
         "latency_p50_ms_4096": p50,
+        "latency_p50_ms_4096_thread_per_pose_mapping": p50_thread_per_pose,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "other_rigs_device_resident": other,

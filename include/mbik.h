@@ -97,6 +97,16 @@ typedef struct mbik_solve_params {
 #define MBIK_IO_HOST 0u   /* buffers are host memory (pinned or pageable); the call copies, solves and returns when done */
 #define MBIK_IO_DEVICE 1u /* buffers are device memory on params->device; the call enqueues on params->stream and returns */
 
+/* Kernel mapping (default: chosen by batch size).  Both mappings run the same per-pose arithmetic in the same order
+ * and return identical bits; these flags exist for tests and measurements.
+ *   THROUGHPUT        one thread per pose, 512-pose CTAs in lockstep (large batches)
+ *   SEGMENT_PARALLEL  32 poses per CTA, one warp per concurrently solvable segment: sibling segments of the segment
+ *                     tree are independent in IKBoneSegment3D::segment_solver's post-order recursion (reference
+ *                     src/ik_bone_segment_3d.cpp:210-225), so the latency of a small batch is the critical path of
+ *                     the tree instead of the whole bone list; ignored for rigs whose tree is a single chain */
+#define MBIK_SCHED_THROUGHPUT 2u
+#define MBIK_SCHED_SEGMENT_PARALLEL 4u
+
 typedef struct mbik_rig mbik_rig; /* opaque: host schedule + per-device copies */
 
 /* Schedule facts, for tests and callers that size buffers. */
@@ -115,6 +125,9 @@ typedef struct mbik_rig_info {
 	double flops_per_solve;   /* algorithmic flop floor, SURVEY.md section 8(d) convention */
 	int32_t max_segment_len;  /* bones in the longest kept segment */
 	int32_t max_walk_stack;   /* branch-point stack depth of the deepest effector walk */
+	int32_t sp_roles;         /* segment-parallel schedule: warps per 32-pose group (<= 1: the tree is a chain) */
+	int32_t sp_phases;        /* barrier-separated phases per iteration (= height of the segment tree) */
+	double sp_gain;           /* estimated serial cost / critical-path cost of that schedule */
 } mbik_rig_info;
 
 int mbik_device_count(void);

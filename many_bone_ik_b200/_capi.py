@@ -46,11 +46,14 @@ class RigInfo(C.Structure):
     _fields_ = [("n_bones", C.c_int32), ("n_solved", C.c_int32), ("n_segments", C.c_int32), ("n_steps", C.c_int32),
                 ("n_effectors", C.c_int32), ("n_pins", C.c_int32), ("max_headings", C.c_int32), ("n_cones", C.c_int32),
                 ("iterations", C.c_int32), ("kernel_capacity", C.c_int32), ("rig_blob_bytes", C.c_int64),
-                ("flops_per_solve", C.c_double), ("max_segment_len", C.c_int32), ("max_walk_stack", C.c_int32)]
+                ("flops_per_solve", C.c_double), ("max_segment_len", C.c_int32), ("max_walk_stack", C.c_int32),
+                ("sp_roles", C.c_int32), ("sp_phases", C.c_int32), ("sp_gain", C.c_double)]
 
 
 MBIK_IO_HOST = 0
 MBIK_IO_DEVICE = 1
+MBIK_SCHED_THROUGHPUT = 2
+MBIK_SCHED_SEGMENT_PARALLEL = 4
 
 # every symbol include/mbik.h declares (tests check the library exports exactly these)
 EXPORTED_SYMBOLS = [

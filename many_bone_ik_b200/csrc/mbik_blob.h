@@ -3,7 +3,7 @@
 // One contiguous, 16-byte aligned blob of rig constants.  The kernel stages it into shared memory
 // with one TMA bulk copy per CTA; every lane then reads the same words (broadcast).  Layout:
 //   BlobHeader | BlobStep[n_steps] | BlobBone[n_solved] | BlobEff[n_effs] | BlobFk[n_fk] |
-//   BlobCone[n_cones] | BlobPass[n_pass] | chain[n_chain] (int16) | rest_local[n_bones*12]
+//   BlobCone[n_cones] | BlobPass[n_pass] | chain[n_chain] (int16) | rest_local[n_bones*12] | BlobSpan[sp_phases*sp_slots*sp_roles]
 // Solved bones are renumbered in depth-first preorder ("t index": parents before children, children in
 // the reference's ascending order), which is also the order in which a segment's effector list
 // enumerates its effectors.
@@ -32,8 +32,11 @@ struct BlobHeader {
 	uint32_t total_bytes; // multiple of 16
 	int32_t n_bones, n_solved, n_steps, n_pins, n_effs, n_fk, n_cones, n_pass;
 	int32_t iterations, constraint_mode, stabilization_passes, n_chain;
-	int32_t max_seg_len, max_stack, reserved0, reserved1;
-	uint32_t off_steps, off_bones, off_effs, off_fk, off_cones, off_pass, off_rest, off_chain;
+	int32_t max_seg_len, max_stack;
+	// segment-parallel schedule (see BlobSpan): sibling segments of the segment tree are independent, so a group of
+	// `sp_roles` warps can solve them concurrently; sp_roles <= 1 means the tree offers no parallelism
+	int32_t sp_roles, sp_phases, sp_slots, reserved0;
+	uint32_t off_steps, off_bones, off_effs, off_fk, off_cones, off_pass, off_rest, off_chain, off_sched, reserved1;
 };
 
 struct BlobStep { // 64 bytes
@@ -100,6 +103,17 @@ struct BlobCone { // 160 bytes
 	float t2xc1[3];         // (tc2 x cp).normalized()           (:305)
 	float c2xt2[3];         // (next.cp x tc2).normalized()      (:306)
 	float pad[5];
+};
+
+// Segment-parallel schedule: spans[(phase * sp_slots + slot) * sp_roles + role] = the step range [s0, s1) that warp
+// `role` of a pose group runs in that slot of that phase (s0 == s1: idle).  A span is always one whole kept segment
+// (segment_solver's post-order recursion, reference src/ik_bone_segment_3d.cpp:210-225: a segment only reads its
+// ancestors' bones, which no segment of the same or an earlier phase writes, and the bones of its own subtree, which
+// are final once its child segments -- all in earlier phases -- are done).  All roles meet at a barrier after each phase.
+constexpr int kMaxSpRoles = 8; // warps per pose group of the segment-parallel kernel
+
+struct BlobSpan { // 4 bytes
+	int16_t s0, s1;
 };
 
 struct BlobPass { // skeleton bones outside bone_list: copied through to the output

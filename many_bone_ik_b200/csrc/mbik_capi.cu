@@ -200,6 +200,14 @@ int resolve_device(const mbik_solve_params *params, int *device) {
 	return MBIK_OK;
 }
 
+// what launch_solve needs to know about the rig's segment-parallel schedule (mbik_blob.h: BlobSpan)
+void set_launch_hints(mbik::SolveArgs &a, const mbik::FlatRig &F, uint32_t flags) {
+	a.n_solved = (int32_t)F.bones.size();
+	a.sp_roles = F.sp_roles;
+	a.sp_gain = F.sp_critical_cost > 0 ? (float)(F.sp_serial_cost / F.sp_critical_cost) : 1.0f;
+	a.sched_mode = (flags & MBIK_SCHED_THROUGHPUT) ? 1 : ((flags & MBIK_SCHED_SEGMENT_PARALLEL) ? 2 : 0);
+}
+
 // one shard on one device; host or device buffers
 int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user_stream, int iterations, size_t n_poses,
 		const float *targets, const float *start_pose, float *out_pose, float *out_local, uint32_t *out_status) {
@@ -223,6 +231,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 	a.iterations = iterations;
 	a.n_poses = n_poses;
 	a.stabilize = F.stabilization_passes > 0 ? 1 : 0;
+	set_launch_hints(a, F, flags);
 
 	if (flags & MBIK_IO_DEVICE) {
 		a.targets = targets;
@@ -457,6 +466,9 @@ int mbik_rig_get_info(const mbik_rig *rig, mbik_rig_info *o) {
 	o->flops_per_solve = F.flops_per_solve;
 	o->max_segment_len = F.max_seg_len;
 	o->max_walk_stack = F.max_stack;
+	o->sp_roles = F.sp_roles;
+	o->sp_phases = F.sp_phases;
+	o->sp_gain = F.sp_critical_cost > 0 ? F.sp_serial_cost / F.sp_critical_cost : 1.0;
 	return MBIK_OK;
 }
 
@@ -572,7 +584,7 @@ int mbik_solve_batch_multi(mbik_rig *rig, const mbik_solve_params *params, size_
 		// contiguous split of the pose index range: device g gets [g*n/G, (g+1)*n/G)
 		size_t b = n_poses * (size_t)g / (size_t)n_devices, e = n_poses * (size_t)(g + 1) / (size_t)n_devices;
 		workers.emplace_back([&, g, b, e]() {
-			rcs[g] = solve_on_device(rig, devs[g], MBIK_IO_HOST, nullptr, iterations, e - b, targets + b * np * 12,
+			rcs[g] = solve_on_device(rig, devs[g], MBIK_IO_HOST | (params ? params->flags & (MBIK_SCHED_THROUGHPUT | MBIK_SCHED_SEGMENT_PARALLEL) : 0u), nullptr, iterations, e - b, targets + b * np * 12,
 					start_pose ? start_pose + b * nb * 12 : nullptr, out_pose + b * nb * 10, out_local ? out_local + b * nb * 12 : nullptr,
 					out_status ? out_status + b : nullptr);
 			if (rcs[g] != MBIK_OK) {
@@ -782,6 +794,7 @@ int mbik_stream_submit(mbik_stream *st, const float *targets, float *out_pose, u
 	}
 	a.n_poses = n;
 	a.stabilize = F.stabilization_passes > 0 ? 1 : 0;
+	set_launch_hints(a, F, 0);
 	a.targets = st->d_targets[slot];
 	a.start_pose = st->local[st->cur];
 	a.out_pose = st->d_out[slot];

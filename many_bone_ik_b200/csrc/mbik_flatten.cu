@@ -883,6 +883,92 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 		return MBIK_ERR_UNSUPPORTED;
 	}
 
+	// ---- segment-parallel schedule (BlobSpan): phase = height of the segment above its deepest leaf segment, so every
+	//      child segment sits in an earlier phase than its parent (the post-order of segment_solver, :210-225); within a
+	//      phase the segments go to the `roles` warps of a pose group longest-first onto the least loaded warp ----
+	{
+		const int nseg = (int)R.segments.size();
+		std::vector<int> s0(nseg, -1), s1(nseg, -1), height(nseg, 0);
+		std::vector<double> cost(nseg, 0.0);
+		for (int s = 0; s < (int)R.steps.size(); s++) {
+			const int si = R.seg_of_bone[R.bone_order[s]];
+			if (s0[si] < 0) {
+				s0[si] = s;
+			}
+			s1[si] = s + 1;
+			const BlobStep &st = R.steps[s];
+			const double passes = (st.flags & STEP_TRANSLATE) ? 2.0 : 1.0;
+			const bool snaps = (st.flags & STEP_IK_PARENT) && (st.flags & (STEP_SWING | STEP_TWIST));
+			cost[si] += (snaps ? 3000.0 : 1600.0) + passes * (450.0 * st.eff_cnt + 70.0 * st.fk_cnt) + 14.0 * st.cone_cnt;
+		}
+		bool contiguous = true;
+		for (int si = 0; si < nseg; si++) {
+			if (R.segments[si].kept && s0[si] >= 0 && s1[si] - s0[si] != (int)R.segments[si].bones.size()) {
+				contiguous = false; // cannot happen: bone_list lists a segment's bones consecutively
+			}
+		}
+		std::function<int(int)> seg_height = [&](int si) {
+			int h = 0;
+			for (int c : R.segments[si].child_segs) {
+				h = std::max(h, 1 + seg_height(c));
+			}
+			height[si] = h;
+			return h;
+		};
+		int n_phases = 0;
+		for (int si : R.root_segments) {
+			n_phases = std::max(n_phases, 1 + seg_height(si));
+		}
+		R.sp_serial_cost = 0;
+		for (int si = 0; si < nseg; si++) {
+			R.sp_serial_cost += cost[si];
+		}
+		R.sp_roles = R.sp_phases = R.sp_slots = 0;
+		R.sp_critical_cost = R.sp_serial_cost;
+		R.sched.clear();
+		if (contiguous && n_phases > 0 && ns > 0 && ns < 32767) {
+			std::vector<std::vector<int>> by_phase(n_phases);
+			int width = 1;
+			for (int si = 0; si < nseg; si++) {
+				if (R.segments[si].kept && s0[si] >= 0) {
+					by_phase[height[si]].push_back(si);
+				}
+			}
+			for (auto &v : by_phase) {
+				width = std::max(width, (int)v.size());
+			}
+			const int roles = std::min(width, kMaxSpRoles);
+			std::vector<std::vector<std::vector<int>>> assign(n_phases, std::vector<std::vector<int>>(roles));
+			int slots = 1;
+			double critical = 0;
+			for (int ph = 0; ph < n_phases; ph++) {
+				std::vector<int> order = by_phase[ph];
+				std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+				std::vector<double> load(roles, 0.0);
+				for (int si : order) {
+					int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+					assign[ph][r].push_back(si);
+					load[r] += cost[si];
+					slots = std::max(slots, (int)assign[ph][r].size());
+				}
+				critical += *std::max_element(load.begin(), load.end());
+			}
+			R.sp_roles = roles;
+			R.sp_phases = n_phases;
+			R.sp_slots = slots;
+			R.sp_critical_cost = critical;
+			R.sched.assign((size_t)n_phases * slots * roles, BlobSpan{ 0, 0 });
+			for (int ph = 0; ph < n_phases; ph++) {
+				for (int r = 0; r < roles; r++) {
+					for (size_t k = 0; k < assign[ph][r].size(); k++) {
+						const int si = assign[ph][r][k];
+						R.sched[((size_t)ph * slots + k) * roles + r] = BlobSpan{ (int16_t)s0[si], (int16_t)s1[si] };
+					}
+				}
+			}
+		}
+	}
+
 	// ---- assemble the blob ----
 	BlobHeader hdr;
 	memset(&hdr, 0, sizeof(hdr));
@@ -902,6 +988,9 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	hdr.n_chain = (int)R.chain.size();
 	hdr.max_seg_len = R.max_seg_len;
 	hdr.max_stack = R.max_stack;
+	hdr.sp_roles = R.sp_roles;
+	hdr.sp_phases = R.sp_phases;
+	hdr.sp_slots = R.sp_slots;
 	R.blob.clear();
 	R.blob.resize(sizeof(BlobHeader), 0);
 	hdr.off_steps = append_section(R.blob, R.steps);
@@ -914,6 +1003,7 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	std::vector<float> rest(nb * 12);
 	memcpy(rest.data(), d->rest_local, sizeof(float) * 12 * nb);
 	hdr.off_rest = append_section(R.blob, rest);
+	hdr.off_sched = append_section(R.blob, R.sched);
 	while (R.blob.size() % 16) {
 		R.blob.push_back(0);
 	}
@@ -983,6 +1073,55 @@ bool validate_schedule(const FlatRig &R, int cap_bones, int cap_seg, int cap_sta
 			if (op.child < 0 || op.child >= ns || op.src_slot < -1 || op.src_slot >= cap_stack || op.push_slot < -1 || op.push_slot >= cap_stack ||
 					op.eff < -1 || op.eff >= S.eff_cnt) {
 				return bad("walk op", s);
+			}
+		}
+	}
+	// segment-parallel schedule: every step in exactly one span, every span one whole segment (tip .. segment root), and
+	// every segment in a later phase than all segments below it
+	if (R.sp_roles > 0) {
+		const int n_steps = (int)R.steps.size();
+		if (R.sp_roles > kMaxSpRoles || R.sp_phases < 1 || R.sp_slots < 1 || (int)R.sched.size() != R.sp_phases * R.sp_slots * R.sp_roles) {
+			return bad("segment-parallel table shape", -1);
+		}
+		std::vector<int> phase_of_step(n_steps, -1);
+		for (int ph = 0; ph < R.sp_phases; ph++) {
+			for (int k = 0; k < R.sp_slots * R.sp_roles; k++) {
+				const BlobSpan sp = R.sched[(size_t)ph * R.sp_slots * R.sp_roles + k];
+				if (sp.s0 < 0 || sp.s1 < sp.s0 || sp.s1 > n_steps) {
+					return bad("segment-parallel span", sp.s0);
+				}
+				if (sp.s0 == sp.s1) {
+					continue;
+				}
+				if (!(R.steps[sp.s0].flags & STEP_SEG_FIRST) || !(R.steps[sp.s1 - 1].flags & STEP_SEG_ROOT)) {
+					return bad("segment-parallel span is not a whole segment", sp.s0);
+				}
+				for (int s = sp.s0; s < sp.s1; s++) {
+					if (phase_of_step[s] >= 0 || (s > sp.s0 && (R.steps[s].flags & STEP_SEG_FIRST))) {
+						return bad("segment-parallel span overlap", s);
+					}
+					phase_of_step[s] = ph;
+				}
+			}
+		}
+		std::vector<int> phase_of_bone(ns, -1);
+		for (int s = 0; s < n_steps; s++) {
+			if (phase_of_step[s] < 0) {
+				return bad("step missing from the segment-parallel schedule", s);
+			}
+			phase_of_bone[R.steps[s].bone] = phase_of_step[s];
+		}
+		for (int s = 0; s < n_steps; s++) {
+			// a bone-step reads the bones on its effector walk (its own segment or segments below it) and its ancestors
+			for (int k = 0; k < R.steps[s].fk_cnt; k++) {
+				if (phase_of_bone[R.fk[R.steps[s].fk_off + k].child] > phase_of_step[s]) {
+					return bad("segment-parallel phase order (walk)", s);
+				}
+			}
+			for (int p = R.steps[s].parent; p >= 0; p = R.bones[p].parent) {
+				if (phase_of_bone[p] < phase_of_step[s]) {
+					return bad("segment-parallel phase order (ancestor)", s);
+				}
 			}
 		}
 	}

@@ -55,6 +55,10 @@ struct FlatRig {
 	int iterations = 15;
 	int stabilization_passes = 0;
 	double flops_per_solve = 0;
+	// segment-parallel schedule (BlobSpan): roles = warps per pose group, cost estimates in arbitrary units
+	std::vector<BlobSpan> sched;
+	int sp_roles = 0, sp_phases = 0, sp_slots = 0;
+	double sp_serial_cost = 0, sp_critical_cost = 0; // all steps on one warp vs the longest role per phase, summed
 	std::string error;
 };
 

@@ -20,7 +20,54 @@ int kernel_variant_for(int n_solved, int max_seg_len, int max_stack, size_t blob
 
 int kernel_capacity_of_variant(int v) { return (v >= 0 && v < kNumVariants) ? kVariants[v][0] : -1; }
 
+// Segment-parallel mapping (mbik_solve_kernel_sp): wins while the batch is small enough that the one-thread-per-pose
+// mapping leaves most warp slots of the GPU empty -- its latency is the critical path of the segment tree instead of
+// the whole bone list.  Returns 0 = one thread per pose, 1 = segment-parallel with the full register budget (at most
+// one 32-pose group per SM: a 4096-pose batch on 148 SMs), 2 = segment-parallel compiled for 128 registers so that
+// floor(16 / roles) groups share an SM in ONE wave; past that the machine is full either way and the lockstep
+// kernel's shared instruction stream is the better use of it (measured, humanoid22: 8192 poses 0.95 vs 1.56 ms,
+// 16384 poses 1.98 vs 1.62 ms).
+int segment_parallel_choice(const SolveArgs &a, int variant, int sm_count) {
+	if (a.sched_mode == 1 || a.sp_roles < (a.sched_mode == 2 ? 1 : 2) || a.sp_roles > kMaxSpRoles || variant == 2) {
+		return 0;
+	}
+	const size_t smem = (((size_t)a.blob_bytes + 127) & ~(size_t)127) + (size_t)a.n_solved * 12 * 32 * sizeof(float);
+	if (smem > 227 * 1024) {
+		return 0;
+	}
+	const size_t groups = (a.n_poses + 31) / 32;
+	static const int forced = getenv("MBIK_SP_MINB") ? atoi(getenv("MBIK_SP_MINB")) : 0; // tuning knob
+	if (forced == 1 || forced == 2) {
+		return (a.sched_mode == 2 || a.sp_gain >= 1.25f) ? forced : 0;
+	}
+	if (groups <= (size_t)sm_count) {
+		return (a.sched_mode == 2 || a.sp_gain >= 1.25f) ? 1 : 0;
+	}
+	const size_t by_regs = 16 / (size_t)a.sp_roles, by_smem = (size_t)(227 * 1024) / (smem + 1024);
+	const size_t resident = by_regs < by_smem ? by_regs : by_smem;
+	if (a.sched_mode == 2) {
+		return resident >= 2 ? 2 : 1;
+	}
+	return (a.sp_gain >= 1.25f && resident >= 2 && groups <= resident * (size_t)sm_count) ? 2 : 0;
+}
+bool uses_segment_parallel(const SolveArgs &a, int variant, int sm_count) { return segment_parallel_choice(a, variant, sm_count) != 0; }
+
 cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStream_t stream) {
+	const int sp = segment_parallel_choice(a, variant, sm_count);
+	if (sp != 0) {
+		switch (variant) {
+			case 0:
+				return launch_sp_v0(a, sp, stream);
+			case 1:
+				return launch_sp_v1(a, sp, stream);
+			case 3:
+				return launch_sp_v3(a, sp, stream);
+			case 4:
+				return launch_sp_v4(a, sp, stream);
+			default:
+				break;
+		}
+	}
 	int threads = kBlockThreads;
 	if (a.stabilize) {
 		threads = 0;

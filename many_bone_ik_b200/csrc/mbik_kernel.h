@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include "mbik_blob.h"
 #include <stdint.h>
 
 namespace mbik {
@@ -21,6 +22,11 @@ struct SolveArgs {
 	float *out_local;        // [n_poses][n_bones][12] or nullptr
 	uint32_t *out_status;    // [n_poses] or nullptr
 	int32_t stabilize;       // rig has stabilization_passes > 0 (reference src/ik_bone_segment_3d.cpp:163-176)
+	// host-side launch hints (the kernel reads the schedule itself from the blob header)
+	int32_t n_solved;        // solved bones of the rig
+	int32_t sp_roles;        // warps per pose group of the rig's segment-parallel schedule (<= 1: none)
+	float sp_gain;           // estimated serial / critical-path cost of that schedule
+	int32_t sched_mode;      // 0 = choose by batch size, 1 = one thread per pose (throughput mapping), 2 = segment-parallel
 };
 
 // Compiled size variants {solved-bone capacity, longest segment, walk-stack depth}; per-pose thread-local state is
@@ -39,6 +45,15 @@ cudaError_t launch_v1(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v2(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v3(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v4(const SolveArgs &a, int threads, cudaStream_t stream);
+
+// segment-parallel instantiations (mbik_kernel_sp*.cu); min_groups_per_sm 1 = full register budget, 2 = 128 registers
+// (several 32-pose groups per SM)
+cudaError_t launch_sp_v0(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
+cudaError_t launch_sp_v1(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
+cudaError_t launch_sp_v3(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
+cudaError_t launch_sp_v4(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
+// true if launch_solve would run the segment-parallel mapping for these arguments
+bool uses_segment_parallel(const SolveArgs &a, int variant, int sm_count);
 
 // stage probes (mbik_selftest.cu): device pointers in, device pointers out
 struct BlobCone;

@@ -533,7 +533,13 @@ __device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, boo
 // the kernel
 // ---------------------------------------------------------------------------------------------------
 // SCR_STRIDE > 0: the scratch transforms live in shared memory behind the rig blob (SCR_STRIDE = CTA size)
-template <int NB, int NSEG, int NSTK, bool STAB, int SCR_STRIDE>
+//
+// SP (segment-parallel, the small-batch / latency mapping): a CTA is one GROUP of 32 poses (lane = pose) solved by
+// `sp_roles` warps.  Sibling segments of the segment tree are independent (BlobSpan, mbik_blob.h), so in each phase of
+// the rig's schedule every warp ("role") runs the bone-steps of its own segments; the local poses of the group live in
+// shared memory ([bone][word][lane] columns) where all roles read and write them, with one CTA barrier per phase.  The
+// per-pose arithmetic and its order are exactly those of the one-thread-per-pose mapping: bit-identical results.
+template <int NB, int NSEG, int NSTK, bool STAB, int SCR_STRIDE, bool SP = false>
 __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t bar;
@@ -565,10 +571,13 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	const BlobPass *pass = reinterpret_cast<const BlobPass *>(smem + H.off_pass);
 	const int16_t *chain = reinterpret_cast<const int16_t *>(smem + H.off_chain);
 	const float *rest = reinterpret_cast<const float *>(smem + H.off_rest);
+	const BlobSpan *spans = reinterpret_cast<const BlobSpan *>(smem + H.off_sched);
+	const int sp_roles = SP ? H.sp_roles : 1, sp_phases = SP ? H.sp_phases : 1, sp_slots = SP ? H.sp_slots : 1;
+	const int role = SP ? (int)(threadIdx.x >> 5) : 0;
 
 	// Every thread stays alive for the whole kernel (CTA-wide barriers below); threads past the end of the
 	// batch redo the last pose and skip the stores.
-	const size_t pose_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t pose_raw = SP ? (size_t)blockIdx.x * 32 + (threadIdx.x & 31) : (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const bool live = pose_raw < a.n_poses;
 	const size_t pose = live ? pose_raw : a.n_poses - 1;
 	const int ns = H.n_solved;
@@ -580,12 +589,14 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	const float *my_start = a.start_pose ? a.start_pose + pose * (size_t)n_bones * 12 : nullptr;
 
 	// Per-pose state (thread-local, lane-interleaved):
-	float L[NB * 12];      // local transform of every solved bone (t order) -- the only state carried between steps
+	float L_local[SP ? 1 : NB * 12]; // local transform of every solved bone (t order) -- the only state carried between steps
+	// SP: the group's local poses in shared memory behind the rig blob, [bone][word][lane]
+	const Scratch<SP ? 32 : 0> L{ SP ? reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + (threadIdx.x & 31) : L_local };
 	// globals of the parents of the current segment's bones (ancestors do not move while a segment is being solved,
 	// so this replaces the reference's lazy global-transform cache) and of the branch points of the current walk
 	float Pseg_local[SCR_STRIDE > 0 ? 1 : NSEG * 12];
 	float Gstk_local[SCR_STRIDE > 0 ? 1 : NSTK * 12];
-	float *scr = reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + threadIdx.x;
+	float *scr = reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + threadIdx.x; // (SP: SCR_STRIDE == 0, unused)
 	const Scratch<SCR_STRIDE> Pseg{ SCR_STRIDE > 0 ? scr : Pseg_local };
 	const Scratch<SCR_STRIDE> Gstk{ SCR_STRIDE > 0 ? scr + NSEG * 12 * SCR_STRIDE : Gstk_local };
 	// stabilisation only (STAB variants): effector-bone origins from before the step (what the step's target
@@ -599,21 +610,32 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	double prev_dev = (double)INFINITY;
 
 	// seed: ManyBoneIK3D::_update_ik_bones_transform -> IKBone3D::set_initial_pose (src/ik_bone_3d.cpp:161-168)
-	for (int t = 0; t < ns; t++) {
+	for (int t = role; t < ns; t += sp_roles) {
 		int sb = bones[t].skel_bone;
 		X34 x = my_start ? ldg_x34(my_start + (size_t)sb * 12) : ld_x34(rest, sb);
-		st_x34(L, t, x);
+		L.st(t, x);
+	}
+	if (SP) {
+		__syncthreads();
 	}
 
 	for (int it = 0; it < a.iterations; it++) {
-		for (int s = 0; s < n_steps; s++) {
+	for (int ph = 0; ph < sp_phases; ph++) {
+	for (int slot = 0; slot < sp_slots; slot++) {
+		int s_begin = 0, s_end = n_steps;
+		if (SP) {
+			const BlobSpan span = spans[(ph * sp_slots + slot) * sp_roles + role];
+			s_begin = span.s0;
+			s_end = span.s1;
+		}
+		for (int s = s_begin; s < s_end; s++) {
 			// Keep the CTA's warps in lockstep at bone-step granularity: the step body is ~75 KB of straight-line
 			// SASS, far more than the instruction cache holds, so warps that drift apart each stream it from L2
 			// on their own (ncu: 60% of stall samples were stall_no_inst before this barrier).
 #ifndef MBIK_SYNC_EVERY
 #define MBIK_SYNC_EVERY 1
 #endif
-			if (MBIK_SYNC_EVERY == 1 || (s % MBIK_SYNC_EVERY) == 0) {
+			if (!SP && (MBIK_SYNC_EVERY == 1 || (s % MBIK_SYNC_EVERY) == 0)) {
 				__syncthreads();
 			}
 			const BlobStep &S = steps[s];
@@ -632,13 +654,13 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				X34 g = x_identity();
 				X34 l_next = x_identity();
 				if (S.chain_cnt > 0) {
-					l_next = ld_x34(L, chain[S.chain_off]);
+					l_next = L.ld(chain[S.chain_off]);
 				}
 				for (int k = 0; k < S.chain_cnt; k++) {
 					const int t = chain[S.chain_off + k];
 					const X34 l = l_next; // software-pipelined like the effector walk below
 					if (k + 1 < S.chain_cnt) {
-						l_next = ld_x34(L, chain[S.chain_off + k + 1]);
+						l_next = L.ld(chain[S.chain_off + k + 1]);
 					}
 					if (k == 0) {
 						g = (bones[t].flags & STEP_NODE_PARENT) ? x_mul(x_identity(), l) : l;
@@ -657,7 +679,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			X34 Gb;
 			{
 				const X34 P0 = S.parent >= 0 ? Pseg.ld(S.pslot) : x_identity();
-				const X34 L0 = ld_x34(L, b);
+				const X34 L0 = L.ld(b);
 				Gb = node_parent ? x_mul(P0, L0) : L0;
 			}
 			Q4 q = q4(0.0f, 0.0f, 0.0f, 1.0f);
@@ -708,7 +730,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					X34 run = Gb;
 					X34 child = x_identity();
 					if (MBIK_PIPE_CHILD && S.fk_cnt > 0) {
-						child = ld_x34(L, fk[S.fk_off].child);
+						child = L.ld(fk[S.fk_off].child);
 					}
 					for (int k = 0; k < S.fk_cnt; k++) {
 						const BlobFk op = fk[S.fk_off + k];
@@ -717,14 +739,14 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 							T = ldg_x34(my_targets + (size_t)effs[S.eff_off + op.eff].pin * 12);
 						}
 						if (!MBIK_PIPE_CHILD) {
-							child = ld_x34(L, op.child);
+							child = L.ld(op.child);
 						}
 						if (op.src_slot >= 0) {
 							run = Gstk.ld(op.src_slot);
 						}
 						run = x_mul(run, child);
 						if (MBIK_PIPE_CHILD && k + 1 < S.fk_cnt) {
-							child = ld_x34(L, fk[S.fk_off + k + 1].child);
+							child = L.ld(fk[S.fk_off + k + 1].child);
 						}
 						if (op.push_slot >= 0) {
 							Gstk.st(op.push_slot, run);
@@ -768,7 +790,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			int b_reload = b, pslot_reload = S.pslot;
 			asm volatile("" : "+r"(b_reload), "+r"(pslot_reload));
 			const X34 P = S.parent >= 0 ? Pseg.ld(pslot_reload) : x_identity();
-			X34 Lb = ld_x34(L, b_reload);
+			X34 Lb = L.ld(b_reload);
 			M3 Pinv = m3_identity();
 			if (node_parent) {
 				Pinv = m3_inverse(P.b);
@@ -809,7 +831,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					if (op.src_slot >= 0) {
 						run = Gstk.ld(op.src_slot);
 					}
-					run = x_mul(run, ld_x34(L, op.child));
+					run = x_mul(run, L.ld(op.child));
 					if (op.push_slot >= 0) {
 						Gstk.st(op.push_slot, run);
 					}
@@ -886,7 +908,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						if (op.src_slot >= 0) {
 							run = Gstk.ld(op.src_slot);
 						}
-						run = x_mul(run, ld_x34(L, op.child));
+						run = x_mul(run, L.ld(op.child));
 						if (op.push_slot >= 0) {
 							Gstk.st(op.push_slot, run);
 						}
@@ -900,15 +922,20 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					if (current_msd <= r_mul(prev_dev, 1.0001)) {
 						prev_dev = current_msd;
 					} else {
-						Lb = ld_x34(L, b); // IKBone3D::set_pose(prev_transform)
+						Lb = L.ld(b); // IKBone3D::set_pose(prev_transform)
 					}
 				}
 				if (flags & STEP_SEG_ROOT) {
 					prev_dev = (double)INFINITY; // :178-180
 				}
 			}
-			st_x34(L, b, Lb);
+			L.st(b, Lb);
 		}
+	}
+		if (SP) {
+			__syncthreads(); // phase boundary: the segments of the next phase read what this one wrote
+		}
+	}
 	}
 
 	// write-back: ManyBoneIK3D::_update_skeleton_bones_transform (src/many_bone_ik_3d.cpp:104-116)
@@ -916,21 +943,39 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	float *my_out = a.out_pose + pose * (size_t)n_bones * 10;
 	float *my_loc = a.out_local ? a.out_local + pose * (size_t)n_bones * 12 : nullptr;
 	if (live) {
-		for (int t = 0; t < ns; t++) {
+		for (int t = role; t < ns; t += sp_roles) {
 			int sb = bones[t].skel_bone;
-			X34 l = ld_x34(L, t);
+			X34 l = L.ld(t);
 			status |= write_bone_pose(l, my_out + (size_t)sb * 10);
 			if (my_loc) {
 				stg_x34(my_loc + (size_t)sb * 12, l);
 			}
 		}
-		for (int k = 0; k < H.n_pass; k++) {
+		for (int k = role; k < H.n_pass; k += sp_roles) {
 			int sb = pass[k].skel_bone;
 			X34 l = my_start ? ldg_x34(my_start + (size_t)sb * 12) : ld_x34(rest, sb);
 			status |= write_bone_pose(l, my_out + (size_t)sb * 10);
 			if (my_loc) {
 				stg_x34(my_loc + (size_t)sb * 12, l);
 			}
+		}
+	}
+	if (SP) {
+		// one status word per pose: OR the roles' partial words through shared memory (first row of the L columns,
+		// dead once every role is past its write-back loop)
+		uint32_t *st_sh = reinterpret_cast<uint32_t *>(smem + ((a.blob_bytes + 127u) & ~127u));
+		__syncthreads();
+		if (role == 0) {
+			st_sh[threadIdx.x & 31] = 0u;
+		}
+		__syncthreads();
+		if (status) {
+			atomicOr(&st_sh[threadIdx.x & 31], status);
+		}
+		__syncthreads();
+		status = st_sh[threadIdx.x & 31];
+		if (role != 0) {
+			return;
 		}
 	}
 	if (a.out_status && live) {
@@ -971,6 +1016,42 @@ static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 	unsigned grid = (unsigned)((a.n_poses + THREADS - 1) / THREADS);
 	mbik_solve_kernel<NB, NSEG, NSTK, THREADS, STAB, MINB><<<grid, THREADS, smem, stream>>>(a);
 	return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// segment-parallel (small-batch) kernel: one CTA = one group of 32 poses x sp_roles warps
+// ---------------------------------------------------------------------------------------------------
+template <int NB, int NSEG, int NSTK, bool STAB, int MINB>
+__global__ void __launch_bounds__(32 * kMaxSpRoles, MINB) mbik_solve_kernel_sp(SolveArgs a) {
+	solve_body<NB, NSEG, NSTK, STAB, 0, true>(a);
+}
+// shared memory of one group: rig blob + the group's local poses (n_solved x 12 words x 32 lanes)
+inline size_t sp_smem_bytes(const SolveArgs &a) {
+	return (((size_t)a.blob_bytes + 127) & ~(size_t)127) + (size_t)a.n_solved * 12 * 32 * sizeof(float);
+}
+template <int NB, int NSEG, int NSTK, bool STAB, int MINB>
+static cudaError_t launch_variant_sp_m(const SolveArgs &a, cudaStream_t stream) {
+	const size_t smem = sp_smem_bytes(a);
+	if (smem > 227 * 1024 || a.sp_roles < 1 || a.sp_roles > kMaxSpRoles) {
+		return cudaErrorInvalidValue; // launch_solve checks both before choosing this mapping
+	}
+	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	// several groups per SM: ask for the shared-memory-heavy split of the L1 / shared array (the groups' poses live there)
+	cudaFuncSetAttribute(mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	unsigned grid = (unsigned)((a.n_poses + 31) / 32);
+	mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB><<<grid, 32 * a.sp_roles, smem, stream>>>(a);
+	return cudaGetLastError();
+}
+template <int NB, int NSEG, int NSTK, bool STAB>
+static cudaError_t launch_variant_sp(const SolveArgs &a, int minb, cudaStream_t stream) {
+	if (minb == 2) {
+		return launch_variant_sp_m<NB, NSEG, NSTK, STAB, 2>(a, stream);
+	}
+	return launch_variant_sp_m<NB, NSEG, NSTK, STAB, 1>(a, stream);
 }
 
 } // namespace mbik

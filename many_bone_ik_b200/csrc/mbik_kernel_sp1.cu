@@ -1,0 +1,14 @@
+// mbik_kernel_sp1.cu -- segment-parallel (small-batch) instantiations of the solve kernel for the size variant
+// {32 solved bones, segment 8, stack 4}: one group of 32 poses per CTA, one warp per concurrently solvable segment.
+#include "mbik_kernel_body.cuh"
+
+namespace mbik {
+
+cudaError_t launch_sp_v1(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream) {
+	if (a.stabilize) {
+		return launch_variant_sp<32, 8, 4, true>(a, min_groups_per_sm, stream);
+	}
+	return launch_variant_sp<32, 8, 4, false>(a, min_groups_per_sm, stream);
+}
+
+} // namespace mbik

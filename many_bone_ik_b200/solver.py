@@ -11,7 +11,10 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import MBIK_IO_DEVICE, MBIK_IO_HOST, RigInfo, SolveParams
+from ._capi import MBIK_IO_DEVICE, MBIK_IO_HOST, MBIK_SCHED_SEGMENT_PARALLEL, MBIK_SCHED_THROUGHPUT, RigInfo, SolveParams
+
+# kernel mapping selectors of mbik_solve_params.flags (include/mbik.h); identical results, for tests and measurements
+SCHED_FLAGS = {"auto": 0, "throughput": MBIK_SCHED_THROUGHPUT, "segment_parallel": MBIK_SCHED_SEGMENT_PARALLEL}
 
 
 class MbikError(RuntimeError):
@@ -95,9 +98,10 @@ class BatchedIKRig:
         return out[:max(n, 0)].copy()
 
     # ---- the hot path -------------------------------------------------------------------------------
-    def solve(self, targets, start_pose=None, iterations=-1, device=-1, want_local=False, devices=None):
+    def solve(self, targets, start_pose=None, iterations=-1, device=-1, want_local=False, devices=None, sched="auto"):
         """Host-buffer solve.  targets [n, n_pins, 12] float32 -> out_pose [n, n_bones, 10]
-        (+ out_local [n, n_bones, 12]) + status [n].  `devices`: list of ordinals -> sharded multi-GPU call."""
+        (+ out_local [n, n_bones, 12]) + status [n].  `devices`: list of ordinals -> sharded multi-GPU call.
+        `sched`: kernel mapping, one of SCHED_FLAGS (same bits either way)."""
         targets = np.ascontiguousarray(targets, np.float32)
         n = targets.shape[0]
         if targets.shape != (n, self.n_pins, 12):
@@ -109,7 +113,7 @@ class BatchedIKRig:
         out = np.empty((n, self.n_bones, 10), np.float32)
         loc = np.empty((n, self.n_bones, 12), np.float32) if want_local else None
         st = np.zeros(n, np.uint32)
-        p = SolveParams(int(iterations), int(device), MBIK_IO_HOST, None)
+        p = SolveParams(int(iterations), int(device), MBIK_IO_HOST | SCHED_FLAGS[sched], None)
         if devices is None:
             rc = self.lib.mbik_solve_batch(self.handle, C.byref(p), n, _ptr(targets), _ptr(start_pose), _ptr(out), _ptr(loc), _ptr(st))
         else:

@@ -108,6 +108,24 @@ def test_schedule_facts_of_the_benchmark_rigs():
         assert r.info["flops_per_solve"] > 0
 
 
+def test_segment_parallel_schedule_facts():
+    """Sibling segments are independent in segment_solver's post-order recursion (reference
+    src/ik_bone_segment_3d.cpp:210-225).  humanoid22: phase 0 = {head, 2 arms, 2 legs} on 5 warps, phase 1 = spine,
+    phase 2 = hips; a chain has nothing to run concurrently.  (mbik_rig_create also range- and order-checks the
+    schedule: validate_schedule.)"""
+    h = BatchedIKRig(rigs.humanoid22()).info
+    assert (h["sp_roles"], h["sp_phases"]) == (5, 3) and h["sp_gain"] > 1.8
+    c = BatchedIKRig(rigs.chain64()).info
+    assert c["sp_roles"] == 1 and c["sp_phases"] == 9 and c["sp_gain"] == 1.0
+    q = BatchedIKRig(rigs.quad80()).info
+    assert 2 <= q["sp_roles"] <= 8 and q["sp_gain"] > 1.5
+    t = BatchedIKRig(rig_cases.EDGE_RIGS["two_roots"]()).info  # independent skeleton roots run side by side
+    assert (t["sp_roles"], t["sp_phases"]) == (2, 1)
+    for seed in range(24):
+        i = BatchedIKRig(rig_cases.random_rig(seed)).info
+        assert 1 <= i["sp_roles"] <= 8 and 1 <= i["sp_phases"] <= i["n_segments"] and i["sp_gain"] >= 1.0
+
+
 def test_flops_floor_matches_survey_formula():
     """humanoid22 floor = 30.5 kflop/iteration -> ~305 kflop per 10-iteration solve."""
     h = BatchedIKRig(rigs.humanoid22())

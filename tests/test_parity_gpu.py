@@ -31,15 +31,32 @@ def _assert_same(rig, got, ref):
 def _compare(rig, n, iterations=-1, start_pose=None, first=0):
     R = BatchedIKRig(rig)
     T = rigs.random_targets(rig, first, n)
-    got = R.solve(T, start_pose=start_pose, iterations=iterations, want_local=True)
     ref = O.solve_batch(rig, T, start_pose=start_pose, iterations=iterations, want_local=True, threads=8)
-    _assert_same(rig, got, ref)
+    # both kernel mappings (one thread per pose in lockstep CTAs / one warp per concurrently solvable segment) and
+    # whatever the library picks for this batch size: all three must equal the oracle bit for bit
+    for sched in ("throughput", "segment_parallel", "auto"):
+        got = R.solve(T, start_pose=start_pose, iterations=iterations, want_local=True, sched=sched)
+        _assert_same(rig, got, ref)
     return got
 
 
 @pytest.mark.parametrize("name,n", [("humanoid22", 4096), ("chain64", 256), ("quad80", 256)])
 def test_bit_exact_default_configs(name, n):
     _compare(rigs.RIGS[name](), n)
+
+
+@pytest.mark.parametrize("name,n", [("humanoid22", 6000), ("quad80", 4800), ("big_tree120", 4800)])
+def test_segment_parallel_several_groups_per_sm(name, n):
+    """Batches of more than one 32-pose group per SM run the 128-register build of the segment-parallel kernel
+    (mbik_kernel.cu: segment_parallel_choice); same bits as the oracle, ragged last group included."""
+    cases = dict(rigs.RIGS)
+    cases.update(rig_cases.EDGE_RIGS)
+    rig = cases[name]()
+    R = BatchedIKRig(rig)
+    T = rigs.random_targets(rig, 0, n)
+    ref = O.solve_batch(rig, T, want_local=True, threads=8)
+    for sched in ("segment_parallel", "auto"):
+        _assert_same(rig, R.solve(T, want_local=True, sched=sched), ref)
 
 
 @pytest.mark.parametrize("iterations", [0, 1, 2, 15])
