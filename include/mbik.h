@@ -141,6 +141,9 @@ int mbik_rig_get_info(const mbik_rig *rig, mbik_rig_info *out_info);
 int mbik_rig_get_bone_order(const mbik_rig *rig, int32_t *out_bones /* [n_solved] */);
 /* heading weights of the segment that owns step `step` (reference :281-343); returns count */
 int mbik_rig_get_step_weights(const mbik_rig *rig, int32_t step, double *out_weights, int32_t capacity);
+/* segment-parallel schedule, one row of 6 per non-empty span: phase, warp (role), first step, end step, team size,
+ * member index (0 = the warp that owns the segment; > 0 = heading helper).  Returns the row count. */
+int mbik_rig_get_schedule(const mbik_rig *rig, int32_t *out_rows /* [capacity][6] */, int32_t capacity);
 /* per solved bone (bone_list order): bone-direction local basis[9], twist-axes local basis[9] (setup constants) */
 int mbik_rig_get_bone_frames(const mbik_rig *rig, float *out_dir_basis /* [n_solved][9] */, float *out_twist_basis /* [n_solved][9] */);
 /* per cone, flattened in constraint-row order: control point[3], tangent centre 1[3], tangent centre 2[3] */

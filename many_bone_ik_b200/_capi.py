@@ -58,7 +58,7 @@ MBIK_SCHED_SEGMENT_PARALLEL = 4
 # every symbol include/mbik.h declares (tests check the library exports exactly these)
 EXPORTED_SYMBOLS = [
     "mbik_device_count", "mbik_strerror", "mbik_last_error", "mbik_rig_create", "mbik_rig_destroy",
-    "mbik_rig_get_info", "mbik_rig_get_bone_order", "mbik_rig_get_step_weights", "mbik_rig_get_bone_frames",
+    "mbik_rig_get_info", "mbik_rig_get_bone_order", "mbik_rig_get_schedule", "mbik_rig_get_step_weights", "mbik_rig_get_bone_frames",
     "mbik_rig_get_cone_geometry", "mbik_solve_batch", "mbik_solve_batch_multi", "mbik_alloc_pinned",
     "mbik_free_pinned", "mbik_last_kernel_ms", "mbik_measure_fp32_tflops", "mbik_selftest",
     "mbik_stream_create", "mbik_stream_destroy", "mbik_stream_submit", "mbik_stream_sync", "mbik_stream_read_local",
@@ -134,6 +134,7 @@ def load_library():
     lib.mbik_rig_destroy.argtypes = [vp]
     lib.mbik_rig_get_info.argtypes = [vp, C.POINTER(RigInfo)]
     lib.mbik_rig_get_bone_order.argtypes = [vp, i32p]
+    lib.mbik_rig_get_schedule.argtypes = [vp, i32p, C.c_int32]
     lib.mbik_rig_get_step_weights.argtypes = [vp, C.c_int32, dp, C.c_int32]
     lib.mbik_rig_get_bone_frames.argtypes = [vp, fp, fp]
     lib.mbik_rig_get_cone_geometry.argtypes = [vp, fp]

@@ -3,7 +3,8 @@
 // One contiguous, 16-byte aligned blob of rig constants.  The kernel stages it into shared memory
 // with one TMA bulk copy per CTA; every lane then reads the same words (broadcast).  Layout:
 //   BlobHeader | BlobStep[n_steps] | BlobBone[n_solved] | BlobEff[n_effs] | BlobFk[n_fk] |
-//   BlobCone[n_cones] | BlobPass[n_pass] | chain[n_chain] (int16) | rest_local[n_bones*12] | BlobSpan[sp_phases*sp_slots*sp_roles]
+//   BlobCone[n_cones] | BlobPass[n_pass] | chain[n_chain] (int16) | rest_local[n_bones*12] | BlobSpan[sp_phases*sp_slots*sp_roles] |
+//   step_path[n_steps] (int32) | BlobPathRef[] | paths[] (int16)
 // Solved bones are renumbered in depth-first preorder ("t index": parents before children, children in
 // the reference's ascending order), which is also the order in which a segment's effector list
 // enumerates its effectors.
@@ -35,8 +36,12 @@ struct BlobHeader {
 	int32_t max_seg_len, max_stack;
 	// segment-parallel schedule (see BlobSpan): sibling segments of the segment tree are independent, so a group of
 	// `sp_roles` warps can solve them concurrently; sp_roles <= 1 means the tree offers no parallelism
-	int32_t sp_roles, sp_phases, sp_slots, reserved0;
-	uint32_t off_steps, off_bones, off_effs, off_fk, off_cones, off_pass, off_rest, off_chain, off_sched, reserved1;
+	int32_t sp_roles, sp_phases, sp_slots;
+	int32_t sp_team_bufs;     // heading buffers a group needs (teams that can be active in one phase, 0..kMaxSpTeams)
+	int32_t sp_team_headings; // headings per buffer (largest heading list of any team step)
+	int32_t reserved0;
+	uint32_t off_steps, off_bones, off_effs, off_fk, off_cones, off_pass, off_rest, off_chain, off_sched;
+	uint32_t off_step_path, off_path_refs, off_paths; // BlobPathRef tables of the team steps (see BlobSpan)
 };
 
 struct BlobStep { // 64 bytes
@@ -74,7 +79,8 @@ struct BlobEff { // one entry per (segment, effector); 80 bytes
 	double w_axis[3];        // heading weight of each axis pair (0 when unused)
 	float w_origin_f;        // (float)w_origin, (float)w_axis[i]: the narrowed weights the reference multiplies
 	float w_axis_f[3];       // headings by (real_t w = p_weights->get(index), src/ik_effector_3d.cpp:103)
-	int32_t pad[2];
+	int32_t h_off;           // index of the effector's first heading in its segment's heading list
+	int32_t pad;
 };
 
 // One step of the depth-first walk from the solved bone down to the effectors of its segment's list:
@@ -112,8 +118,22 @@ struct BlobCone { // 160 bytes
 // are final once its child segments -- all in earlier phases -- are done).  All roles meet at a barrier after each phase.
 constexpr int kMaxSpRoles = 8; // warps per pose group of the segment-parallel kernel
 
-struct BlobSpan { // 4 bytes
+// Teams: when a phase leaves warps idle, they join a busy segment as heading helpers.  Every member of a team runs
+// the span's steps; in each step member m walks to effectors m, m + team, ... of the segment's list (path tables
+// below), writes their raw tip / target headings to the team's shared-memory buffer `buf`, and the owner (member 0)
+// alone folds them into the QCP sums -- in list order, so the arithmetic is unchanged -- and finishes the step.
+constexpr int kMaxSpTeams = 2;
+struct BlobSpan { // 8 bytes
 	int16_t s0, s1;
+	int8_t team;   // members of the team running this span (1 = the owner alone, the plain path)
+	int8_t member; // 0 = owner
+	int8_t buf;    // heading buffer / named barrier of the team
+	int8_t pad;
+};
+// step_path[s] = index of the first BlobPathRef of step s (one per effector of its list) or -1 when s is no team step;
+// paths[off .. off+cnt) = t indices of the bones from below the solved bone down to the effector's bone
+struct BlobPathRef { // 8 bytes
+	int32_t off, cnt;
 };
 
 struct BlobPass { // skeleton bones outside bone_list: copied through to the output

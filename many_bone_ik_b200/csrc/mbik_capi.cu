@@ -204,8 +204,63 @@ int resolve_device(const mbik_solve_params *params, int *device) {
 void set_launch_hints(mbik::SolveArgs &a, const mbik::FlatRig &F, uint32_t flags) {
 	a.n_solved = (int32_t)F.bones.size();
 	a.sp_roles = F.sp_roles;
+	a.sp_team_bytes = (int32_t)((size_t)F.sp_team_bufs * F.sp_team_headings * 6 * 32 * sizeof(float));
 	a.sp_gain = F.sp_critical_cost > 0 ? (float)(F.sp_serial_cost / F.sp_critical_cost) : 1.0f;
 	a.sched_mode = (flags & MBIK_SCHED_THROUGHPUT) ? 1 : ((flags & MBIK_SCHED_SEGMENT_PARALLEL) ? 2 : 0);
+	a.sp_trace = nullptr;
+}
+
+// debug knob MBIK_SP_TRACE=1: per (iteration, phase, warp) busy cycles of CTA 0 of one device-buffer launch, to stderr
+void sp_trace_launch(mbik::SolveArgs a, const mbik::FlatRig &F, int variant, int sm_count, cudaStream_t stream) {
+	if (!mbik::uses_segment_parallel(a, variant, sm_count) || F.sp_phases < 1) {
+		return;
+	}
+	const size_t n = (size_t)a.iterations * F.sp_phases * F.sp_roles * 2;
+	long long *d = nullptr;
+	if (n == 0 || cudaMalloc(&d, n * sizeof(long long)) != cudaSuccess) {
+		return;
+	}
+	cudaMemset(d, 0, n * sizeof(long long));
+	a.sp_trace = d;
+	mbik::launch_solve(a, variant, sm_count, stream);
+	std::vector<long long> h(n);
+	cudaStreamSynchronize(stream);
+	cudaMemcpy(h.data(), d, n * sizeof(long long), cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	{
+		// whole-kernel view: per iteration, first start .. last end of every phase
+		fprintf(stderr, "[mbik sp trace] per iteration: cycles from the first phase start to the last phase end, and gaps between phases\n ");
+		long long prev_end = -1;
+		for (int i2 = 0; i2 < a.iterations; i2++) {
+			long long first = -1, last = -1;
+			for (int ph = 0; ph < F.sp_phases; ph++) {
+				for (int r = 0; r < F.sp_roles; r++) {
+					const long long s = h[(((size_t)i2 * F.sp_phases + ph) * F.sp_roles + r) * 2], e = h[(((size_t)i2 * F.sp_phases + ph) * F.sp_roles + r) * 2 + 1];
+					first = (first < 0 || s < first) ? s : first;
+					last = e > last ? e : last;
+				}
+			}
+			fprintf(stderr, " it%d %lld(gap %lld)", i2, last - first, prev_end < 0 ? 0 : first - prev_end);
+			prev_end = last;
+		}
+		fprintf(stderr, "\n");
+	}
+	int it = atoi(getenv("MBIK_SP_TRACE")); // iteration whose phases are listed
+	it = it < 0 ? 0 : (it >= a.iterations ? a.iterations - 1 : it);
+	fprintf(stderr, "[mbik sp trace] iteration %d, cycles per phase and warp (end - start; start relative to the phase's first warp)\n", it);
+	for (int ph = 0; ph < F.sp_phases; ph++) {
+		long long t0 = -1;
+		for (int r = 0; r < F.sp_roles; r++) {
+			const long long s = h[(((size_t)it * F.sp_phases + ph) * F.sp_roles + r) * 2];
+			t0 = (t0 < 0 || s < t0) ? s : t0;
+		}
+		fprintf(stderr, "  phase %d:", ph);
+		for (int r = 0; r < F.sp_roles; r++) {
+			const long long s = h[(((size_t)it * F.sp_phases + ph) * F.sp_roles + r) * 2], e = h[(((size_t)it * F.sp_phases + ph) * F.sp_roles + r) * 2 + 1];
+			fprintf(stderr, "  w%d %lld(+%lld)", r, e - s, s - t0);
+		}
+		fprintf(stderr, "\n");
+	}
 }
 
 // one shard on one device; host or device buffers
@@ -239,6 +294,10 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 		a.out_pose = out_pose;
 		a.out_local = out_local;
 		a.out_status = out_status;
+		static const bool trace = getenv("MBIK_SP_TRACE") != nullptr;
+		if (trace) {
+			sp_trace_launch(a, F, rig->variant, ds->sm_count, user_stream);
+		}
 		cudaEventRecord(ds->ev_start, user_stream);
 		e = mbik::launch_solve(a, rig->variant, ds->sm_count, user_stream);
 		cudaEventRecord(ds->ev_stop, user_stream);
@@ -480,6 +539,30 @@ int mbik_rig_get_bone_order(const mbik_rig *rig, int32_t *out_bones) {
 		out_bones[i] = rig->flat.bone_order[i];
 	}
 	return MBIK_OK;
+}
+
+int mbik_rig_get_schedule(const mbik_rig *rig, int32_t *out_rows, int32_t capacity) {
+	if (!rig) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	const mbik::FlatRig &F = rig->flat;
+	int n = 0;
+	for (int ph = 0; ph < F.sp_phases; ph++) {
+		for (int slot = 0; slot < F.sp_slots; slot++) {
+			for (int r = 0; r < F.sp_roles; r++) {
+				const mbik::BlobSpan sp = F.sched[((size_t)ph * F.sp_slots + slot) * F.sp_roles + r];
+				if (sp.s0 == sp.s1) {
+					continue;
+				}
+				if (out_rows && n < capacity) {
+					int32_t *o = out_rows + (size_t)n * 6;
+					o[0] = ph; o[1] = r; o[2] = sp.s0; o[3] = sp.s1; o[4] = sp.team; o[5] = sp.member;
+				}
+				n++;
+			}
+		}
+	}
+	return n;
 }
 
 int mbik_rig_get_step_weights(const mbik_rig *rig, int32_t step, double *out_weights, int32_t capacity) {

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 
@@ -697,6 +698,7 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 			memset(&E, 0, sizeof(E));
 			E.bone = R.t_of_bone[e];
 			E.pin = pin_of_bone[e];
+			E.h_off = h;
 			E.w_origin = S.weights[h++];
 			E.w_origin_f = (float)E.w_origin;
 			E.n_headings = 1;
@@ -956,16 +958,186 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 			R.sp_roles = roles;
 			R.sp_phases = n_phases;
 			R.sp_slots = slots;
-			R.sp_critical_cost = critical;
-			R.sched.assign((size_t)n_phases * slots * roles, BlobSpan{ 0, 0 });
+			R.sched.assign((size_t)n_phases * slots * roles, BlobSpan{ 0, 0, 1, 0, 0, 0 });
 			for (int ph = 0; ph < n_phases; ph++) {
 				for (int r = 0; r < roles; r++) {
 					for (size_t k = 0; k < assign[ph][r].size(); k++) {
 						const int si = assign[ph][r][k];
-						R.sched[((size_t)ph * slots + k) * roles + r] = BlobSpan{ (int16_t)s0[si], (int16_t)s1[si] };
+						R.sched[((size_t)ph * slots + k) * roles + r] = BlobSpan{ (int16_t)s0[si], (int16_t)s1[si], 1, 0, 0, 0 };
 					}
 				}
 			}
+			// Teams: warps a phase leaves idle become heading helpers of its busiest multi-effector segments (at most
+			// kMaxSpTeams per phase; the stabilisation loop and constraint mode keep the plain path).
+			R.step_path.assign(R.steps.size(), -1);
+			R.path_refs.clear();
+			R.paths.clear();
+			R.sp_team_bufs = R.sp_team_headings = 0;
+			critical = 0;
+			const bool teams_allowed = d->stabilization_passes <= 0 && !d->constraint_mode;
+			// Estimated cost of a span run by a team of k warps (instruction-equivalents of the owner's critical path):
+			// the walk products (80 each) and raw headings (140 per effector) are what the members share, the
+			// QCP accumulation (51 per heading, +13 for the centroid pass) stays with the owner; a team step pays two
+			// barriers and a shared-memory round trip of the headings.
+			auto span_cost = [&](int si, int k) {
+				double total = 0;
+				for (int s = s0[si]; s < s1[si]; s++) {
+					const BlobStep &st = R.steps[s];
+					const bool tr = (st.flags & STEP_TRANSLATE) != 0;
+					const bool snaps = (st.flags & STEP_IK_PARENT) && (st.flags & (STEP_SWING | STEP_TWIST));
+					double c = (snaps ? 3000.0 : 1600.0) + 14.0 * st.cone_cnt + st.n_headings * (51.0 + (tr ? 13.0 : 0.0));
+					if (k <= 1) {
+						c += 80.0 * st.fk_cnt * ((tr && st.eff_cnt > 16) ? 2.0 : 1.0) + 140.0 * st.eff_cnt * (tr ? 2.0 : 1.0);
+					} else {
+						std::vector<double> load(k, 0.0);
+						const int b = R.bone_order[s];
+						int e_i = 0;
+						for (int e : R.segments[si].effectors) {
+							int plen = 0;
+							for (int x = e; x != b && x >= 0; x = ik_parent[x]) {
+								plen++;
+							}
+							load[e_i % k] += 80.0 * plen + 160.0;
+							e_i++;
+						}
+						c += 150.0 + 6.0 * st.n_headings + *std::max_element(load.begin(), load.end());
+					}
+					total += c;
+				}
+				return total;
+			};
+			R.sp_serial_cost = 0;
+			for (int si = 0; si < nseg; si++) {
+				if (R.segments[si].kept && s0[si] >= 0) {
+					R.sp_serial_cost += span_cost(si, 1);
+				}
+			}
+			for (int ph = 0; ph < n_phases; ph++) {
+				std::vector<int> idle, busy;
+				bool single_slot = true;
+				for (int r = 0; r < roles; r++) {
+					if (assign[ph][r].empty()) {
+						idle.push_back(r);
+					} else {
+						busy.push_back(r);
+						single_slot = single_slot && assign[ph][r].size() == 1;
+					}
+				}
+				std::vector<int> team_of_role(roles, 1); // owner role -> team size
+				std::vector<std::vector<int>> helpers(roles);
+				static const long team_phase_mask = getenv("MBIK_SP_TEAM_PHASES") ? strtol(getenv("MBIK_SP_TEAM_PHASES"), nullptr, 0) : -1; // tuning knob
+				// Teams only in phases with ONE busy segment: every warp of a group streams the ~100 KB step body through the
+				// SM's instruction caches, and warps at different places of it compete for that fetch path -- measured on
+				// quad80, helpers next to a second busy segment slowed every warp of the SM by ~30 % (the team's own span
+				// got 28 % shorter, the batch 20 % slower), whereas helpers of a lone segment run in step with each other
+				// and with their owner (humanoid22: spine and hips phases, -10 % latency).
+				static const bool teams_beside_busy = getenv("MBIK_SP_TEAMS_BESIDE_BUSY") != nullptr; // tuning knob
+				if (teams_allowed && single_slot && !idle.empty() && (busy.size() == 1 || teams_beside_busy) && ((team_phase_mask >> (ph < 60 ? ph : 60)) & 1)) {
+					// give idle warps, one at a time, to the span on the phase's critical path while that shortens it
+					std::vector<double> cur(roles, 0.0);
+					for (int r : busy) {
+						cur[r] = span_cost(assign[ph][r][0], 1);
+					}
+					int n_teams = 0;
+					while (!idle.empty()) {
+						int crit = busy[0];
+						for (int r : busy) {
+							if (cur[r] > cur[crit]) {
+								crit = r;
+							}
+						}
+						const int si = assign[ph][crit][0];
+						const int E = R.steps[s0[si]].eff_cnt;
+						if (team_of_role[crit] >= E || (team_of_role[crit] == 1 && n_teams >= kMaxSpTeams)) {
+							break;
+						}
+						// a second member may not pay for the barriers where a third does: look ahead over the sizes reachable
+						int best_k = -1;
+						double best_c = cur[crit] * 0.97;
+						for (int k = team_of_role[crit] + 1; k <= std::min(E, team_of_role[crit] + (int)idle.size()); k++) {
+							const double c = span_cost(si, k);
+							if (c < best_c) {
+								best_c = c;
+								best_k = k;
+							}
+						}
+						if (best_k < 0) {
+							break;
+						}
+						if (team_of_role[crit] == 1) {
+							n_teams++;
+						}
+						while (team_of_role[crit] < best_k) {
+							// prefer a warp whose scheduler (warp index mod 4) no busy warp of this phase uses: two warps
+							// on one scheduler share its L0 instruction cache, and they run different code
+							size_t pick = 0;
+							int pick_clash = 1 << 30;
+							for (size_t i = 0; i < idle.size(); i++) {
+								int clash = 0;
+								for (int r : busy) {
+									clash += (r % 4 == idle[i] % 4) ? (r == crit ? 1 : 4) : 0;
+								}
+								for (int r = 0; r < roles; r++) {
+									for (int h : helpers[r]) {
+										clash += (h % 4 == idle[i] % 4) ? 1 : 0;
+									}
+								}
+								if (clash < pick_clash) {
+									pick_clash = clash;
+									pick = i;
+								}
+							}
+							helpers[crit].push_back(idle[pick]);
+							idle.erase(idle.begin() + pick);
+							team_of_role[crit]++;
+						}
+						cur[crit] = best_c;
+					}
+				}
+				int n_bufs = 0;
+				double phase_cost = 0;
+				for (int r : busy) {
+					double load = 0;
+					for (int si : assign[ph][r]) {
+						load += span_cost(si, 1);
+					}
+					if (team_of_role[r] > 1) {
+						const int si = assign[ph][r][0];
+						const int team = team_of_role[r], buf = n_bufs++;
+						BlobSpan &own = R.sched[((size_t)ph * slots + 0) * roles + r];
+						own.team = (int8_t)team;
+						own.buf = (int8_t)buf;
+						for (size_t m = 0; m < helpers[r].size(); m++) {
+							R.sched[((size_t)ph * slots + 0) * roles + helpers[r][m]] = BlobSpan{ own.s0, own.s1, (int8_t)team, (int8_t)(m + 1), (int8_t)buf, 0 };
+						}
+						load = span_cost(si, team);
+						for (int s = s0[si]; s < s1[si]; s++) {
+							const BlobStep &st = R.steps[s];
+							const FlatSegment &S = R.segments[si];
+							R.sp_team_headings = std::max(R.sp_team_headings, st.n_headings);
+							R.step_path[s] = (int32_t)R.path_refs.size();
+							const int b = R.bone_order[s];
+							for (int e : S.effectors) {
+								std::vector<int> up;
+								for (int x = e; x != b && x >= 0; x = ik_parent[x]) {
+									up.push_back(x);
+								}
+								BlobPathRef pr;
+								pr.off = (int32_t)R.paths.size();
+								pr.cnt = (int32_t)up.size();
+								for (auto it2 = up.rbegin(); it2 != up.rend(); ++it2) {
+									R.paths.push_back((int16_t)R.t_of_bone[*it2]);
+								}
+								R.path_refs.push_back(pr);
+							}
+						}
+					}
+					phase_cost = std::max(phase_cost, load);
+				}
+				R.sp_team_bufs = std::max(R.sp_team_bufs, n_bufs);
+				critical += phase_cost;
+			}
+			R.sp_critical_cost = critical;
 		}
 	}
 
@@ -991,6 +1163,8 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	hdr.sp_roles = R.sp_roles;
 	hdr.sp_phases = R.sp_phases;
 	hdr.sp_slots = R.sp_slots;
+	hdr.sp_team_bufs = R.sp_team_bufs;
+	hdr.sp_team_headings = R.sp_team_headings;
 	R.blob.clear();
 	R.blob.resize(sizeof(BlobHeader), 0);
 	hdr.off_steps = append_section(R.blob, R.steps);
@@ -1004,6 +1178,9 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	memcpy(rest.data(), d->rest_local, sizeof(float) * 12 * nb);
 	hdr.off_rest = append_section(R.blob, rest);
 	hdr.off_sched = append_section(R.blob, R.sched);
+	hdr.off_step_path = append_section(R.blob, R.step_path);
+	hdr.off_path_refs = append_section(R.blob, R.path_refs);
+	hdr.off_paths = append_section(R.blob, R.paths);
 	while (R.blob.size() % 16) {
 		R.blob.push_back(0);
 	}
@@ -1084,10 +1261,14 @@ bool validate_schedule(const FlatRig &R, int cap_bones, int cap_seg, int cap_sta
 			return bad("segment-parallel table shape", -1);
 		}
 		std::vector<int> phase_of_step(n_steps, -1);
+		if (R.sp_team_bufs < 0 || R.sp_team_bufs > kMaxSpTeams || (int)R.step_path.size() != n_steps) {
+			return bad("team table shape", -1);
+		}
 		for (int ph = 0; ph < R.sp_phases; ph++) {
+			std::vector<int> members_seen(kMaxSpTeams, 0), team_size(kMaxSpTeams, 0), team_s0(kMaxSpTeams, -1);
 			for (int k = 0; k < R.sp_slots * R.sp_roles; k++) {
 				const BlobSpan sp = R.sched[(size_t)ph * R.sp_slots * R.sp_roles + k];
-				if (sp.s0 < 0 || sp.s1 < sp.s0 || sp.s1 > n_steps) {
+				if (sp.s0 < 0 || sp.s1 < sp.s0 || sp.s1 > n_steps || sp.team < 1 || sp.member < 0 || sp.member >= sp.team) {
 					return bad("segment-parallel span", sp.s0);
 				}
 				if (sp.s0 == sp.s1) {
@@ -1096,11 +1277,66 @@ bool validate_schedule(const FlatRig &R, int cap_bones, int cap_seg, int cap_sta
 				if (!(R.steps[sp.s0].flags & STEP_SEG_FIRST) || !(R.steps[sp.s1 - 1].flags & STEP_SEG_ROOT)) {
 					return bad("segment-parallel span is not a whole segment", sp.s0);
 				}
+				if (sp.team > 1) {
+					// every member of a team carries the same span; each member index exactly once (a missing member
+					// would leave the others waiting at the team barrier)
+					if (sp.buf < 0 || sp.buf >= R.sp_team_bufs || k >= R.sp_roles /* teams live in slot 0 */ || sp.team > R.sp_roles) {
+						return bad("team span", sp.s0);
+					}
+					if (team_size[sp.buf] == 0) {
+						team_size[sp.buf] = sp.team;
+						team_s0[sp.buf] = sp.s0;
+					} else if (team_size[sp.buf] != sp.team || team_s0[sp.buf] != sp.s0) {
+						return bad("team members disagree", sp.s0);
+					}
+					if (members_seen[sp.buf] & (1 << sp.member)) {
+						return bad("duplicate team member", sp.s0);
+					}
+					members_seen[sp.buf] |= 1 << sp.member;
+					for (int s = sp.s0; s < sp.s1; s++) {
+						const BlobStep &S = R.steps[s];
+						const int ref = R.step_path[s];
+						if (ref < 0 || ref + S.eff_cnt > (int)R.path_refs.size() || S.n_headings > R.sp_team_headings || S.eff_cnt < 2) {
+							return bad("team step path table", s);
+						}
+						int h = 0;
+						for (int e = 0; e < S.eff_cnt; e++) {
+							const BlobPathRef pr = R.path_refs[ref + e];
+							const BlobEff &E = R.effs[S.eff_off + e];
+							if (pr.off < 0 || pr.cnt < 0 || pr.off + pr.cnt > (int)R.paths.size() || E.h_off != h) {
+								return bad("team step path", s);
+							}
+							h += E.n_headings;
+							int at = S.bone; // the path descends from the solved bone to the effector's bone
+							for (int q = 0; q < pr.cnt; q++) {
+								const int t = R.paths[pr.off + q];
+								if (t < 0 || t >= ns || R.bones[t].parent != at) {
+									return bad("team step path entry", s);
+								}
+								at = t;
+							}
+							if (at != E.bone) {
+								return bad("team step path end", s);
+							}
+						}
+						if (h != S.n_headings) {
+							return bad("team step heading count", s);
+						}
+					}
+					if (sp.member != 0) {
+						continue; // helpers repeat the owner's span
+					}
+				}
 				for (int s = sp.s0; s < sp.s1; s++) {
 					if (phase_of_step[s] >= 0 || (s > sp.s0 && (R.steps[s].flags & STEP_SEG_FIRST))) {
 						return bad("segment-parallel span overlap", s);
 					}
 					phase_of_step[s] = ph;
+				}
+			}
+			for (int b = 0; b < kMaxSpTeams; b++) {
+				if (team_size[b] > 0 && members_seen[b] != (1 << team_size[b]) - 1) {
+					return bad("incomplete team", team_s0[b]);
 				}
 			}
 		}

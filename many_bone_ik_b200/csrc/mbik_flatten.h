@@ -58,6 +58,10 @@ struct FlatRig {
 	// segment-parallel schedule (BlobSpan): roles = warps per pose group, cost estimates in arbitrary units
 	std::vector<BlobSpan> sched;
 	int sp_roles = 0, sp_phases = 0, sp_slots = 0;
+	int sp_team_bufs = 0, sp_team_headings = 0;
+	std::vector<int32_t> step_path;     // per step: first BlobPathRef or -1
+	std::vector<BlobPathRef> path_refs;
+	std::vector<int16_t> paths;
 	double sp_serial_cost = 0, sp_critical_cost = 0; // all steps on one warp vs the longest role per phase, summed
 	std::string error;
 };

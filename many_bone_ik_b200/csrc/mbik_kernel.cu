@@ -22,16 +22,16 @@ int kernel_capacity_of_variant(int v) { return (v >= 0 && v < kNumVariants) ? kV
 
 // Segment-parallel mapping (mbik_solve_kernel_sp): wins while the batch is small enough that the one-thread-per-pose
 // mapping leaves most warp slots of the GPU empty -- its latency is the critical path of the segment tree instead of
-// the whole bone list.  Returns 0 = one thread per pose, 1 = segment-parallel with the full register budget (at most
-// one 32-pose group per SM: a 4096-pose batch on 148 SMs), 2 = segment-parallel compiled for 128 registers so that
-// floor(16 / roles) groups share an SM in ONE wave; past that the machine is full either way and the lockstep
-// kernel's shared instruction stream is the better use of it (measured, humanoid22: 8192 poses 0.95 vs 1.56 ms,
-// 16384 poses 1.98 vs 1.62 ms).
+// the whole bone list.  Returns 0 = one thread per pose, 1 = segment-parallel with the full register budget (one
+// 32-pose group per SM: a 4096-pose batch on 148 SMs), 2 = segment-parallel compiled for 128 registers so that
+// floor(16 / roles) groups share an SM; past a few waves of groups the machine is full either way and the lockstep
+// kernel's shared instruction stream is the better use of it (measured, humanoid22: 8192 poses 0.81 vs 1.55 ms,
+// 16384 poses 1.69 vs 1.58 ms; quad80: 8192 poses 6.3 vs 11.3 ms).
 int segment_parallel_choice(const SolveArgs &a, int variant, int sm_count) {
 	if (a.sched_mode == 1 || a.sp_roles < (a.sched_mode == 2 ? 1 : 2) || a.sp_roles > kMaxSpRoles || variant == 2) {
 		return 0;
 	}
-	const size_t smem = (((size_t)a.blob_bytes + 127) & ~(size_t)127) + (size_t)a.n_solved * 12 * 32 * sizeof(float);
+	const size_t smem = sp_smem_bytes(a);
 	if (smem > 227 * 1024) {
 		return 0;
 	}
@@ -48,7 +48,20 @@ int segment_parallel_choice(const SolveArgs &a, int variant, int sm_count) {
 	if (a.sched_mode == 2) {
 		return resident >= 2 ? 2 : 1;
 	}
-	return (a.sp_gain >= 1.25f && resident >= 2 && groups <= resident * (size_t)sm_count) ? 2 : 0;
+	if (a.sp_gain < 1.25f) {
+		return 0;
+	}
+	// Larger batches, in units of the time of one wave of full-register groups: the full-register build runs
+	// ceil(groups / SMs) waves, the 128-register build packs `resident` groups per SM at ~1.2x per wave (measured,
+	// humanoid22: 0.81 vs 0.67 ms), and the one-thread-per-pose mapping takes ~sp_gain such units while its CTAs still
+	// fit one wave (measured: humanoid22 1.55 ms up to 16k poses; quad80 11.3 ms).  Segment-parallel only with margin.
+	const double waves1 = (double)((groups + sm_count - 1) / sm_count);
+	const double waves2 = resident >= 2 ? 1.2 * (double)((groups + resident * sm_count - 1) / (resident * sm_count)) : 1e30;
+	const double best = waves1 < waves2 ? waves1 : waves2;
+	if (best >= 0.85 * (double)a.sp_gain) {
+		return 0;
+	}
+	return waves1 <= waves2 ? 1 : 2;
 }
 bool uses_segment_parallel(const SolveArgs &a, int variant, int sm_count) { return segment_parallel_choice(a, variant, sm_count) != 0; }
 

@@ -25,7 +25,9 @@ struct SolveArgs {
 	// host-side launch hints (the kernel reads the schedule itself from the blob header)
 	int32_t n_solved;        // solved bones of the rig
 	int32_t sp_roles;        // warps per pose group of the rig's segment-parallel schedule (<= 1: none)
+	int32_t sp_team_bytes;   // shared memory of the heading buffers of its teams (per group)
 	float sp_gain;           // estimated serial / critical-path cost of that schedule
+	long long *sp_trace;     // debug (MBIK_SP_TRACE=1): per (iteration, phase, warp) start / end clock of CTA 0, or nullptr
 	int32_t sched_mode;      // 0 = choose by batch size, 1 = one thread per pose (throughput mapping), 2 = segment-parallel
 };
 
@@ -52,6 +54,10 @@ cudaError_t launch_sp_v0(const SolveArgs &a, int min_groups_per_sm, cudaStream_t
 cudaError_t launch_sp_v1(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
 cudaError_t launch_sp_v3(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
 cudaError_t launch_sp_v4(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
+// shared memory of one 32-pose group: rig blob + the group's local poses (n_solved x 12 words x 32 lanes) + team buffers
+inline size_t sp_smem_bytes(const SolveArgs &a) {
+	return (((size_t)a.blob_bytes + 127) & ~(size_t)127) + (size_t)a.n_solved * 12 * 32 * sizeof(float) + (size_t)a.sp_team_bytes;
+}
 // true if launch_solve would run the segment-parallel mapping for these arguments
 bool uses_segment_parallel(const SolveArgs &a, int variant, int sm_count);
 

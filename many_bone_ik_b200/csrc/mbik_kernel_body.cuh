@@ -503,16 +503,17 @@ __device__ __forceinline__ void heading_emit(HeadingAcc &A, int pass_i, bool tra
 
 // Ge = global transform of the effector's bone, De = its bone-direction local basis, T = its target,
 // bo = origin of the SOLVED bone's bone-direction frame, tgtO = effector-bone origin the TARGET headings are taken
-// from (= xform_zero(Ge), except in the stabilisation pass where target headings date from before the step)
-__device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, bool translate, const BlobEff &E, const X34 &Ge, const M3 &De,
-		const X34 &T, V3 bo, V3 tgtO) {
+// from (= xform_zero(Ge), except in the stabilisation pass where target headings date from before the step).
+// sink(target heading, tip heading, weight, (float)weight) is called once per heading, in the reference's list order.
+template <class Sink>
+__device__ __forceinline__ void effector_raw_headings(const BlobEff &E, const X34 &Ge, const M3 &De, const X34 &T, V3 bo, V3 tgtO, Sink &&sink) {
 	const V3 tipO = xform_zero(Ge);
 	// heading 0: origins.  Target heading is taken from the EFFECTOR's own bone (:97), tip heading from the solved bone (:125)
 	V3 th = vsub(T.o, tgtO);
 	V3 mh = vsub(tipO, bo);
 	float dist = vlen(vsub(bo, T.o));
 	float scale_by = dist < 1.0f ? dist : 1.0f; // MIN(distance, 1.0f)
-	heading_emit(A, pass_i, translate, th, mh, E.w_origin, E.w_origin_f);
+	sink(th, mh, E.w_origin, E.w_origin_f);
 #pragma unroll
 	for (int ax = 0; ax < 3; ax++) {
 		if (E.prio[ax] > 0.0f) {
@@ -527,11 +528,18 @@ __device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, boo
 			V3 tcol = vmuls(m3_xform(Ge.b, m3_col(De, ax)), E.prio[ax]);
 			V3 mhp = vmuls(vsub(vadd(tcol, tipO), bo), scale_by);
 			V3 mhm = vmuls(vsub(vsub(tipO, tcol), bo), scale_by);
-			heading_emit(A, pass_i, translate, thp, mhp, wd, w);
-			heading_emit(A, pass_i, translate, thm, mhm, wd, w);
+			sink(thp, mhp, wd, w);
+			sink(thm, mhm, wd, w);
 		}
 	}
 }
+__device__ __forceinline__ void effector_headings(HeadingAcc &A, int pass_i, bool translate, const BlobEff &E, const X34 &Ge, const M3 &De,
+		const X34 &T, V3 bo, V3 tgtO) {
+	effector_raw_headings(E, Ge, De, T, bo, tgtO, [&](V3 th, V3 mh, double wd, float wf) { heading_emit(A, pass_i, translate, th, mh, wd, wf); });
+}
+
+// named barrier of a team of warps (segment-parallel kernel; barrier 0 is __syncthreads)
+__device__ __forceinline__ void team_barrier(int id, int n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
@@ -576,6 +584,9 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	const int16_t *chain = reinterpret_cast<const int16_t *>(smem + H.off_chain);
 	const float *rest = reinterpret_cast<const float *>(smem + H.off_rest);
 	const BlobSpan *spans = reinterpret_cast<const BlobSpan *>(smem + H.off_sched);
+	const int32_t *step_path = reinterpret_cast<const int32_t *>(smem + H.off_step_path);
+	const BlobPathRef *path_refs = reinterpret_cast<const BlobPathRef *>(smem + H.off_path_refs);
+	const int16_t *paths = reinterpret_cast<const int16_t *>(smem + H.off_paths);
 	const int sp_roles = SP ? H.sp_roles : 1, sp_phases = SP ? H.sp_phases : 1, sp_slots = SP ? H.sp_slots : 1;
 	const int role = SP ? (int)(threadIdx.x >> 5) : 0;
 
@@ -625,12 +636,23 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 
 	for (int it = 0; it < a.iterations; it++) {
 	for (int ph = 0; ph < sp_phases; ph++) {
+		if (SP && a.sp_trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+			a.sp_trace[(((size_t)it * sp_phases + ph) * sp_roles + role) * 2] = clock64();
+		}
 	for (int slot = 0; slot < sp_slots; slot++) {
 		int s_begin = 0, s_end = n_steps;
+		int team = 1, member = 0;   // SP: heading helpers (BlobSpan)
+		float *hbuf = nullptr;      // the team's raw headings, [heading][th xyz, mh xyz][lane]
+		int team_bar = 0;
 		if (SP) {
 			const BlobSpan span = spans[(ph * sp_slots + slot) * sp_roles + role];
 			s_begin = span.s0;
 			s_end = span.s1;
+			team = span.team;
+			member = span.member;
+			team_bar = 1 + span.buf;
+			hbuf = reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + (size_t)ns * 12 * 32 + (size_t)span.buf * H.sp_team_headings * 6 * 32 +
+					(threadIdx.x & 31);
 		}
 		for (int s = s_begin; s < s_end; s++) {
 			// Keep the CTA's warps in lockstep at bone-step granularity: the step body is ~75 KB of straight-line
@@ -641,6 +663,9 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 #endif
 			if (!SP && (MBIK_SYNC_EVERY == 1 || (s % MBIK_SYNC_EVERY) == 0)) {
 				__syncthreads();
+			}
+			if (SP && team > 1) {
+				team_barrier(team_bar, 32 * team); // the owner's previous step is in shared memory; the heading buffer is free
 			}
 			const BlobStep &S = steps[s];
 			const int b = S.bone;
@@ -699,6 +724,63 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				if (flags & STEP_PUSH_SELF) {
 					Gstk.st(0, Gb);
 				}
+				if (SP && team > 1) {
+					// team step: member m builds the raw headings of effectors m, m + team, ... (global transform of the
+					// effector's bone = the same left-to-right product chain as the depth-first walk below)
+					const int ref = step_path[s];
+					for (int e = member; e < S.eff_cnt; e += team) {
+						const BlobEff &E = effs[S.eff_off + e];
+						const BlobPathRef pr = path_refs[ref + e];
+						X34 run = Gb;
+						for (int k = 0; k < pr.cnt; k++) {
+							run = x_mul(run, L.ld(paths[pr.off + k]));
+						}
+						float *hb = hbuf + (size_t)E.h_off * 6 * 32;
+						effector_raw_headings(E, run, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, xform_zero(run),
+								[&](V3 th, V3 mh, double, float) {
+									hb[0] = th.x; hb[32] = th.y; hb[64] = th.z;
+									hb[96] = mh.x; hb[128] = mh.y; hb[160] = mh.z;
+									hb += 6 * 32;
+								});
+					}
+					team_barrier(team_bar, 32 * team);
+					if (member != 0) {
+						continue; // helpers are done with this step
+					}
+					// owner: fold the headings into the QCP sums in list order (pass 0: centroids of a translating segment)
+					for (int pass_i = translate ? 0 : 1; pass_i < 2; pass_i++) {
+						A.total_w = 0.0;
+						A.csum_m = A.csum_t = v3(0.0f, 0.0f, 0.0f);
+						const float *hb = hbuf;
+						for (int e = 0; e < S.eff_cnt; e++) {
+							const BlobEff &E = effs[S.eff_off + e];
+							auto emit = [&](double wd, float wf) {
+								heading_emit(A, pass_i, translate, v3(hb[0], hb[32], hb[64]), v3(hb[96], hb[128], hb[160]), wd, wf);
+								hb += 6 * 32;
+							};
+							emit(E.w_origin, E.w_origin_f);
+#pragma unroll
+							for (int ax = 0; ax < 3; ax++) {
+								if (E.prio[ax] > 0.0f) {
+									emit(E.w_axis[ax], E.w_axis_f[ax]);
+									emit(E.w_axis[ax], E.w_axis_f[ax]);
+								}
+							}
+						}
+						if (pass_i == 0) {
+							V3 moved_center, target_center;
+							if (A.total_w > 0.0) {
+								moved_center = vdivs(A.csum_m, (float)A.total_w);
+								target_center = vdivs(A.csum_t, (float)A.total_w);
+							} else {
+								moved_center = A.csum_m;
+								target_center = A.csum_t;
+							}
+							A.neg_mc = vmuls(moved_center, -1.0f);
+							A.neg_tc = vmuls(target_center, -1.0f);
+						}
+					}
+				} else {
 				// pass 0 (translating root segment only): weighted centroids; pass 1: inner product (:225-248)
 				const bool cache_frames = ECACHE > 0 && translate && S.eff_cnt <= ECACHE;
 				for (int pass_i = translate ? 0 : 1; pass_i < 2; pass_i++) {
@@ -782,6 +864,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						A.neg_mc = vmuls(moved_center, -1.0f);
 						A.neg_tc = vmuls(target_center, -1.0f);
 					}
+				}
 				}
 				q = (S.n_headings == 1) ? qcp_rotation_single(A.csum_m, A.csum_t) : qcp_rotation(A.sums);
 				// translation = target_center - moved_center (src/math/qcp.cpp:135-137); the centres are the exact
@@ -937,6 +1020,9 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 		}
 	}
 		if (SP) {
+			if (a.sp_trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+				a.sp_trace[(((size_t)it * sp_phases + ph) * sp_roles + role) * 2 + 1] = clock64();
+			}
 			__syncthreads(); // phase boundary: the segments of the next phase read what this one wrote
 		}
 	}
@@ -1030,10 +1116,6 @@ template <int NB, int NSEG, int NSTK, bool STAB, int MINB>
 __global__ void __launch_bounds__(32 * kMaxSpRoles, MINB) mbik_solve_kernel_sp(SolveArgs a) {
 	solve_body<NB, NSEG, NSTK, STAB, 0, true>(a);
 }
-// shared memory of one group: rig blob + the group's local poses (n_solved x 12 words x 32 lanes)
-inline size_t sp_smem_bytes(const SolveArgs &a) {
-	return (((size_t)a.blob_bytes + 127) & ~(size_t)127) + (size_t)a.n_solved * 12 * 32 * sizeof(float);
-}
 template <int NB, int NSEG, int NSTK, bool STAB, int MINB>
 static cudaError_t launch_variant_sp_m(const SolveArgs &a, cudaStream_t stream) {
 	const size_t smem = sp_smem_bytes(a);
@@ -1044,8 +1126,16 @@ static cudaError_t launch_variant_sp_m(const SolveArgs &a, cudaStream_t stream) 
 	if (e != cudaSuccess) {
 		return e;
 	}
-	// several groups per SM: ask for the shared-memory-heavy split of the L1 / shared array (the groups' poses live there)
-	cudaFuncSetAttribute(mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	// L1 / shared split: exactly what the resident groups need as shared memory (MINB == 1: one group per SM), the rest
+	// stays L1 for the thread-local scratch (segment chain, walk stack) -- with the maximum carve-out the local loads of
+	// a 6-warp group missed L1 and a team step cost more than it saved
+	{
+		const size_t by_regs = MINB == 1 ? 1 : 16 / (size_t)a.sp_roles, by_smem = (size_t)(227 * 1024) / (smem + 1024);
+		const size_t resident = by_regs < by_smem ? by_regs : by_smem;
+		int pct = (int)((resident * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+		pct = pct > 100 ? 100 : pct;
+		cudaFuncSetAttribute(mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+	}
 	unsigned grid = (unsigned)((a.n_poses + 31) / 32);
 	mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB><<<grid, 32 * a.sp_roles, smem, stream>>>(a);
 	return cudaGetLastError();

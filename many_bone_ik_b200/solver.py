@@ -76,6 +76,13 @@ class BatchedIKRig:
         self.lib.mbik_rig_get_bone_order(self.handle, out.ctypes.data_as(C.POINTER(C.c_int32)))
         return out
 
+    def schedule(self):
+        """Segment-parallel schedule: rows (phase, warp, first step, end step, team size, member index)."""
+        n = self.lib.mbik_rig_get_schedule(self.handle, None, 0)
+        out = np.zeros((max(n, 1), 6), np.int32)
+        self.lib.mbik_rig_get_schedule(self.handle, out.ctypes.data_as(C.POINTER(C.c_int32)), n)
+        return out[:n]
+
     def step_weights(self, step):
         buf = np.zeros(512, np.float64)
         n = self.lib.mbik_rig_get_step_weights(self.handle, int(step), buf.ctypes.data_as(C.POINTER(C.c_double)), 512)

@@ -126,6 +126,30 @@ def test_segment_parallel_schedule_facts():
         assert 1 <= i["sp_roles"] <= 8 and 1 <= i["sp_phases"] <= i["n_segments"] and i["sp_gain"] >= 1.0
 
 
+def test_segment_parallel_teams():
+    """Warps a phase leaves idle join its one busy multi-effector segment as heading helpers: humanoid22's spine
+    (3 effectors: head, hands) gets a team of 3 and its hips (5 effectors) a team of 5; phases with several busy
+    segments and single-effector segments keep one warp per segment; stabilisation / constraint mode never team up."""
+    rows = BatchedIKRig(rigs.humanoid22()).schedule()
+    by_phase = {ph: rows[rows[:, 0] == ph] for ph in range(3)}
+    assert (by_phase[0][:, 4] == 1).all() and len(by_phase[0]) == 5
+    assert sorted(by_phase[1][:, 5]) == [0, 1, 2] and (by_phase[1][:, 4] == 3).all() and len(set(map(tuple, by_phase[1][:, 2:4]))) == 1
+    assert sorted(by_phase[2][:, 5]) == [0, 1, 2, 3, 4] and (by_phase[2][:, 4] == 5).all()
+    q = BatchedIKRig(rigs.quad80()).schedule()
+    assert (q[q[:, 0] == 1][:, 4] == 1).all()      # spine and tail run side by side: no helpers
+    assert (q[q[:, 0] == 2][:, 4] == 6).all()      # the pelvis step alone: all six warps
+    for name in ("humanoid_stabilized", "humanoid_constraint_mode"):
+        assert (BatchedIKRig(rig_cases.EDGE_RIGS[name]()).schedule()[:, 4] == 1).all()
+    # every step is owned exactly once per iteration
+    for f in list(rigs.RIGS.values()) + [rig_cases.EDGE_RIGS[n] for n in sorted(rig_cases.EDGE_RIGS)]:
+        R = BatchedIKRig(f())
+        owned = np.zeros(R.info["n_steps"], int)
+        for ph, w, s0, s1, team, member in R.schedule():
+            if member == 0:
+                owned[s0:s1] += 1
+        assert (owned == 1).all(), R.rig.name
+
+
 def test_flops_floor_matches_survey_formula():
     """humanoid22 floor = 30.5 kflop/iteration -> ~305 kflop per 10-iteration solve."""
     h = BatchedIKRig(rigs.humanoid22())
