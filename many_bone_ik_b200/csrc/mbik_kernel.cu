@@ -84,17 +84,19 @@ cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStre
 	int threads = kBlockThreads;
 	if (a.stabilize) {
 		threads = 0;
-	} else if (variant <= 1) {
+	} else {
 		// Small batches: one CTA per SM with as few warps as cover the batch (a 4096-pose batch runs as 128
-		// one-warp CTAs on 128 SMs instead of 11 twelve-warp CTAs on 11 SMs) -- latency, not throughput.
+		// one-warp CTAs on 128 SMs instead of 8 sixteen-warp CTAs on 8 SMs) -- latency, not throughput.
 		static const int forced = getenv("MBIK_THREADS") ? atoi(getenv("MBIK_THREADS")) : 0; // tuning knob
 		if (forced > 0) {
 			threads = forced;
 		} else {
-			const int cands[] = { 32, 64, 128, 256 };
-			for (int c : cands) {
-				if ((a.n_poses + c - 1) / c <= (size_t)sm_count) {
-					threads = c;
+			const int cands_small[] = { 32, 64, 128, 256 }, cands_large[] = { 32, 128 }; // instantiated CTA sizes per variant
+			const int *cands = variant <= 1 ? cands_small : cands_large;
+			const int n_cands = variant <= 1 ? 4 : 2;
+			for (int i = 0; i < n_cands; i++) {
+				if ((a.n_poses + cands[i] - 1) / cands[i] <= (size_t)sm_count) {
+					threads = cands[i];
 					break;
 				}
 			}

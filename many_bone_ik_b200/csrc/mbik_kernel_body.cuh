@@ -34,7 +34,9 @@
 // Software pipelining of the effector walk (tuning knobs): request the local pose of walk child k+1 before the
 // products / headings of child k (on: +2 % humanoid22, +7 % quad80, +11 % chain64); hoist the effector's target
 // load above the product (off: the extra live registers cost more than the latency they hide).
-// effector frames kept between the two heading passes of a translating step on the small-rig variants (0 = walk twice)
+// effector frames kept between the two heading passes of a translating step on the small-rig variants of the
+// segment-parallel kernel (0 = walk twice).  The lockstep kernel gains 0.5 % from it but its DRAM traffic grows 60 %
+// (384 more bytes of thread-local state per pose), so there it stays off.
 #ifndef MBIK_ECACHE_SMALL
 #define MBIK_ECACHE_SMALL 8
 #endif
@@ -620,7 +622,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	// translating (root) segments build every heading twice (centroid pass, inner-product pass): on the large-rig
 	// variants the effector frames of the first pass are kept, so the second pass needs no walk (chain64: 8 steps x
 	// 56-bone walks per iteration)
-	constexpr int ECACHE = NB >= 64 ? 16 : MBIK_ECACHE_SMALL;
+	constexpr int ECACHE = NB >= 64 ? 16 : (SP ? MBIK_ECACHE_SMALL : 0);
 	float Efr[ECACHE > 0 ? ECACHE * 12 : 1];
 	double prev_dev = (double)INFINITY;
 
