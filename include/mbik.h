@@ -209,7 +209,9 @@ int mbik_measure_fp32_tflops(int32_t device, int32_t reps, double *out_tflops);
 
 /* Device self-test (not on the solve path): the kernel's grouped sqrt/division sequences against the compiler's
  * correctly rounded __fsqrt_rn/__fdiv_rn, bit for bit (sqrt exhaustively over the guarded range; division over all
- * 2^23 divisor mantissas x rounds x 64 numerators).  *out_mismatches must come back 0. */
+ * 2^23 divisor mantissas x rounds x 64 numerators), and that the packed FP32x2 operations (two lanes per instruction)
+ * equal the scalar individually rounded ones lane by lane, a product feeding a sum included (no FMA contraction).
+ * *out_mismatches must come back 0. */
 int mbik_selftest(int32_t device, int32_t rounds, uint64_t *out_checked, uint64_t *out_mismatches);
 
 /*

@@ -142,6 +142,72 @@ __global__ void vector_cases(unsigned long long *bad, unsigned long long *n, uin
 }
 
 // ---- stage probes: the kernel's own device functions on caller-supplied inputs ----
+// Packed FP32x2 operations (mbik_math.cuh: f2_mul / f2_add / f2_sub and the composites built on them) against the scalar
+// individually rounded intrinsics, per lane, on random bit patterns: ordinary values, matched exponents (cancellation),
+// zeros of both signs, subnormals, infinities and NaNs.
+__device__ float f2_case_value(uint64_t h, int k) {
+	uint32_t bits = (uint32_t)(h >> (k * 7));
+	switch ((h >> 59) & 7) {
+		case 0: return __uint_as_float(bits);                                              // anything, NaN / Inf included
+		case 1: return __uint_as_float((bits & 0x807fffffu) | 0x3f800000u);                // [1, 2)
+		case 2: return __uint_as_float((bits & 0x807fffffu) | (((bits >> 23) & 7u) + 124u) << 23); // 2^-3 .. 2^4
+		case 3: return __uint_as_float(bits & 0x80000000u);                                // +-0
+		case 4: return __uint_as_float(bits & 0x807fffffu);                                // subnormal
+		case 5: return __uint_as_float((bits & 0x80000000u) | 0x7f800000u);                // +-Inf
+		default: return __uint_as_float((bits & 0x807fffffu) | (((bits >> 23) & 63u) + 96u) << 23);
+	}
+}
+__global__ void f2_cases(unsigned long long *bad, unsigned long long *n, uint32_t round) {
+	uint64_t h = splitmix(((uint64_t)round << 40) ^ ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) ^ 0xF2F2F2F2ull);
+	unsigned long long bd = 0, cnt = 0;
+	for (int it = 0; it < 64; it++) {
+		h = splitmix(h);
+		uint64_t g = splitmix(h ^ 0x5555u);
+		float a0 = f2_case_value(h, 0), a1 = f2_case_value(h, 1), b0 = f2_case_value(g, 0), b1 = f2_case_value(g, 1);
+		if (it & 1) { // equal magnitudes: exact cancellation and signed-zero results
+			b0 = (it & 2) ? a0 : -a0;
+		}
+		float lo, hi;
+		f2_get(f2_mul(f2(a0, a1), f2(b0, b1)), lo, hi);
+		bd += !same(lo, __fmul_rn(a0, b0)) + !same(hi, __fmul_rn(a1, b1));
+		f2_get(f2_add(f2(a0, a1), f2(b0, b1)), lo, hi);
+		bd += !same(lo, __fadd_rn(a0, b0)) + !same(hi, __fadd_rn(a1, b1));
+		f2_get(f2_sub(f2(a0, a1), f2(b0, b1)), lo, hi);
+		bd += !same(lo, __fsub_rn(a0, b0)) + !same(hi, __fsub_rn(a1, b1));
+		// a product feeding a sum must stay two roundings (no contraction into FFMA2)
+		f2_get(f2_add(f2_mul(f2(a0, a1), f2(b0, b1)), f2(b1, a0)), lo, hi);
+		bd += !same(lo, __fadd_rn(__fmul_rn(a0, b0), b1)) + !same(hi, __fadd_rn(__fmul_rn(a1, b1), a0));
+		f2_get(f2_sub(f2(b1, a0), f2_mul(f2(a0, a1), f2(b0, b1))), lo, hi);
+		bd += !same(lo, __fsub_rn(b1, __fmul_rn(a0, b0))) + !same(hi, __fsub_rn(a0, __fmul_rn(a1, b1)));
+		// composites: Basis product / xform rows, Vector3 dot, against the literal scalar formulas
+		M3 A, B;
+		uint64_t q = h;
+		for (int k = 0; k < 9; k++) {
+			q = splitmix(q);
+			A.m[k] = f2_case_value(q, 0);
+			B.m[k] = f2_case_value(q, 2);
+		}
+		M3 P = m3_mul(A, B);
+		for (int i = 0; i < 3; i++) {
+			for (int j = 0; j < 3; j++) {
+				float ref = __fadd_rn(__fadd_rn(__fmul_rn(B.m[j], A.m[3 * i]), __fmul_rn(B.m[3 + j], A.m[3 * i + 1])), __fmul_rn(B.m[6 + j], A.m[3 * i + 2]));
+				bd += !same(P.m[3 * i + j], ref);
+			}
+		}
+		V3 v = v3(a0, b1, b0), w = m3_xform(A, v);
+		float wr[3] = { w.x, w.y, w.z };
+		for (int i = 0; i < 3; i++) {
+			float ref = __fadd_rn(__fadd_rn(__fmul_rn(A.m[3 * i], v.x), __fmul_rn(A.m[3 * i + 1], v.y)), __fmul_rn(A.m[3 * i + 2], v.z));
+			bd += !same(wr[i], ref);
+		}
+		V3 u = v3(a1, b0, b1);
+		bd += !same(vdot(u, v), __fadd_rn(__fadd_rn(__fmul_rn(u.x, v.x), __fmul_rn(u.y, v.y)), __fmul_rn(u.z, v.z)));
+		cnt += 10 + 9 + 3 + 1;
+	}
+	atomicAdd(bad, bd);
+	atomicAdd(n, cnt);
+}
+
 __global__ void stage_qcp_kernel(int n, const float *moved, const float *target, const double *weight, int translate, float *out7) {
 	if (threadIdx.x != 0 || blockIdx.x != 0) {
 		return;
@@ -230,6 +296,7 @@ int mbik_selftest(int32_t device, int32_t rounds, uint64_t *out_checked, uint64_
 	for (int r = 0; r < (rounds > 0 ? rounds : 1); r++) {
 		div_sweep<<<148 * 8, 256>>>(d, d + 1, (uint32_t)r);
 		vector_cases<<<148 * 8, 256>>>(d, d + 1, (uint32_t)r);
+		f2_cases<<<148 * 8, 256>>>(d, d + 1, (uint32_t)r);
 	}
 	unsigned long long h[2] = { 0, 0 };
 	cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);

@@ -95,6 +95,8 @@ def addr(r):
 
 
 base = addr(data[0])
+scalar_caller = collections.Counter()  # scalar r_mul / r_add / r_sub instructions by the function that calls them
+SCALAR = ("r_mul", "r_add", "r_sub")
 inner = collections.Counter()
 stage = collections.Counter()
 stmt = collections.Counter()
@@ -119,6 +121,10 @@ for r in data:
         inner_s["(no line info)"] += sm
         continue
     fi = func_of(*ours[0])
+    if fi in SCALAR:
+        callers = [func_of(*x) for x in ours[1:]]
+        callers = [c for c in callers if c not in SCALAR]
+        scalar_caller[(callers[0] if callers else "?") + (" < " + callers[1] if len(callers) > 1 else "")] += ie
     inner[fi] += ie
     inner_s[fi] += sm
     # the chain is innermost first; the last entry is the kernel body statement
@@ -135,6 +141,10 @@ print(f"total warp-instructions {tot}, stall samples {tots}")
 print("\nby stage (outermost device function called from the kernel body): share of executed instructions / of stall samples")
 for k, v in stage.most_common(top):
     print(f"  {k:28s} {100.0 * v / tot:6.2f}%  {100.0 * stage_s[k] / max(tots, 1):6.2f}%")
+if "--scalar-callers" in sys.argv:
+    print("\nscalar FMUL / FADD (r_mul, r_add, r_sub) by calling function < its caller: share of ALL executed instructions")
+    for k, v in scalar_caller.most_common(top):
+        print(f"  {k:60s} {100.0 * v / tot:6.2f}%")
 print("\nby innermost function:")
 for k, v in inner.most_common(top):
     print(f"  {k:28s} {100.0 * v / tot:6.2f}%  {100.0 * inner_s[k] / max(tots, 1):6.2f}%")
