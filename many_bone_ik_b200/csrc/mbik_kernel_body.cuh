@@ -206,14 +206,20 @@ __device__ __forceinline__ void qcp_accumulate(QcpSums &s, V3 target, V3 moved, 
 	V3 wc1 = vmuls(target, wf);
 	s.ss1 = r_add(s.ss1, (double)vdot(wc1, target));
 	s.ss2 = r_add(s.ss2, r_mul(w, (double)vdot(moved, moved)));
-	s.xx = r_add(s.xx, (double)r_mul(wc1.x, moved.x));
-	s.xy = r_add(s.xy, (double)r_mul(wc1.x, moved.y));
+	// the nine float products: moved.x and moved.y lanes as one packed multiply per row
+	const F2 mxy = f2(moved.x, moved.y);
+	float px, py;
+	f2_get(f2_mul(f2_bc(wc1.x), mxy), px, py);
+	s.xx = r_add(s.xx, (double)px);
+	s.xy = r_add(s.xy, (double)py);
 	s.xz = r_add(s.xz, (double)r_mul(wc1.x, moved.z));
-	s.yx = r_add(s.yx, (double)r_mul(wc1.y, moved.x));
-	s.yy = r_add(s.yy, (double)r_mul(wc1.y, moved.y));
+	f2_get(f2_mul(f2_bc(wc1.y), mxy), px, py);
+	s.yx = r_add(s.yx, (double)px);
+	s.yy = r_add(s.yy, (double)py);
 	s.yz = r_add(s.yz, (double)r_mul(wc1.y, moved.z));
-	s.zx = r_add(s.zx, (double)r_mul(wc1.z, moved.x));
-	s.zy = r_add(s.zy, (double)r_mul(wc1.z, moved.y));
+	f2_get(f2_mul(f2_bc(wc1.z), mxy), px, py);
+	s.zx = r_add(s.zx, (double)px);
+	s.zy = r_add(s.zy, (double)py);
 	s.zz = r_add(s.zz, (double)r_mul(wc1.z, moved.z));
 }
 // calculate_rotation, general branch (:80-123)
