@@ -28,6 +28,11 @@ def _assert_same(rig, got, ref):
     assert np.array_equal(st, ref_st)
 
 
+# Both kernel mappings are product paths (the library picks by batch size): tests that probe one behaviour on a small
+# batch run it through each mapping explicitly.
+SCHEDS = ("throughput", "segment_parallel")
+
+
 def _compare(rig, n, iterations=-1, start_pose=None, first=0):
     R = BatchedIKRig(rig)
     T = rigs.random_targets(rig, first, n)
@@ -114,10 +119,11 @@ def test_cuda_reproduces_golden_fixtures(name):
     g = np.load(os.path.join(GOLD, "oracle_solves.npz"))
     rig = cases[name]()
     R = BatchedIKRig(rig)
-    out, loc, st = R.solve(g[name + "_targets"], want_local=True)
-    assert np.array_equal(loc, g[name + "_local"], equal_nan=True)
-    assert np.array_equal(out, g[name + "_out"], equal_nan=True)
-    assert np.array_equal(st, g[name + "_status"])
+    for sched in SCHEDS:
+        out, loc, st = R.solve(g[name + "_targets"], want_local=True, sched=sched)
+        assert np.array_equal(loc, g[name + "_local"], equal_nan=True), sched
+        assert np.array_equal(out, g[name + "_out"], equal_nan=True), sched
+        assert np.array_equal(st, g[name + "_status"]), sched
 
 
 @pytest.mark.parametrize("n", [1, 31, 33, 383, 385, 148 * 384 + 5])
@@ -126,13 +132,14 @@ def test_ragged_batch_sizes(n):
     rig = rigs.humanoid22()
     R = BatchedIKRig(rig)
     T = rigs.random_targets(rig, 0, n)
-    out, loc, st = R.solve(T, want_local=True)
     m = min(n, 64)
     ref = O.solve_batch(rig, T[:m], want_local=True, threads=8)
-    _assert_same(rig, (out[:m], loc[:m], st[:m]), ref)
-    if n > 64:  # tail of the batch: last poses against the oracle too
-        ref_t = O.solve_batch(rig, T[-32:], want_local=True, threads=8)
-        _assert_same(rig, (out[-32:], loc[-32:], st[-32:]), ref_t)
+    ref_t = O.solve_batch(rig, T[-32:], want_local=True, threads=8) if n > 64 else None
+    for sched in SCHEDS + ("auto",):
+        out, loc, st = R.solve(T, want_local=True, sched=sched)
+        _assert_same(rig, (out[:m], loc[:m], st[:m]), ref)
+        if n > 64:  # tail of the batch: last poses against the oracle too
+            _assert_same(rig, (out[-32:], loc[-32:], st[-32:]), ref_t)
 
 
 def test_empty_batch_is_a_no_op():
@@ -338,12 +345,16 @@ def test_non_finite_targets_propagate_like_the_reference():
     T[4, :, :] = 0.0
     T[5, 4, 0] = -np.inf
     T[6, 0, 9:] = (1e20, -1e20, 1e-20)
-    _assert_same(rig, BatchedIKRig(rig).solve(T, want_local=True), O.solve_batch(rig, T, want_local=True, threads=8))
+    ref = O.solve_batch(rig, T, want_local=True, threads=8)
+    for sched in SCHEDS:
+        _assert_same(rig, BatchedIKRig(rig).solve(T, want_local=True, sched=sched), ref)
     q = rigs.quad80()
     Tq = rigs.random_targets(q, 0, 32)
     Tq[::3, ::2, 9:] *= np.float32(1e19)
     Tq[1::3, 1::2, :9] = 0.0
-    _assert_same(q, BatchedIKRig(q).solve(Tq, want_local=True), O.solve_batch(q, Tq, want_local=True, threads=8))
+    refq = O.solve_batch(q, Tq, want_local=True, threads=8)
+    for sched in SCHEDS:
+        _assert_same(q, BatchedIKRig(q).solve(Tq, want_local=True, sched=sched), refq)
 
 
 def test_concurrent_host_calls_on_one_rig():
@@ -428,4 +439,6 @@ def test_overflow_fuzz_random_rigs(seed):
     if seed % 4 == 0:
         T[::5] = np.float32(1e-30) * T[::5]
     R = BatchedIKRig(rig)
-    _assert_same(rig, R.solve(T, want_local=True), O.solve_batch(rig, T, want_local=True, threads=8))
+    ref = O.solve_batch(rig, T, want_local=True, threads=8)
+    for sched in SCHEDS:
+        _assert_same(rig, R.solve(T, want_local=True, sched=sched), ref)
