@@ -206,6 +206,18 @@ __device__ __forceinline__ void qcp_accumulate(QcpSums &s, V3 target, V3 moved, 
 	V3 wc1 = vmuls(target, wf);
 	s.ss1 = r_add(s.ss1, (double)vdot(wc1, target));
 	s.ss2 = r_add(s.ss2, r_mul(w, (double)vdot(moved, moved)));
+#if !MBIK_F2_DOT
+	s.xx = r_add(s.xx, (double)r_mul(wc1.x, moved.x));
+	s.xy = r_add(s.xy, (double)r_mul(wc1.x, moved.y));
+	s.xz = r_add(s.xz, (double)r_mul(wc1.x, moved.z));
+	s.yx = r_add(s.yx, (double)r_mul(wc1.y, moved.x));
+	s.yy = r_add(s.yy, (double)r_mul(wc1.y, moved.y));
+	s.yz = r_add(s.yz, (double)r_mul(wc1.y, moved.z));
+	s.zx = r_add(s.zx, (double)r_mul(wc1.z, moved.x));
+	s.zy = r_add(s.zy, (double)r_mul(wc1.z, moved.y));
+	s.zz = r_add(s.zz, (double)r_mul(wc1.z, moved.z));
+	return;
+#endif
 	// the nine float products: moved.x and moved.y lanes as one packed multiply per row
 	const F2 mxy = f2(moved.x, moved.y);
 	float px, py;

@@ -1,4 +1,11 @@
 // mbik_kernel_v3.cu -- instantiations of the solve kernel for the size variant {64 solved bones, segment 16, stack 8}.
+// The large-rig variants are register-starved at 128 registers (64+ local poses to address): with the packed FP32x2
+// composites they spill and run 2-3 % slower (chain64 71.6 vs 69.4 ms, quad80 13.8 vs 13.5 ms per 75776-pose launch),
+// so this translation unit keeps the scalar formulations (same bits either way).
+#define MBIK_F2_MAT 0
+#define MBIK_F2_VEC 0
+#define MBIK_F2_DOT 0
+#define MBIK_F2_DIV 0
 #include "mbik_kernel_body.cuh"
 
 namespace mbik {
