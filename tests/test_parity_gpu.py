@@ -64,6 +64,23 @@ def test_segment_parallel_several_groups_per_sm(name, n):
         _assert_same(rig, R.solve(T, want_local=True, sched=sched), ref)
 
 
+@pytest.mark.parametrize("name,n", [("humanoid22", 4096 + 17), ("quad80", 2048), ("big_tree120", 1024)])
+def test_segment_parallel_repeats_bitwise(name, n):
+    """The warps of a pose group exchange poses and headings through shared memory between barriers; a missing or
+    misplaced barrier would show as run-to-run differences.  25 repeats of a full-machine batch must return the same
+    bits every time (compute-sanitizer's racecheck is not available on this pool), and equal the lockstep mapping."""
+    cases = dict(rigs.RIGS)
+    cases.update(rig_cases.EDGE_RIGS)
+    rig = cases[name]()
+    R = BatchedIKRig(rig)
+    T = rigs.random_targets(rig, 3, n)
+    first = R.solve(T, want_local=True, sched="throughput")
+    for rep in range(25):
+        got = R.solve(T, want_local=True, sched="segment_parallel")
+        for a, b in zip(got, first):
+            assert np.array_equal(a, b, equal_nan=True), f"{name}: repeat {rep} differs"
+
+
 @pytest.mark.parametrize("iterations", [0, 1, 2, 15])
 def test_humanoid_iteration_counts(iterations):
     _compare(rigs.humanoid22(), 257, iterations=iterations)
