@@ -197,6 +197,25 @@ struct Basis {
 		rows[1][0] *= s.y; rows[1][1] *= s.y; rows[1][2] *= s.y;
 		rows[2][0] *= s.z; rows[2][1] *= s.z; rows[2][2] *= s.z;
 	}
+	// engine: scaled() = copy + scale() (rows), scaled_local() = *this * diag(s) (columns),
+	// orthogonalize() = orthonormalize keeping the scale.  Referenced by src/math/ik_node_3d.cpp:52,106
+	// behind flags the solve path never sets (DIRTY_LOCAL, disable_scale); only oracle/_ref compiles them.
+	Basis scaled(const Vector3 &s) const {
+		Basis b = *this;
+		b.scale(s);
+		return b;
+	}
+	Basis scaled_local(const Vector3 &s) const {
+		Basis d;
+		d.set(s.x, 0, 0, 0, s.y, 0, 0, 0, s.z);
+		return (*this) * d;
+	}
+	void scale_local(const Vector3 &s) { *this = scaled_local(s); }
+	void orthogonalize() {
+		Vector3 scl = get_scale();
+		orthonormalize();
+		scale_local(scl);
+	}
 	Vector3 get_scale_abs() const {
 		return Vector3(Vector3(rows[0][0], rows[1][0], rows[2][0]).length(),
 				Vector3(rows[0][1], rows[1][1], rows[2][1]).length(),

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY -- forwards the engine include path "core/error/error_macros.h" to the stand-in (see godot_shim.h)
+#pragma once
+#include "../../godot_shim.h"
