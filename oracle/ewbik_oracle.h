@@ -6,11 +6,16 @@
 // the per-step allocations are kept on purpose: this is both the parity checker and the honest
 // "reference CPU cost" baseline.
 //
-// Pinning status: the numeric doctest cases of the reference (tests/test_qcp.h,
+// Pinning status: (1) the numeric doctest cases of the reference (tests/test_qcp.h,
 // tests/test_ik_node_3d.h, tests/test_ik_kusudama_3d.h) are restated in oracle/kat_main.cpp and
-// pass against this code.  The reference has NO test that runs segment_solver / ManyBoneIK3D and
-// cannot be compiled here (needs the Godot engine tree), so END-TO-END SOLVE PARITY IS UNPINNED:
-// it rests on line-by-line review of this restatement against the cited reference lines.
+// pass against this code.  (2) The MODULE LOGIC restated here is pinned against the reference's own
+// code: oracle/_ref/libmbik_ref.so is every translation unit of /root/reference/src compiled
+// unmodified over a stand-in of the Godot engine headers (oracle/godot_shim/, driver
+// oracle/ref_harness.cpp, `make ref`); this restatement is bit-identical to it -- end-to-end
+// solves, warm-started frames, setup facts, heading weights, stage functions -- on every benchmark,
+// edge and random rig (tests/test_reference_cpu.py; frozen as tests/golden/reference_solves.npz).
+// (3) What stays UNPINNED is the engine arithmetic underneath both (godot_math.h): the Godot engine
+// is not in the reference tree, so both run on the same restatement of core/math.
 #pragma once
 #include "godot_math.h"
 

@@ -11,9 +11,12 @@
 // (core/math/{vector3,basis,quaternion,transform_3d}.{h,cpp}, math_funcs.h) with
 //   real_t = float, CMP_EPSILON = 1e-5, UNIT_EPSILON = 1e-3, MATH_CHECKS off (release template).
 // PARITY UNPINNED for everything here that the reference's own tests do not touch (see
-// SURVEY.md section 8c); pinned pieces: Quaternion::xform + QCP (tests/test_qcp.h:40-85),
+// SURVEY.md section 8c); pinned pieces: Quaternion::xform + QCP (tests/test_qcp.h:40-113),
 // identity/translation Transform3D round trips (tests/test_ik_node_3d.h), one axis-angle rotation
-// (tests/test_ik_kusudama_3d.h:127-156).
+// (tests/test_ik_kusudama_3d.h:127-156) -- asserted by the reference's own 15 doctest cases, which
+// run unmodified on the reference's own code over THIS file (oracle/_ref/ref_doctests, 52 checks).
+// This header is also the core/math layer of the engine stand-in (oracle/godot_shim/) that the
+// reference's sources are compiled against, so the module logic above it is the real thing there.
 //
 // Evaluation order matters: every expression below is written in the engine's operand order so
 // that, compiled with -ffp-contract=off, it is a deterministic IEEE-754 sequence the CUDA kernel

@@ -1,5 +1,5 @@
-"""Generates tests/golden/*.npz from the CPU oracle (the only runnable form of the reference here; the reference
-itself cannot be imported or compiled in this image).  The fixtures freeze (a) the numeric known-answer values of
+"""Generates tests/golden/oracle_solves.npz and reference_kats.npz from the CPU oracle (the restatement; the fixtures
+written by the reference module's own code are tests/golden/reference_solves.npz, make_reference_golden.py).  The fixtures freeze (a) the numeric known-answer values of
 the reference's own doctest cases and (b) oracle solve outputs for a few seeded poses of every benchmark rig, so
 that any later change to the oracle or the kernel that moves a result is caught.
 

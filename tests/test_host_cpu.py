@@ -51,8 +51,9 @@ def test_no_oracle_in_the_product():
                 src = open(os.path.join(dp, f), errors="replace").read()
                 assert "oracle" not in src.lower() or f in ("build.py", "mbik_math.cuh", "mbik_flatten.cu"), f
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+                assert "libmbik_ref" not in src and "_ref/" not in src and "godot_shim" not in src, f
     ldd = subprocess.run(["ldd", _capi.LIB_PATH], capture_output=True, text=True).stdout
-    assert "oracle" not in ldd
+    assert "oracle" not in ldd and "mbik_ref" not in ldd
 
 
 @pytest.mark.parametrize("name", sorted(ALL_RIGS))
