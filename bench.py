@@ -288,6 +288,35 @@ def main():
     barrier()
     e2e_value = total * args.steps / e2e_s
 
+    # ---- side measurement: what the host link gives this rank while ALL ranks copy at once (plain pinned-memory copies of the
+    # same buffers, no solve): the ceiling of e2e at N GPUs is min(kernel rate, link rate / 1120 B per solve) ----
+    host_link = None
+    try:
+        for _ in range(1):
+            o_host.copy_(o_dev, non_blocking=True)
+            t_dev.copy_(t_host, non_blocking=True)
+        barrier()
+        h0, h1, h2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        reps = 3
+        h0.record()
+        for _ in range(reps):
+            o_host.copy_(o_dev, non_blocking=True)
+        h1.record()
+        for _ in range(reps):
+            t_dev.copy_(t_host, non_blocking=True)
+        h2.record()
+        torch.cuda.synchronize()
+        d2h_ms, h2d_ms = max_over_ranks(h0.elapsed_time(h1)) / reps, max_over_ranks(h1.elapsed_time(h2)) / reps
+        barrier()
+        d2h_gbs, h2d_gbs = o_host.numel() * 4 / (d2h_ms * 1e-3) / 1e9, t_host.numel() * 4 / (h2d_ms * 1e-3) / 1e9
+        per_solve_s = (nb * 40) / (d2h_gbs * 1e9)  # D2H and H2D run on separate copy engines: the slower direction bounds
+        per_solve_s = max(per_solve_s, (npins * 48) / (h2d_gbs * 1e9))
+        host_link = {"d2h_gbs_per_gpu_all_ranks_copying": d2h_gbs, "h2d_gbs_per_gpu_all_ranks_copying": h2d_gbs,
+                     "e2e_ceiling_solves_per_s": world / per_solve_s,
+                     "note": "slowest rank, pinned host buffers of the e2e leg, every rank copying simultaneously; ceiling = N / max(880 B / d2h, 240 B / h2d)"}
+    except Exception as e:  # a side measurement must never break the headline line
+        host_link = {"error": str(e)}
+
     # ---- side measurement: BASELINE configs[2] read literally = ONE 2^20-pose batch sharded over the N GPUs (strong
     # scaling; each rank solves the first 2^20/N poses of its buffer), device-resident ----
     strong = None
@@ -428,6 +457,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "other_rigs_device_resident": other,
         "strong_scaling_1M_batch": strong,
+        "host_link": host_link,
         "clocks": clocks,
         "device_equals_host_path": same,
     }
