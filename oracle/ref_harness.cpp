@@ -15,219 +15,11 @@
 //   skeleton bone poses <- start pose; target nodes <- targets; emit "modification_processed" (the module's own
 //   connection re-seeds the IK bones and targets, :1084 -> :91-102); SkeletonModifier3D::process_modification()
 //   (-> _process_modification(): rebuild if dirty, iterations x segment_solver, write-back).
-#include <atomic>
-#include <cstring>
-#include <thread>
-#include <vector>
+#include "ref_scene.h"
 
-#include "godot_shim/godot_shim.h"
-
-// The harness reads two private tables the module offers no accessor for (bone_damp: written only by
-// _set_bone_count with the default value, src/many_bone_ik_3d.cpp:756-763; heading_weights: facts export).
-// Access specifiers do not change layout or mangling, so this TU sees the same classes the module TUs define.
-#define private public
-#define protected public
-#include "ik_bone_segment_3d.h"
-#include "ik_kusudama_3d.h"
-#include "ik_open_cone_3d.h"
-#include "many_bone_ik_3d.h"
-#include "math/qcp.h"
-#undef private
-#undef protected
-
-#include "../include/mbik.h"
+using namespace ref_scene;
 
 namespace {
-
-Transform3D load_xform(const float *p) {
-	Transform3D t;
-	for (int r = 0; r < 3; r++) {
-		for (int c = 0; c < 3; c++) {
-			t.basis.rows[r][c] = p[r * 3 + c];
-		}
-	}
-	t.origin = Vector3(p[9], p[10], p[11]);
-	return t;
-}
-
-void store_xform(float *o, const Transform3D &t) {
-	for (int r = 0; r < 3; r++) {
-		for (int c = 0; c < 3; c++) {
-			o[r * 3 + c] = t.basis.rows[r][c];
-		}
-	}
-	o[9] = t.origin.x;
-	o[10] = t.origin.y;
-	o[11] = t.origin.z;
-}
-
-String bone_name(int b) {
-	return String("bone_") + itos(b);
-}
-
-// One headless scene: Skeleton3D + ManyBoneIK3D (child of the skeleton) + one target Node3D per pin
-// (children of the modifier, addressed by relative node paths "target_<i>").
-struct RefScene {
-	Skeleton3D *skeleton = nullptr;
-	ManyBoneIK3D *ik = nullptr;
-	std::vector<Node3D *> targets;
-	std::vector<Transform3D> solved_local; // IK bone poses captured when "modification_processed" fires
-	std::vector<char> solved;
-
-	RefScene(const mbik_rig_desc *d, int iterations) {
-		skeleton = new Skeleton3D();
-		for (int b = 0; b < d->n_bones; b++) {
-			skeleton->add_bone(bone_name(b));
-		}
-		for (int b = 0; b < d->n_bones; b++) {
-			skeleton->set_bone_parent(b, d->parent[b]);
-			Transform3D rest = load_xform(d->rest_local + 12 * b);
-			skeleton->set_bone_rest(b, rest);
-			skeleton->set_bone_pose(b, rest); // the rig is built with the skeleton in its rest pose (mbik.h)
-		}
-		ik = new ManyBoneIK3D();
-		solved_local.resize((size_t)d->n_bones);
-		solved.assign((size_t)d->n_bones, 0);
-		// connected before the module's own handler, so it sees the solved IK bones before they are re-seeded
-		Callable capture;
-		capture.object = this;
-		capture.method_id = "harness_capture";
-		capture.fn = [this]() { capture_locals(); };
-		ik->connect(SNAME("modification_processed"), capture);
-		ik->shim_attach_skeleton(skeleton); // -> _skeleton_changed: signal connections + first _bone_list_changed
-
-		for (int p = 0; p < d->n_pins; p++) {
-			Node3D *t = new Node3D();
-			t->set_name(String("target_") + itos(p));
-			ik->add_child(t);
-			targets.push_back(t);
-		}
-		// configuration through the property paths a saved scene uses (ManyBoneIK3D::_set, :296-375)
-		ik->set("pin_count", d->n_pins);
-		for (int p = 0; p < d->n_pins; p++) {
-			const mbik_pin_desc &pd = d->pins[p];
-			String base = String("pins/") + itos(p) + "/";
-			ik->set(StringName(base + "bone_name"), pd.bone >= 0 ? bone_name(pd.bone) : String());
-			ik->set(StringName(base + "target_node"), NodePath(String("target_") + itos(p)));
-			ik->set(StringName(base + "motion_propagation_factor"), pd.motion_propagation_factor);
-			ik->set(StringName(base + "weight"), pd.weight);
-			ik->set(StringName(base + "direction_priorities"),
-					Vector3(pd.direction_priorities[0], pd.direction_priorities[1], pd.direction_priorities[2]));
-		}
-		ik->set("constraint_count", d->n_constraints);
-		for (int c = 0; c < d->n_constraints; c++) {
-			const mbik_constraint_desc &cd = d->constraints[c];
-			String base = String("constraints/") + itos(c) + "/";
-			ik->set(StringName(base + "bone_name"), bone_name(cd.bone));
-			ik->set(StringName(base + "twist_from"), cd.twist_from);
-			ik->set(StringName(base + "twist_range"), cd.twist_range);
-			ik->set(StringName(base + "kusudama_open_cone_count"), cd.n_cones);
-			for (int j = 0; j < cd.n_cones; j++) {
-				const mbik_cone_desc &cone = d->cones[cd.cone_offset + j];
-				String cbase = base + "kusudama_open_cone/" + itos(j) + "/";
-				ik->set(StringName(cbase + "center"), Vector3(cone.center[0], cone.center[1], cone.center[2]));
-				ik->set(StringName(cbase + "radius"), cone.radius);
-			}
-		}
-		ik->set_default_damp(d->default_damp);
-		ik->set_iterations_per_frame((float)(iterations >= 0 ? iterations : d->iterations_per_frame));
-		ik->set_stabilization_passes(d->stabilization_passes);
-		ik->set_constraint_mode(d->constraint_mode != 0);
-		// bone_damp: no public writer in the module (see the note at the includes)
-		ik->bone_damp.resize(d->n_bone_damp);
-		for (int i = 0; i < d->n_bone_damp; i++) {
-			ik->bone_damp.write[i] = d->bone_damp[i];
-		}
-		ik->set_dirty();
-		// the rebuild happens inside the next frame (is_dirty, :655-658) with the skeleton still in its rest pose;
-		// run that frame now so that every later frame only re-seeds and solves
-		ik->process_modification();
-	}
-
-	~RefScene() {
-		for (Node3D *t : targets) {
-			delete t;
-		}
-		delete ik;
-		delete skeleton;
-	}
-
-	void capture_locals() {
-		std::fill(solved.begin(), solved.end(), 0);
-		Vector<Ref<IKBone3D>> list = ik->get_bone_list();
-		for (int i = 0; i < list.size(); i++) {
-			Ref<IKBone3D> b = list[i];
-			if (b.is_null() || b->get_bone_id() < 0) {
-				continue;
-			}
-			solved_local[(size_t)b->get_bone_id()] = b->get_pose();
-			solved[(size_t)b->get_bone_id()] = 1;
-		}
-	}
-
-	void solve(const mbik_rig_desc *d, const float *targets12, const float *start12, float *out10, float *out_local12, uint32_t *status) {
-		std::vector<Transform3D> start((size_t)d->n_bones);
-		for (int b = 0; b < d->n_bones; b++) {
-			start[(size_t)b] = load_xform(start12 ? start12 + 12 * b : d->rest_local + 12 * b);
-			skeleton->set_bone_pose(b, start[(size_t)b]);
-		}
-		for (int p = 0; p < d->n_pins; p++) {
-			targets[(size_t)p]->set_global_transform(load_xform(targets12 + 12 * p));
-		}
-		// the frame boundary: the previous frame's "modification_processed" re-seeds IK bones and targets
-		ik->emit_signal(SNAME("modification_processed"));
-		std::fill(solved.begin(), solved.end(), 0);
-		bool wrote = frame_will_write(d);
-		ik->process_modification();
-		uint32_t st = 0;
-		for (int b = 0; b < d->n_bones; b++) {
-			bool is_solved = wrote && solved[(size_t)b];
-			Transform3D local = is_solved ? solved_local[(size_t)b] : start[(size_t)b];
-			if (out_local12) {
-				store_xform(out_local12 + 12 * b, local);
-			}
-			if (!local.basis.is_finite()) {
-				st |= MBIK_POSE_NONFINITE_RESET;
-			}
-			Vector3 pos;
-			Quaternion rot;
-			Vector3 scl;
-			if (is_solved) {
-				// exactly what IKBone3D::set_skeleton_bone_pose handed to the skeleton (src/ik_bone_3d.cpp:170-179)
-				pos = skeleton->get_bone_pose_position(b);
-				rot = skeleton->get_bone_pose_rotation(b);
-				scl = skeleton->get_bone_pose_scale(b);
-			} else {
-				// bones the solver does not own pass through (mbik.h): the same decomposition of the start pose
-				Basis basis = local.basis;
-				if (!basis.is_finite()) {
-					basis = Basis();
-				}
-				pos = local.origin;
-				rot = basis.get_rotation_quaternion();
-				scl = basis.get_scale();
-			}
-			float *o = out10 + 10 * b;
-			o[0] = pos.x; o[1] = pos.y; o[2] = pos.z;
-			o[3] = rot.x; o[4] = rot.y; o[5] = rot.z; o[6] = rot.w;
-			o[7] = scl.x; o[8] = scl.y; o[9] = scl.z;
-		}
-		if (status) {
-			*status = st;
-		}
-	}
-
-	// _process_modification returns before the write-back when there is no pin (or none with a bone name)
-	// (:649-651, :671-677); then the skeleton keeps the start pose.
-	bool frame_will_write(const mbik_rig_desc *d) const {
-		for (int p = 0; p < d->n_pins; p++) {
-			if (d->pins[p].bone >= 0) {
-				return true;
-			}
-		}
-		return false;
-	}
-};
 
 void solve_range(const mbik_rig_desc *d, size_t begin, size_t end, const float *targets, const float *start_pose, float *out_pose,
 		float *out_local, uint32_t *out_status, int iterations, bool rebuild_each) {

@@ -19,6 +19,7 @@ from many_bone_ik_b200._capi import RigDesc, rig_to_desc
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "libmbik_ref.so")
 DOCTESTS = os.path.join(_HERE, "_ref", "ref_doctests")
+BINDING_LIB = os.path.join(_HERE, "_ref", "libmbik_ref_binding.so")
 REFERENCE = os.environ.get("MBIK_REFERENCE_DIR", "/root/reference")
 
 
@@ -31,6 +32,14 @@ def build(force=False):
     if source_present():
         subprocess.check_call(["make", "-C", _HERE, "-s", "-j8", "ref", f"REFERENCE={REFERENCE}"] + (["-B"] if force else []))
     return LIB if os.path.exists(LIB) else None
+
+
+def build_binding(force=False):
+    """oracle/_ref/libmbik_ref_binding.so: the reference's classes with _process_modification replaced by the libmbik.so
+    binding (many_bone_ik_b200/host/godot_module_binding.h).  Needs many_bone_ik_b200/libmbik.so built first."""
+    if source_present():
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-j8", "ref_binding", f"REFERENCE={REFERENCE}"] + (["-B"] if force else []))
+    return BINDING_LIB if os.path.exists(BINDING_LIB) else None
 
 
 def available():
@@ -149,6 +158,30 @@ def swing_twist_y(q):
     out = np.zeros(8, np.float32)
     L.ref_swing_twist_y(_p(q), _p(out))
     return out[:4].copy(), out[4:].copy()
+
+
+_blib = None
+
+
+def binding_solve_batch(rig, targets, start_pose=None, iterations=-1, rebuild_each=False):
+    """The same scene as solve_batch, but every frame is solved by the CUDA path through the module binding.
+    Returns (rc, out_pose [n, n_bones, 10], status [n]); rc = 0 or the first mbik error the binding saw."""
+    global _blib
+    if _blib is None:
+        if not os.path.exists(BINDING_LIB) and build_binding() is None:
+            raise RuntimeError("oracle/_ref/libmbik_ref_binding.so is not built and the reference sources are not present")
+        _blib = C.CDLL(BINDING_LIB)
+        vp = C.c_void_p
+        _blib.ref_binding_solve_batch.argtypes = [C.POINTER(RigDesc), C.c_size_t, vp, vp, vp, vp, C.c_int, C.c_uint]
+    desc, keep = rig_to_desc(rig)
+    targets = np.ascontiguousarray(targets, np.float32)
+    n = targets.shape[0]
+    if start_pose is not None:
+        start_pose = np.ascontiguousarray(start_pose, np.float32)
+    out = np.zeros((n, rig.n_bones, 10), np.float32)
+    st = np.zeros(n, np.uint32)
+    rc = _blib.ref_binding_solve_batch(C.byref(desc), n, _p(targets), _p(start_pose), _p(out), _p(st), int(iterations), 1 if rebuild_each else 0)
+    return int(rc), out, st
 
 
 def run_doctests():

@@ -142,3 +142,24 @@ def test_committed_reference_fixtures_are_current(gold):
         rig = CASES[name]()
         out, loc, st = Rf.solve_batch(rig, gold[name + "_targets"], want_local=True, rebuild_each=True)
         assert _same(loc, gold[name + "_local"]) and _same(out, gold[name + "_out"]) and np.array_equal(st, gold[name + "_status"])
+
+
+needs_binding = pytest.mark.skipif(not (os.path.exists(Rf.BINDING_LIB) or Rf.source_present()),
+                                   reason="oracle/_ref/libmbik_ref_binding.so not built and /root/reference not present")
+
+
+@needs_binding
+def test_module_binding_without_a_gpu_reports_and_leaves_the_pose_untouched():
+    """many_bone_ik_b200/host/godot_module_binding.h compiled against the reference's own classes: with no CUDA device the
+    binding's _process_modification logs MBIK_ERR_NO_DEVICE (there is no CPU fallback) and the skeleton keeps its pose,
+    the behaviour of the reference's ERR_FAIL_* early-outs."""
+    from many_bone_ik_b200 import device_count
+    if device_count() > 0:
+        pytest.skip("a CUDA device is present: the binding solves (covered by tests/test_reference_gpu.py)")
+    rig = rigs.humanoid22()
+    T = rigs.random_targets(rig, 0, 3)
+    start = rig_cases.perturbed_start_pose(rig, 3, seed=5)
+    rc, out, st = Rf.binding_solve_batch(rig, T, start_pose=start)
+    assert rc == -4  # MBIK_ERR_NO_DEVICE (include/mbik.h)
+    untouched, _ = Rf.solve_batch(rig, T, start_pose=start, iterations=0)
+    assert np.array_equal(out, untouched)

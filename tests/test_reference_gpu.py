@@ -93,3 +93,28 @@ def test_cuda_frame_sequence_equals_live_reference():
         orf, lrf, srf = Rf.solve_batch(rig, T, start_pose=start_r, want_local=True, threads=4)
         assert _same(lg, lrf) and _same(og, orf) and np.array_equal(sg, srf), frame
         start_g, start_r = lg, lrf
+
+
+needs_binding = pytest.mark.skipif(not os.path.exists(Rf.BINDING_LIB), reason="prebuilt oracle/_ref/libmbik_ref_binding.so did not travel to this box")
+
+
+@needs_ref
+@needs_binding
+@pytest.mark.parametrize("name", ["humanoid22", "chain64", "quad80", "star_mixed_pins", "two_roots", "humanoid_stabilized", "humanoid_constraint_mode",
+                                  "no_pins", "scaled_bones", "random_rig_7", "random_rig_19"])
+def test_module_binding_drop_in_equals_the_reference(name):
+    """The drop-in claim at the reference's own class boundary.  Two identical headless scenes built from the reference's
+    own classes and configured through its property paths; in one, ManyBoneIK3D::_process_modification is the reference's
+    CPU solver, in the other it is the binding a maintainer would add (many_bone_ik_b200/host/godot_module_binding.h ->
+    mbik_rig_create / mbik_solve_batch, one pose per frame).  The Skeleton3D must receive bit-identical position /
+    rotation / scale for every bone, for a fresh node per pose, a long-lived node over many frames, and perturbed poses."""
+    rig = CASES[name]()
+    n = 6
+    T = rigs.random_targets(rig, 300, n)
+    start = rig_cases.perturbed_start_pose(rig, n, seed=3)
+    for sp in (None, start):
+        for rebuild in (True, False):
+            ref_out, ref_st = Rf.solve_batch(rig, T, start_pose=sp, rebuild_each=rebuild)
+            rc, out, st = Rf.binding_solve_batch(rig, T, start_pose=sp, rebuild_each=rebuild)
+            assert rc == 0
+            assert _same(out, ref_out), (name, rebuild)
