@@ -46,6 +46,20 @@
 #ifndef MBIK_PIPE_CHILD
 #define MBIK_PIPE_CHILD 1
 #endif
+// Large rigs: the local poses of all resident poses (64 bones x 48 B x 75 776 poses = 233 MB) do not fit the 126 MB L2,
+// so the effector walk streams them from HBM (ncu, chain64: 4.1 TB/s, L2 hit rate 12 %, stall_long_sb 50 %;
+// profiles/r1_v7_kernel_chain64_75776.txt).  MBIK_PREFETCH_DIST > 0 issues prefetch.local.L1/.L2 (MBIK_PREFETCH_LEVEL) for
+// the local pose of walk child k + DIST (SASS: CCTLL.PF2).  Measured, 75 776 poses: chain64 69.3 ms without, 69.5 ms
+// (L2, distance 4), 70.5 ms (L1, distance 3); quad80 13.47 / 13.51 / 13.69 ms -- the memory system is already saturated
+// by the demand loads of 16 warps per SM, so the knob stays 0.  Fewer resident poses do not pay either
+// (profiles/run_residency.py: 2 x 128 threads per SM 93 ms, 1 x 128 122 ms): the kernel then runs out of warps to hide
+// the dependent FP32 chains faster than the L2 hit rate recovers.
+#ifndef MBIK_PREFETCH_DIST
+#define MBIK_PREFETCH_DIST 0
+#endif
+#ifndef MBIK_PREFETCH_LEVEL
+#define MBIK_PREFETCH_LEVEL 2
+#endif
 
 namespace mbik {
 
@@ -124,6 +138,27 @@ struct Scratch {
 		}
 		t.o = v3(q[9 * (STRIDE > 0 ? STRIDE : 1)], q[10 * (STRIDE > 0 ? STRIDE : 1)], q[11 * (STRIDE > 0 ? STRIDE : 1)]);
 		return t;
+	}
+	// thread-local arrays only: ask L2 for the 48 bytes of transform i (three 16-byte vectors = three interleaved lines)
+	__device__ __forceinline__ void prefetch_l2(int i) const {
+		if (STRIDE == 0) {
+			const float *q = p + i * 12;
+			asm volatile(
+					"{\n"
+					".reg .u64 la;\n"
+					"cvta.to.local.u64 la, %0;\n"
+#if MBIK_PREFETCH_LEVEL == 1
+					"prefetch.local.L1 [la];\n"
+					"prefetch.local.L1 [la+16];\n"
+					"prefetch.local.L1 [la+32];\n"
+#else
+					"prefetch.local.L2 [la];\n"
+					"prefetch.local.L2 [la+16];\n"
+					"prefetch.local.L2 [la+32];\n"
+#endif
+
+					"}\n" ::"l"(q));
+		}
 	}
 	__device__ __forceinline__ void st(int i, const X34 &t) const {
 		float *q = p + i * 12 * (STRIDE > 0 ? STRIDE : 1);
@@ -854,6 +889,9 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						if (MBIK_PIPE_CHILD && k + 1 < S.fk_cnt) {
 							child = L.ld(fk[S.fk_off + k + 1].child);
 						}
+						if (!SP && MBIK_PREFETCH_DIST > 0 && k + MBIK_PREFETCH_DIST < S.fk_cnt) {
+							L.prefetch_l2(fk[S.fk_off + k + MBIK_PREFETCH_DIST].child);
+						}
 						if (op.push_slot >= 0) {
 							Gstk.st(op.push_slot, run);
 						}
@@ -1113,6 +1151,11 @@ static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 		if (smem > 227 * 1024) {
 			return cudaErrorInvalidValue; // cannot happen: blob <= 64 KiB for these variants (checked at rig creation)
 		}
+	}
+	// tuning knob: pad the dynamic shared memory request to cap how many CTAs of this size share an SM
+	static const int smem_floor = getenv("MBIK_SMEM_FLOOR") ? atoi(getenv("MBIK_SMEM_FLOOR")) : 0;
+	if (smem_floor > 0 && smem < (size_t)smem_floor) {
+		smem = (size_t)smem_floor;
 	}
 	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel<NB, NSEG, NSTK, THREADS, STAB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) {
