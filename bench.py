@@ -432,6 +432,13 @@ def main():
                            "latency_p50_ms_4096": float(np.median(lat_g)), "segment_parallel_warps": Rg.info["sp_roles"],
                            "flops_per_solve": Rg.info["flops_per_solve"],
                            "fp32_roofline_frac": Rg.info["flops_per_solve"] * m / (ms * 1e-3) / 1e12 / float(tf.value) if tf.value else None}
+            try:  # DRAM traffic of this rig's kernel from the committed ncu capture -> fraction of the measured HBM peak
+                tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["other_rigs"][name]
+                gbs = float(tr["dram_bytes"]) / float(tr["poses"]) * m / (ms * 1e-3) / 1e9
+                other[name]["hbm"] = {"traffic_bytes_per_launch": float(tr["dram_bytes"]) / float(tr["poses"]) * m, "achieved_gbs": gbs,
+                                      "frac_of_measured_peak": gbs / hbm_peak, "source": tr["source"]}
+            except Exception:
+                pass
             del Rg, tg, og
         except Exception as e:  # never let the side measurements break the headline line
             other[name] = {"error": str(e)}
