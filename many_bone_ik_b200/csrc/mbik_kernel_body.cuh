@@ -873,6 +873,14 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					if (MBIK_PIPE_CHILD && S.fk_cnt > 0) {
 						child = L.ld(fk[S.fk_off].child);
 					}
+#if MBIK_PIPE_CHILD >= 2
+					// two walk children in flight per thread (the large-rig state streams from HBM: bytes in flight, not
+					// arithmetic, bound the walk there)
+					X34 child2 = x_identity();
+					if (!SP && S.fk_cnt > 1) {
+						child2 = L.ld(fk[S.fk_off + 1].child);
+					}
+#endif
 					for (int k = 0; k < S.fk_cnt; k++) {
 						const BlobFk op = fk[S.fk_off + k];
 						X34 T = x_identity();
@@ -886,6 +894,14 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 							run = Gstk.ld(op.src_slot);
 						}
 						run = x_mul(run, child);
+#if MBIK_PIPE_CHILD >= 2
+						if (!SP) {
+							child = child2;
+							if (k + 2 < S.fk_cnt) {
+								child2 = L.ld(fk[S.fk_off + k + 2].child);
+							}
+						} else
+#endif
 						if (MBIK_PIPE_CHILD && k + 1 < S.fk_cnt) {
 							child = L.ld(fk[S.fk_off + k + 1].child);
 						}
