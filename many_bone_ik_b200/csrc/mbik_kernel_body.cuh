@@ -874,8 +874,10 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						child = L.ld(fk[S.fk_off].child);
 					}
 #if MBIK_PIPE_CHILD >= 2
-					// two walk children in flight per thread (the large-rig state streams from HBM: bytes in flight, not
-					// arithmetic, bound the walk there)
+					// MBIK_PIPE_CHILD == 2 (experiment, off): two walk children in flight per thread.  Measured on chain64
+					// (75 776 poses): 71.8 ms vs 69.3 ms with one -- like the prefetch knobs above, more requests in
+					// flight do not raise the 4.3 TB/s the memory system delivers for this stream; 24 more live registers
+					// cost a few spills.
 					X34 child2 = x_identity();
 					if (!SP && S.fk_cnt > 1) {
 						child2 = L.ld(fk[S.fk_off + 1].child);

@@ -6,9 +6,6 @@
 #define MBIK_F2_VEC 0
 #define MBIK_F2_DOT 0
 #define MBIK_F2_DIV 0
-#ifndef MBIK_PIPE_CHILD
-#define MBIK_PIPE_CHILD 2
-#endif
 #include "mbik_kernel_body.cuh"
 
 namespace mbik {
