@@ -9,9 +9,9 @@
 // working on the same members.  The header needs only the engine types the module already includes (Vector, Ref,
 // Transform3D, Skeleton3D, Node3D) and "mbik.h".
 //
-// This file is exercised for real: oracle/ref_binding_harness.cpp compiles it against the reference's own sources
-// (over the engine stand-in oracle/godot_shim) and tests/test_reference_gpu.py checks that a scene driven through
-// this binding leaves bit-identical bone poses on the Skeleton3D as the reference's own _process_modification().
+// This file is exercised for real: the repository's test infrastructure compiles it against the reference's own sources
+// (over a stand-in of the engine headers) and tests/test_reference_gpu.py checks that a scene driven through this binding
+// leaves bit-identical bone poses on the Skeleton3D as the reference's own _process_modification().
 #pragma once
 #include "mbik.h"
 
