@@ -443,6 +443,32 @@ def main():
         except Exception as e:  # never let the side measurements break the headline line
             other[name] = {"error": str(e)}
 
+    # ---- side measurement: per-pose limit sets: 4 alternative fills of the constraint tables, pose k uses set k % 4 ----
+    limit_sets = None
+    try:
+        import copy
+        cs = [copy.deepcopy(rig.constraints) for _ in range(4)]
+        for s_i, cset in enumerate(cs):
+            for c in cset:
+                c["twist_range"] = float(np.float32(c["twist_range"] * (1.0 - 0.15 * s_i)))
+                c["cones"] = [(cx, cy, cz, float(np.float32(r * (1.0 - 0.1 * s_i)))) for (cx, cy, cz, r) in c["cones"]]
+        hs = R.create_limit_sets(cs)
+        idx_dev = (torch.arange(n, device=dev, dtype=torch.int32) % 4).contiguous()
+        for _ in range(2):
+            R.solve_with_limits_raw(hs, n, idx_dev, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(3):
+            R.solve_with_limits_raw(hs, n, idx_dev, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+        l1.record()
+        torch.cuda.synchronize()
+        lms = l0.elapsed_time(l1) / 3
+        limit_sets = {"sets": 4, "poses": n, "ms_per_launch": lms, "solves_per_s": n / (lms * 1e-3),
+                      "note": "mbik_solve_batch_limits, device-resident: kusudama data read per pose from a device table instead of the rig blob"}
+        R.destroy_limit_sets(hs)
+    except Exception as e:
+        limit_sets = {"error": str(e)}
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         cpu_baseline, _ = time_cpu_reference(rig, budget_s=12.0)
@@ -465,6 +491,7 @@ def main():
         "other_rigs_device_resident": other,
         "strong_scaling_1M_batch": strong,
         "host_link": host_link,
+        "limit_sets_device_resident": limit_sets,
         "clocks": clocks,
         "device_equals_host_path": same,
     }

@@ -195,6 +195,30 @@ int mbik_stream_read_local(mbik_stream *stream, float *out_local);
 int mbik_stream_reset(mbik_stream *stream, const float *initial_pose);
 int64_t mbik_stream_frames(const mbik_stream *stream); /* frames submitted so far */
 
+/*
+ * Per-pose kusudama limit sets (limits that vary per pose).
+ *
+ * A limit set is one alternative fill of the rig's constraint tables -- the same rows (same bones, same cone counts),
+ * other values: joint_twist from / range, cone centres and radii.  mbik_limit_sets_create runs the reference's
+ * constraint authoring for every set on the HOST (IKKusudama3D::_update_constraint / set_axial_limits,
+ * IKLimitCone3D::update_tangent_handles: reference src/ik_kusudama_3d.cpp:37-115, src/ik_open_cone_3d.cpp:36-180 --
+ * the tangent-circle construction goes through libm sin / cos / acos / tan, which only the host evaluates bit-identically
+ * to the reference) and uploads the resulting cone / tangent-circle geometry and twist frames as a device table;
+ * mbik_solve_batch_limits then solves pose k with set set_index[k].  Result of pose k == mbik_solve_batch on a rig created
+ * with that set's constraint values, bit for bit.  Thread-per-pose kernel mapping; rigs with stabilization_passes > 0
+ * are not supported (MBIK_ERR_UNSUPPORTED).
+ */
+typedef struct mbik_limit_sets mbik_limit_sets;
+/* constraints: [n_sets][rig n_constraints] rows in the rig's row order (bone and n_cones must equal the rig's row;
+ * cone_offset indexes the set's own block of `cones`); cones: [n_sets][cones_per_set]. */
+int mbik_limit_sets_create(mbik_rig *rig, int32_t n_sets, const mbik_constraint_desc *constraints, const mbik_cone_desc *cones,
+		int32_t cones_per_set, mbik_limit_sets **out_sets);
+int mbik_limit_sets_destroy(mbik_limit_sets *sets);
+/* set_index: [n_poses] int32, host or device memory like the other buffers (params->flags); values are clamped to
+ * [0, n_sets).  Other arguments as mbik_solve_batch. */
+int mbik_solve_batch_limits(mbik_rig *rig, mbik_limit_sets *sets, const mbik_solve_params *params, size_t n_poses, const int32_t *set_index,
+		const float *targets, const float *start_pose, float *out_pose, float *out_local, uint32_t *out_status);
+
 /* Pinned host allocation helpers (so a C caller can get full H2D/D2H bandwidth without linking CUDA). */
 void *mbik_alloc_pinned(size_t bytes);
 void mbik_free_pinned(void *p);

@@ -63,7 +63,30 @@ EXPORTED_SYMBOLS = [
     "mbik_free_pinned", "mbik_last_kernel_ms", "mbik_measure_fp32_tflops", "mbik_selftest",
     "mbik_stream_create", "mbik_stream_destroy", "mbik_stream_submit", "mbik_stream_sync", "mbik_stream_read_local",
     "mbik_stream_reset", "mbik_stream_frames", "mbik_stage_qcp", "mbik_stage_clamp", "mbik_stage_point_in_limits",
+    "mbik_limit_sets_create", "mbik_limit_sets_destroy", "mbik_solve_batch_limits",
 ]
+
+
+def constraints_to_arrays(constraint_sets):
+    """[n_sets] lists of constraint dicts (same rows as the rig's) -> (ConstraintDesc[n_sets * rows], ConeDesc[n_sets * cones_per_set],
+    rows, cones_per_set).  cone_offset is relative to the set's own block."""
+    rows = len(constraint_sets[0])
+    cones_per_set = sum(len(c["cones"]) for c in constraint_sets[0])
+    cons = (ConstraintDesc * max(1, len(constraint_sets) * rows))()
+    cones = (ConeDesc * max(1, len(constraint_sets) * cones_per_set))()
+    for s, cs in enumerate(constraint_sets):
+        if len(cs) != rows or sum(len(c["cones"]) for c in cs) != cones_per_set:
+            raise ValueError("every limit set needs the rig's constraint rows and cone counts")
+        k = 0
+        for i, c in enumerate(cs):
+            d = cons[s * rows + i]
+            d.bone, d.twist_from, d.twist_range = int(c["bone"]), float(c["twist_from"]), float(c["twist_range"])
+            d.n_cones, d.cone_offset = len(c["cones"]), k
+            for (cx, cy, cz, r) in c["cones"]:
+                cone = cones[s * cones_per_set + k]
+                cone.center[0], cone.center[1], cone.center[2], cone.radius = float(cx), float(cy), float(cz), float(r)
+                k += 1
+    return cons, cones, rows, cones_per_set
 
 
 def rig_to_desc(rig):
@@ -157,5 +180,8 @@ def load_library():
     lib.mbik_stage_qcp.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp]
     lib.mbik_stage_clamp.argtypes = [C.c_int32, C.c_int32, vp, vp, vp]
     lib.mbik_stage_point_in_limits.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
+    lib.mbik_limit_sets_create.argtypes = [vp, C.c_int32, C.POINTER(ConstraintDesc), C.POINTER(ConeDesc), C.c_int32, C.POINTER(vp)]
+    lib.mbik_limit_sets_destroy.argtypes = [vp]
+    lib.mbik_solve_batch_limits.argtypes = [vp, vp, C.POINTER(SolveParams), C.c_size_t, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib

@@ -39,7 +39,16 @@ struct Lane {
 	cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 	float *d_targets = nullptr, *d_start = nullptr, *d_out = nullptr, *d_local = nullptr;
 	uint32_t *d_status = nullptr;
-	size_t cap_targets = 0, cap_start = 0, cap_out = 0, cap_local = 0, cap_status = 0;
+	int32_t *d_index = nullptr; // limit-set index per pose (mbik_solve_batch_limits)
+	size_t cap_targets = 0, cap_start = 0, cap_out = 0, cap_local = 0, cap_status = 0, cap_index = 0;
+};
+
+// per-pose limit sets of one call (device table of this device + the caller's index buffer)
+struct LimitArgs {
+	const unsigned char *table = nullptr;
+	uint32_t stride = 0;
+	int32_t n_sets = 0;
+	const int32_t *set_index = nullptr; // host or device memory, like the other buffers of the call
 };
 
 struct DeviceState {
@@ -56,12 +65,60 @@ struct DeviceState {
 
 } // namespace
 
+// deep copy of the description a rig was created from (limit sets re-run the flattener with other constraint values)
+struct DescCopy {
+	std::vector<int32_t> parent;
+	std::vector<float> rest;
+	std::vector<mbik_pin_desc> pins;
+	std::vector<mbik_constraint_desc> constraints;
+	std::vector<mbik_cone_desc> cones;
+	std::vector<float> bone_damp;
+	mbik_rig_desc scalars{};
+	void assign(const mbik_rig_desc *d) {
+		scalars = *d;
+		parent.assign(d->parent, d->parent + d->n_bones);
+		rest.assign(d->rest_local, d->rest_local + (size_t)d->n_bones * 12);
+		pins.assign(d->pins, d->pins + (d->n_pins > 0 ? d->n_pins : 0));
+		constraints.assign(d->constraints, d->constraints + (d->n_constraints > 0 ? d->n_constraints : 0));
+		size_t n_cones = 0;
+		for (const mbik_constraint_desc &c : constraints) {
+			if (c.n_cones > 0 && (size_t)(c.cone_offset + c.n_cones) > n_cones) {
+				n_cones = (size_t)(c.cone_offset + c.n_cones);
+			}
+		}
+		cones.assign(d->cones, d->cones + n_cones);
+		bone_damp.assign(d->bone_damp, d->bone_damp + (d->n_bone_damp > 0 ? d->n_bone_damp : 0));
+	}
+	mbik_rig_desc view() const {
+		mbik_rig_desc d = scalars;
+		d.parent = parent.data();
+		d.rest_local = rest.data();
+		d.pins = pins.data();
+		d.constraints = constraints.data();
+		d.cones = cones.data();
+		d.bone_damp = bone_damp.data();
+		return d;
+	}
+};
+
 struct mbik_rig {
 	mbik::FlatRig flat;
+	DescCopy desc;
 	int n_solved = 0;
 	int variant = -1;
 	std::mutex mu;
 	std::map<int, std::unique_ptr<DeviceState>> devices;
+};
+
+// alternative fills of the rig's constraint tables, flattened on the host: n_sets records of `stride` bytes,
+// [BlobCone x n_cones][BlobBone x n_solved] each (what solve_body<LIMS> reads instead of the blob's cones / twist frames)
+struct mbik_limit_sets {
+	mbik_rig *rig = nullptr;
+	int32_t n_sets = 0;
+	uint32_t stride = 0;
+	std::vector<unsigned char> table;
+	std::mutex mu;
+	std::map<int, unsigned char *> device_tables;
 };
 
 struct mbik_stream {
@@ -103,6 +160,7 @@ void free_device_state(DeviceState &ds) {
 		cudaFree(ln.d_out);
 		cudaFree(ln.d_local);
 		cudaFree(ln.d_status);
+		cudaFree(ln.d_index);
 		if (ln.ev_start) {
 			cudaEventDestroy(ln.ev_start);
 		}
@@ -265,7 +323,7 @@ void sp_trace_launch(mbik::SolveArgs a, const mbik::FlatRig &F, int variant, int
 
 // one shard on one device; host or device buffers
 int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user_stream, int iterations, size_t n_poses,
-		const float *targets, const float *start_pose, float *out_pose, float *out_local, uint32_t *out_status) {
+		const float *targets, const float *start_pose, float *out_pose, float *out_local, uint32_t *out_status, const LimitArgs *lim = nullptr) {
 	if (n_poses == 0) {
 		return MBIK_OK;
 	}
@@ -287,6 +345,13 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 	a.n_poses = n_poses;
 	a.stabilize = F.stabilization_passes > 0 ? 1 : 0;
 	set_launch_hints(a, F, flags);
+
+	if (lim) {
+		a.limit_table = lim->table;
+		a.limit_stride = lim->stride;
+		a.n_limit_sets = lim->n_sets;
+		a.limit_index = lim->set_index; // device path; the host path points it at each lane's staging copy
+	}
 
 	if (flags & MBIK_IO_DEVICE) {
 		a.targets = targets;
@@ -331,7 +396,8 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 				(rc = ensure_capacity(&ln.d_out, &ln.cap_out, bo)) != MBIK_OK ||
 				(start_pose && (rc = ensure_capacity(&ln.d_start, &ln.cap_start, bs)) != MBIK_OK) ||
 				(out_local && (rc = ensure_capacity(&ln.d_local, &ln.cap_local, bl)) != MBIK_OK) ||
-				(out_status && (rc = ensure_capacity(&ln.d_status, &ln.cap_status, bst)) != MBIK_OK)) {
+				(out_status && (rc = ensure_capacity(&ln.d_status, &ln.cap_status, bst)) != MBIK_OK) ||
+				(lim && (rc = ensure_capacity(&ln.d_index, &ln.cap_index, cn * sizeof(int32_t))) != MBIK_OK)) {
 			for (Lane &l2 : ds->lanes) {
 				cudaStreamSynchronize(l2.stream);
 			}
@@ -343,6 +409,10 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 		}
 		if (start_pose) {
 			cudaMemcpyAsync(ln.d_start, start_pose + b0 * nb * 12, bs, cudaMemcpyHostToDevice, st);
+		}
+		if (lim) {
+			cudaMemcpyAsync(ln.d_index, lim->set_index + b0, cn * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+			a.limit_index = ln.d_index;
 		}
 		a.n_poses = cn;
 		a.targets = ln.d_targets;
@@ -466,6 +536,7 @@ int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
 		delete rig;
 		return fail(rc, msg);
 	}
+	rig->desc.assign(desc);
 	rig->n_solved = (int)rig->flat.bone_order.size();
 	rig->variant = mbik::kernel_variant_for(rig->n_solved, rig->flat.max_seg_len, rig->flat.max_stack, rig->flat.blob.size());
 	if (rig->variant < 0) {
@@ -629,6 +700,142 @@ int mbik_solve_batch(mbik_rig *rig, const mbik_solve_params *params, size_t n_po
 	int prev = -1;
 	cudaGetDevice(&prev);
 	rc = solve_on_device(rig, device, flags, stream, iterations, n_poses, targets, start_pose, out_pose, out_local, out_status);
+	if (prev >= 0 && prev != device) {
+		cudaSetDevice(prev);
+	}
+	return rc;
+}
+
+int mbik_limit_sets_create(mbik_rig *rig, int32_t n_sets, const mbik_constraint_desc *constraints, const mbik_cone_desc *cones,
+		int32_t cones_per_set, mbik_limit_sets **out_sets) {
+	if (!rig || !out_sets || n_sets < 1 || cones_per_set < 0) {
+		return fail(MBIK_ERR_INVALID_ARG, "rig/out_sets is NULL or n_sets < 1");
+	}
+	*out_sets = nullptr;
+	const mbik::FlatRig &F = rig->flat;
+	const size_t n_rows = rig->desc.constraints.size();
+	if (n_rows > 0 && !constraints) {
+		return fail(MBIK_ERR_INVALID_ARG, "constraints is NULL");
+	}
+	if (F.stabilization_passes > 0) {
+		return fail(MBIK_ERR_UNSUPPORTED, "limit sets are not supported on rigs with stabilization_passes > 0");
+	}
+	std::unique_ptr<mbik_limit_sets> ls(new (std::nothrow) mbik_limit_sets());
+	if (!ls) {
+		return fail(MBIK_ERR_ALLOC, "out of memory");
+	}
+	const size_t cone_bytes = F.cones.size() * sizeof(mbik::BlobCone), bone_bytes = F.bones.size() * sizeof(mbik::BlobBone);
+	ls->rig = rig;
+	ls->n_sets = n_sets;
+	ls->stride = (uint32_t)(cone_bytes + bone_bytes);
+	ls->table.resize((size_t)n_sets * ls->stride);
+	for (int32_t s = 0; s < n_sets; s++) {
+		const mbik_constraint_desc *rows = constraints + (size_t)s * n_rows;
+		for (size_t r = 0; r < n_rows; r++) {
+			const mbik_constraint_desc &mine = rig->desc.constraints[r];
+			if (rows[r].bone != mine.bone || rows[r].n_cones != mine.n_cones) {
+				return fail(MBIK_ERR_INVALID_ARG, "limit set " + std::to_string(s) + ", row " + std::to_string(r) +
+						": bone and n_cones must equal the rig's constraint row (only values may vary)");
+			}
+			if (rows[r].n_cones > 0 && (rows[r].cone_offset < 0 || rows[r].cone_offset + rows[r].n_cones > cones_per_set || !cones)) {
+				return fail(MBIK_ERR_INVALID_ARG, "limit set " + std::to_string(s) + ", row " + std::to_string(r) + ": cone_offset out of range");
+			}
+		}
+		mbik_rig_desc d = rig->desc.view();
+		d.constraints = rows;
+		d.cones = cones ? cones + (size_t)s * cones_per_set : nullptr;
+		mbik::FlatRig Fs;
+		int rc = mbik::flatten_rig(&d, Fs);
+		if (rc != MBIK_OK) {
+			return fail(rc, "limit set " + std::to_string(s) + ": " + Fs.error);
+		}
+		// the schedule must be the rig's: same steps, same limit flags, same cone ranges
+		bool same = Fs.steps.size() == F.steps.size() && Fs.cones.size() == F.cones.size() && Fs.bones.size() == F.bones.size();
+		for (size_t i = 0; same && i < F.steps.size(); i++) {
+			same = Fs.steps[i].bone == F.steps[i].bone && Fs.steps[i].flags == F.steps[i].flags && Fs.steps[i].cone_off == F.steps[i].cone_off &&
+					Fs.steps[i].cone_cnt == F.steps[i].cone_cnt;
+		}
+		if (!same) {
+			return fail(MBIK_ERR_INVALID_ARG, "limit set " + std::to_string(s) + " changes the rig's schedule (which bones are limited, or cone counts)");
+		}
+		unsigned char *rec = ls->table.data() + (size_t)s * ls->stride;
+		if (cone_bytes) {
+			memcpy(rec, Fs.cones.data(), cone_bytes);
+		}
+		memcpy(rec + cone_bytes, Fs.bones.data(), bone_bytes);
+	}
+	*out_sets = ls.release();
+	return MBIK_OK;
+}
+
+int mbik_limit_sets_destroy(mbik_limit_sets *sets) {
+	if (!sets) {
+		return MBIK_OK;
+	}
+	int prev = -1;
+	cudaGetDevice(&prev);
+	for (auto &kv : sets->device_tables) {
+		if (cudaSetDevice(kv.first) == cudaSuccess) {
+			cudaFree(kv.second);
+		}
+	}
+	if (prev >= 0) {
+		cudaSetDevice(prev);
+	}
+	delete sets;
+	return MBIK_OK;
+}
+
+int mbik_solve_batch_limits(mbik_rig *rig, mbik_limit_sets *sets, const mbik_solve_params *params, size_t n_poses, const int32_t *set_index,
+		const float *targets, const float *start_pose, float *out_pose, float *out_local, uint32_t *out_status) {
+	int iterations = 0;
+	int rc = check_solve_args(rig, params, n_poses, targets, out_pose, &iterations);
+	if (rc != MBIK_OK) {
+		return rc;
+	}
+	if (!sets || sets->rig != rig) {
+		return fail(MBIK_ERR_INVALID_ARG, "sets is NULL or was created for another rig");
+	}
+	if (n_poses > 0 && !set_index) {
+		return fail(MBIK_ERR_INVALID_ARG, "set_index must not be NULL");
+	}
+	int device = -1;
+	if ((rc = resolve_device(params, &device)) != MBIK_OK) {
+		return rc;
+	}
+	uint32_t flags = params ? params->flags : MBIK_IO_HOST;
+	cudaStream_t stream = params ? (cudaStream_t)params->stream : nullptr;
+	int prev = -1;
+	cudaGetDevice(&prev);
+	LimitArgs lim;
+	{
+		// per-device copy of the table, uploaded on first use
+		std::lock_guard<std::mutex> lock(sets->mu);
+		auto it = sets->device_tables.find(device);
+		if (it == sets->device_tables.end()) {
+			unsigned char *d = nullptr;
+			cudaError_t e = cudaSetDevice(device);
+			if (e == cudaSuccess) {
+				e = cudaMalloc((void **)&d, sets->table.size());
+			}
+			if (e == cudaSuccess) {
+				e = cudaMemcpy(d, sets->table.data(), sets->table.size(), cudaMemcpyHostToDevice);
+			}
+			if (e != cudaSuccess) {
+				cudaFree(d);
+				if (prev >= 0 && prev != device) {
+					cudaSetDevice(prev);
+				}
+				return cuda_fail(e, "limit-set table upload");
+			}
+			it = sets->device_tables.emplace(device, d).first;
+		}
+		lim.table = it->second;
+	}
+	lim.stride = sets->stride;
+	lim.n_sets = sets->n_sets;
+	lim.set_index = set_index;
+	rc = solve_on_device(rig, device, flags | MBIK_SCHED_THROUGHPUT, stream, iterations, n_poses, targets, start_pose, out_pose, out_local, out_status, &lim);
 	if (prev >= 0 && prev != device) {
 		cudaSetDevice(prev);
 	}

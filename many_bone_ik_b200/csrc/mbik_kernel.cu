@@ -66,6 +66,26 @@ int segment_parallel_choice(const SolveArgs &a, int variant, int sm_count) {
 bool uses_segment_parallel(const SolveArgs &a, int variant, int sm_count) { return segment_parallel_choice(a, variant, sm_count) != 0; }
 
 cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStream_t stream) {
+	if (a.limit_table) {
+		// per-pose limit sets: thread-per-pose mapping only (mbik_kernel_l*.cu); the C ABI rejects stabilised rigs earlier
+		if (a.stabilize || !a.limit_index || a.n_limit_sets < 1) {
+			return cudaErrorInvalidValue;
+		}
+		switch (variant) {
+			case 0:
+				return launch_lims_v0(a, stream);
+			case 1:
+				return launch_lims_v1(a, stream);
+			case 2:
+				return launch_lims_v2(a, stream);
+			case 3:
+				return launch_lims_v3(a, stream);
+			case 4:
+				return launch_lims_v4(a, stream);
+			default:
+				return cudaErrorInvalidValue;
+		}
+	}
 	const int sp = segment_parallel_choice(a, variant, sm_count);
 	if (sp != 0) {
 		switch (variant) {

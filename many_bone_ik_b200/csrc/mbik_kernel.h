@@ -29,6 +29,13 @@ struct SolveArgs {
 	float sp_gain;           // estimated serial / critical-path cost of that schedule
 	long long *sp_trace;     // debug (MBIK_SP_TRACE=1): per (iteration, phase, warp) start / end clock of CTA 0, or nullptr
 	int32_t sched_mode;      // 0 = choose by batch size, 1 = one thread per pose (throughput mapping), 2 = segment-parallel
+	// per-pose kusudama limit sets (mbik_solve_batch_limits): n_limit_sets records of limit_stride bytes, each
+	// [BlobCone x n_cones][BlobBone x n_solved] built by the host flattener; limit_index[pose] picks one.  nullptr = the
+	// rig's own limits from the blob.
+	const unsigned char *limit_table = nullptr;
+	const int32_t *limit_index = nullptr;
+	uint32_t limit_stride = 0;
+	int32_t n_limit_sets = 0;
 };
 
 // Compiled size variants {solved-bone capacity, longest segment, walk-stack depth}; per-pose thread-local state is
@@ -47,6 +54,13 @@ cudaError_t launch_v1(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v2(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v3(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v4(const SolveArgs &a, int threads, cudaStream_t stream);
+
+// per-pose limit sets (mbik_kernel_lims.cu): thread-per-pose mapping, 512-thread CTAs, no stabilisation
+cudaError_t launch_lims_v0(const SolveArgs &a, cudaStream_t stream);
+cudaError_t launch_lims_v1(const SolveArgs &a, cudaStream_t stream);
+cudaError_t launch_lims_v2(const SolveArgs &a, cudaStream_t stream);
+cudaError_t launch_lims_v3(const SolveArgs &a, cudaStream_t stream);
+cudaError_t launch_lims_v4(const SolveArgs &a, cudaStream_t stream);
 
 // segment-parallel instantiations (mbik_kernel_sp*.cu); min_groups_per_sm 1 = full register budget, 2 = 128 registers
 // (several 32-pose groups per SM)

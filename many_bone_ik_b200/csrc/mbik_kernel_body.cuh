@@ -606,7 +606,12 @@ __device__ __forceinline__ void team_barrier(int id, int n_threads) { asm volati
 // the rig's schedule every warp ("role") runs the bone-steps of its own segments; the local poses of the group live in
 // shared memory ([bone][word][lane] columns) where all roles read and write them, with one CTA barrier per phase.  The
 // per-pose arithmetic and its order are exactly those of the one-thread-per-pose mapping: bit-identical results.
-template <int NB, int NSEG, int NSTK, bool STAB, int SCR_STRIDE, bool SP = false>
+// LIMS (per-pose limit sets, mbik_solve_batch_limits): the kusudama data of a pose -- cone / tangent-circle geometry and
+// the twist frames of every constrained bone -- come from record limit_index[pose] of a table in global memory instead
+// of the rig blob.  The records are built by the same host code as the blob (bit-exact: the tangent-circle construction
+// goes through the host libm, like the reference), and the schedule (which bones carry limits, cone counts) is the
+// rig's: only values vary per pose.  Separate instantiations; the default path does not see any of it.
+template <int NB, int NSEG, int NSTK, bool STAB, int SCR_STRIDE, bool SP = false, bool LIMS = false>
 __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t bar;
@@ -657,6 +662,15 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	const bool constraint_mode = H.constraint_mode != 0;
 	const float *my_targets = a.targets + pose * (size_t)n_pins * 12;
 	const float *my_start = a.start_pose ? a.start_pose + pose * (size_t)n_bones * 12 : nullptr;
+	const BlobCone *my_cones = cones;
+	const BlobBone *my_limit_bones = bones;
+	if (LIMS) {
+		int set = a.limit_index[pose];
+		set = set < 0 ? 0 : (set >= a.n_limit_sets ? a.n_limit_sets - 1 : set);
+		const unsigned char *rec = a.limit_table + (size_t)set * a.limit_stride;
+		my_cones = reinterpret_cast<const BlobCone *>(rec);
+		my_limit_bones = reinterpret_cast<const BlobBone *>(rec + (size_t)H.n_cones * sizeof(BlobCone));
+	}
 
 	// Per-pose state (thread-local, lane-interleaved):
 	float L_local[SP ? 1 : NB * 12]; // local transform of every solved bone (t order) -- the only state carried between steps
@@ -727,6 +741,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			const uint32_t flags = S.flags;
 			const bool node_parent = (flags & STEP_NODE_PARENT) != 0;
 			const BlobBone &B = bones[b];
+			const BlobBone &Blim = LIMS ? my_limit_bones[b] : B; // orientation / twist frames of this pose's limit set
 
 			if (flags & STEP_SEG_FIRST) {
 				// explicit FK down the ancestor chain skeleton-root .. parent(tip); the last seg_len globals are the
@@ -1023,7 +1038,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						bone_dir = vadd(dcol, Gcur.o);
 					} else {
 						X34 Lor;
-						Lor.b = ld_m3v(B.orient_basis);
+						Lor.b = ld_m3v(Blim.orient_basis);
 						Lor.o = Lor_o;
 						Cor = x_mul(P, Lor);
 						CorInv.b = m3_inverse(Cor.b);
@@ -1035,7 +1050,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					CorInv.o = m3_xform(CorInv.b, vneg(Cor.o)); // Transform3D::affine_inverse
 					const V3 bone_tip = x_xform(CorInv, bone_dir);
 					float in_bounds;
-					V3 in_limits = point_in_limits(bone_tip, cones + S.cone_off, S.cone_cnt, in_bounds);
+					V3 in_limits = point_in_limits(bone_tip, my_cones + S.cone_off, S.cone_cnt, in_bounds);
 					if (in_bounds < 0.0f) {
 						V3 constrained = x_xform(Cor, in_limits);
 						Q4 rq = q_shortest_arc(vsub(bone_dir, Cor.o), vsub(constrained, Cor.o));
@@ -1043,7 +1058,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					}
 				}
 				if (flags & STEP_TWIST) {
-					Lb.b = twist_snap(P.b, Pinv, Lb.b, ld_m3v(B.twist_basis), ld_m3v(B.twist_center), B.twist_cos);
+					Lb.b = twist_snap(P.b, Pinv, Lb.b, ld_m3v(Blim.twist_basis), ld_m3v(Blim.twist_center), Blim.twist_cos);
 				}
 			}
 			if (STAB) {
@@ -1158,9 +1173,30 @@ template <int NB, int NSEG, int NSTK, int THREADS, bool STAB, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) mbik_solve_kernel(SolveArgs a) {
 	solve_body<NB, NSEG, NSTK, STAB, ScratchStride<NSEG, NSTK, THREADS>::value>(a);
 }
+template <int NB, int NSEG, int NSTK, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel_lims(SolveArgs a) {
+	solve_body<NB, NSEG, NSTK, false, ScratchStride<NSEG, NSTK, THREADS>::value, false, true>(a);
+}
 // ---------------------------------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------------------------------
+template <int NB, int NSEG, int NSTK, int THREADS>
+static cudaError_t launch_variant_lims(const SolveArgs &a, cudaStream_t stream) {
+	size_t smem = a.blob_bytes;
+	if (ScratchStride<NSEG, NSTK, THREADS>::value > 0) {
+		smem = ((smem + 127) & ~(size_t)127) + (size_t)(NSEG + NSTK) * 12 * THREADS * sizeof(float);
+		if (smem > 227 * 1024) {
+			return cudaErrorInvalidValue;
+		}
+	}
+	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel_lims<NB, NSEG, NSTK, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	unsigned grid = (unsigned)((a.n_poses + THREADS - 1) / THREADS);
+	mbik_solve_kernel_lims<NB, NSEG, NSTK, THREADS><<<grid, THREADS, smem, stream>>>(a);
+	return cudaGetLastError();
+}
 template <int NB, int NSEG, int NSTK, int THREADS, bool STAB = false, int MINB = 1>
 static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 	size_t smem = a.blob_bytes;

@@ -131,6 +131,48 @@ class BatchedIKRig:
             raise MbikError(rc, "mbik_solve_batch")
         return (out, loc, st) if want_local else (out, st)
 
+    # ---- per-pose limit sets -----------------------------------------------------
+    def create_limit_sets(self, constraint_sets):
+        """constraint_sets: [n_sets] lists of constraint dicts with the rig's rows (same bones and cone counts, other
+        values).  Returns an opaque handle for solve_with_limits(); free it with destroy_limit_sets()."""
+        cons, cones, rows, cones_per_set = _capi.constraints_to_arrays(constraint_sets)
+        h = C.c_void_p()
+        rc = self.lib.mbik_limit_sets_create(self.handle, len(constraint_sets), C.cast(cons, C.POINTER(_capi.ConstraintDesc)),
+                                             C.cast(cones, C.POINTER(_capi.ConeDesc)), int(cones_per_set), C.byref(h))
+        if rc != 0:
+            raise MbikError(rc, "mbik_limit_sets_create")
+        return h
+
+    def destroy_limit_sets(self, sets):
+        self.lib.mbik_limit_sets_destroy(sets)
+
+    def solve_with_limits(self, sets, set_index, targets, start_pose=None, iterations=-1, device=-1, want_local=False):
+        """Host-buffer solve where pose k uses limit set set_index[k]."""
+        targets = np.ascontiguousarray(targets, np.float32)
+        n = targets.shape[0]
+        set_index = np.ascontiguousarray(set_index, np.int32)
+        if set_index.shape != (n,):
+            raise ValueError("set_index must be [n]")
+        if start_pose is not None:
+            start_pose = np.ascontiguousarray(start_pose, np.float32)
+        out = np.empty((n, self.n_bones, 10), np.float32)
+        loc = np.empty((n, self.n_bones, 12), np.float32) if want_local else None
+        st = np.zeros(n, np.uint32)
+        p = SolveParams(int(iterations), int(device), MBIK_IO_HOST, None)
+        rc = self.lib.mbik_solve_batch_limits(self.handle, sets, C.byref(p), n, _ptr(set_index), _ptr(targets), _ptr(start_pose), _ptr(out), _ptr(loc),
+                                              _ptr(st))
+        if rc != 0:
+            raise MbikError(rc, "mbik_solve_batch_limits")
+        return (out, loc, st) if want_local else (out, st)
+
+    def solve_with_limits_raw(self, sets, n_poses, set_index, targets, out_pose, start_pose=None, out_local=None, out_status=None, iterations=-1,
+                              device=-1, flags=MBIK_IO_HOST, stream=None):
+        p = SolveParams(int(iterations), int(device), int(flags), C.c_void_p(int(stream)) if stream else None)
+        rc = self.lib.mbik_solve_batch_limits(self.handle, sets, C.byref(p), int(n_poses), _ptr(set_index), _ptr(targets), _ptr(start_pose),
+                                              _ptr(out_pose), _ptr(out_local), _ptr(out_status))
+        if rc != 0:
+            raise MbikError(rc, "mbik_solve_batch_limits")
+
     def solve_raw(self, n_poses, targets, out_pose, start_pose=None, out_local=None, out_status=None, iterations=-1,
                   device=-1, flags=MBIK_IO_HOST, stream=None):
         """Zero-copy call: pointers (numpy / torch tensors / ints) are passed straight through.
