@@ -225,6 +225,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # multi-GPU boxes: keep this rank's threads and pinned buffers on the NUMA node its GPU hangs off (what
+    # `numactl --cpunodebind --membind` does); a no-op where the platform exposes no topology (single-node VMs)
+    numa_binding = None
+    if world > 1:
+        try:
+            from many_bone_ik_b200 import numa
+            numa_binding = numa.bind_to_gpu_node(local_rank)
+        except Exception as e:
+            numa_binding = {"error": str(e)}
+
     rig = rigs.humanoid22()
     R = BatchedIKRig(rig)
     total = args.poses * world
@@ -491,6 +501,7 @@ def main():
         "other_rigs_device_resident": other,
         "strong_scaling_1M_batch": strong,
         "host_link": host_link,
+        "numa_binding_rank0": numa_binding,
         "limit_sets_device_resident": limit_sets,
         "clocks": clocks,
         "device_equals_host_path": same,

@@ -37,17 +37,21 @@ def _parse_list(text):
 
 
 def gpu_pci_bus_id(device):
-    import torch
+    """'dddd:bb:dd.0' of CUDA device `device`, or None (no CUDA device, or the runtime does not say)."""
     try:
+        import torch
+        if not torch.cuda.is_available() or device >= torch.cuda.device_count():
+            return None
         p = torch.cuda.get_device_properties(device)
         if hasattr(p, "pci_bus_id") and hasattr(p, "pci_device_id"):
             return "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
     except Exception:
-        pass
+        return None
     try:
-        from cuda import cudart  # cuda-python
-        err, s = cudart.cudaDeviceGetPCIBusId(32, device)
-        return s.decode().strip("\x00").lower()
+        import subprocess
+        r = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)], capture_output=True, text=True, timeout=10)
+        bdf = r.stdout.strip().lower()
+        return bdf[-12:] if len(bdf) >= 12 else None  # nvidia-smi prints an 8-digit domain
     except Exception:
         return None
 

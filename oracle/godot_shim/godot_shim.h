@@ -8,8 +8,8 @@
 //   * core/math   -> oracle/godot_math.h (the same restatement of Vector3/Basis/Quaternion/Transform3D
 //                    the oracle uses; the engine arithmetic therefore stays "restated", the module's
 //                    logic becomes "the real thing");
-//   * containers  -> Vector<T> (value semantics of the engine's copy-on-write vector), List<T>,
-//                    HashMap-free; String/StringName/NodePath over std::string;
+//   * containers  -> Vector<T> (copy-on-write like the engine's), List<T>, HashMap / RBSet over std::map;
+//                    String / StringName / NodePath over std::string;
 //   * object model-> Object/RefCounted/Ref<T>/WeakRef/Variant/ClassDB: reference counting and
 //                    dynamic casts behave like the engine's; method binding, signals, property
 //                    lists and editor hooks are inert;
@@ -56,7 +56,6 @@ using gd::real_t;
 #define _ALWAYS_INLINE_ inline
 #define likely(x) (x)
 #define unlikely(x) (x)
-#define TOOLS_ENABLED_SHIM_OFF 1
 
 namespace gd {
 namespace Math {

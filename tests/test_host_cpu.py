@@ -300,3 +300,15 @@ def test_bench_reference_arm_contract():
     if line["cpu_baseline"]["kind"] == "reference":
         assert line["cpu_baseline"]["port"]["kind"] == "port" and line["cpu_baseline"]["port"]["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_numa_helpers_degrade_to_a_no_op():
+    """many_bone_ik_b200/numa.py (bench / multi-GPU host glue): list parsing, and binding to the NUMA node of a GPU that
+    does not exist or exposes no topology must be a reported no-op, never an exception."""
+    from many_bone_ik_b200 import numa
+    assert numa._parse_list("0-3,8,10-11") == [0, 1, 2, 3, 8, 10, 11] and numa._parse_list("") == [] and numa._parse_list(None) == []
+    before = os.sched_getaffinity(0)
+    done = numa.bind_to_gpu_node(0)
+    assert "node" in done and ("skipped" in done or done["node"] is not None)
+    if "skipped" in done:
+        assert os.sched_getaffinity(0) == before
