@@ -1186,6 +1186,29 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	}
 	hdr.total_bytes = (uint32_t)R.blob.size();
 	memcpy(R.blob.data(), &hdr, sizeof(hdr));
+	if (getenv("MBIK_DEBUG_WALK_READS")) {
+		// analysis aid: how often each solved bone's local pose is read by the effector walks of one iteration
+		std::vector<double> reads(R.bones.size(), 0.0);
+		double total = 0;
+		for (const BlobStep &st : R.steps) {
+			const double passes = (st.flags & STEP_TRANSLATE) ? 2.0 : 1.0;
+			for (int k = 0; k < st.fk_cnt; k++) {
+				reads[(size_t)R.fk[(size_t)st.fk_off + k].child] += passes;
+				total += passes;
+			}
+		}
+		std::vector<double> sorted = reads;
+		std::sort(sorted.begin(), sorted.end(), [](double a, double b) { return a > b; });
+		fprintf(stderr, "[mbik] walk reads per iteration: %.0f over %zu solved bones; share of the hottest 4 / 7 / 10 / 14 bones:", total, reads.size());
+		for (int m : { 4, 7, 10, 14 }) {
+			double acc = 0;
+			for (int i = 0; i < m && i < (int)sorted.size(); i++) {
+				acc += sorted[(size_t)i];
+			}
+			fprintf(stderr, " %.1f%%", total > 0 ? 100.0 * acc / total : 0.0);
+		}
+		fprintf(stderr, "\n");
+	}
 	return MBIK_OK;
 }
 
