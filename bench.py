@@ -374,6 +374,28 @@ def main():
     p50 = _p50(0)
     p50_thread_per_pose = _p50(MBIK_SCHED_THROUGHPUT)
 
+    # small batches, for scale (BASELINE configs[0] is ONE pose on the CPU: 0.41 ms in the reference): p50 of a device-resident
+    # call with 1 and 32 poses (one 32-pose group either way), and of a HOST-buffer call with 4096 poses (copies included)
+    def _p50_n(n_small, host=False):
+        lat = []
+        th, oh = t_host[:n_small].contiguous().pin_memory(), torch.empty((n_small, nb, 10), dtype=torch.float32).pin_memory()
+        for i in range(120):
+            if host:
+                t0_ = time.perf_counter()
+                R.solve_raw(n_small, th.numpy(), oh.numpy(), device=local_rank, flags=MBIK_IO_HOST)
+                dt_ = (time.perf_counter() - t0_) * 1e3
+            else:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                R.solve_raw(n_small, lt, lo_, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+                b.record()
+                torch.cuda.synchronize()
+                dt_ = a.elapsed_time(b)
+            if i >= 20:
+                lat.append(dt_)
+        return float(np.median(lat))
+    small = {"p50_ms_1_pose_device": _p50_n(1), "p50_ms_32_poses_device": _p50_n(32), "p50_ms_4096_poses_host_buffers": _p50_n(LATENCY_BATCH, host=True)}
+
     # ---- roofline of the one kernel (FP32 CUDA cores; HBM shown as the sanity figure) ----
     import ctypes as C
     peaks = {}
@@ -495,6 +517,7 @@ def main():
         "gpu_launches": args.steps * world,
         "latency_p50_ms_4096": p50,
         "latency_p50_ms_4096_thread_per_pose_mapping": p50_thread_per_pose,
+        "latency_small_batches": small,
         "latency_mapping": "segment-parallel: 32 poses per CTA, %d warps (one per concurrently solvable segment), %d phases per iteration" % (R.info["sp_roles"], R.info["sp_phases"]),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
