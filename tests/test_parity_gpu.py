@@ -280,6 +280,28 @@ def test_large_batch_properties_at_bench_size():
     assert not st.any()
 
 
+@pytest.mark.parametrize("name", ["chain64", "quad80"])
+def test_large_rig_properties_at_baseline_batch(name):
+    """BASELINE configs 4 / 5 at their full 65536-pose batch: a strided sample equals the oracle, a permuted
+    sub-batch gives the permuted result, statuses are all 0, and the 4096-pose batch of the same configs (which the
+    library may run in the segment-parallel mapping) is the bitwise prefix of the big one."""
+    rig = rigs.RIGS[name]()
+    R = BatchedIKRig(rig)
+    n = 1 << 16
+    T = rigs.random_targets(rig, 0, n)
+    out, st = R.solve(T)
+    idx = np.arange(0, n, 2731)
+    ref_out, ref_st = O.solve_batch(rig, T[idx], threads=8)
+    assert np.array_equal(out[idx], ref_out, equal_nan=True)
+    assert np.array_equal(st[idx], ref_st)
+    perm = np.random.default_rng(5).permutation(n)[: 1 << 14]
+    out_p, _ = R.solve(T[perm])
+    assert np.array_equal(out_p, out[perm], equal_nan=True)
+    out_s, _ = R.solve(T[:4096])
+    assert np.array_equal(out_s, out[:4096], equal_nan=True)
+    assert not st.any()
+
+
 def test_guarded_sqrt_div_groups_are_correctly_rounded():
     """The kernel's grouped sqrt/division sequences (mbik_math.cuh) == __fsqrt_rn/__fdiv_rn bit for bit: sqrt
     exhaustively over [2^-80, 2^80), division over all 2^23 divisor mantissas x 4 rounds x 64 numerators,
