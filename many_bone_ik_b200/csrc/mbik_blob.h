@@ -5,6 +5,9 @@
 //   BlobHeader | BlobStep[n_steps] | BlobBone[n_solved] | BlobEff[n_effs] | BlobFk[n_fk] |
 //   BlobCone[n_cones] | BlobPass[n_pass] | chain[n_chain] (int16) | rest_local[n_bones*12] | BlobSpan[sp_phases*sp_slots*sp_roles] |
 //   step_path[n_steps] (int32) | BlobPathRef[] | paths[] (int16)
+// Tail layout (large rigs, BlobHeader::resident_bytes < total_bytes): the walk list BlobFk[] -- quadratic in the depth of a
+// chain -- moves behind paths[] and is read from global memory by the {256, 256, 32} kernel variant; the segment-parallel
+// tables before it are not staged either (that variant has no segment-parallel build).
 // Solved bones are renumbered in depth-first preorder ("t index": parents before children, children in
 // the reference's ascending order), which is also the order in which a segment's effector list
 // enumerates its effectors.
@@ -28,6 +31,9 @@ enum : uint32_t {
 	                           // |entries| <= 2: enables the finite-operand shortcuts of the swing snap (mbik_kernel_body.cuh)
 };
 
+// shared-memory budget of the staged rig constants (the rest of the 227 KiB is scratch / alignment)
+constexpr uint32_t kResidentBlobBudget = 200u * 1024u;
+
 struct BlobHeader {
 	uint32_t magic;       // 'MBIK'
 	uint32_t total_bytes; // multiple of 16
@@ -39,7 +45,8 @@ struct BlobHeader {
 	int32_t sp_roles, sp_phases, sp_slots;
 	int32_t sp_team_bufs;     // heading buffers a group needs (teams that can be active in one phase, 0..kMaxSpTeams)
 	int32_t sp_team_headings; // headings per buffer (largest heading list of any team step)
-	int32_t reserved0;
+	uint32_t resident_bytes; // bytes the kernel stages into shared memory: total_bytes, or -- "tail layout", rigs whose constants exceed
+	                         // the shared-memory budget -- the offset of the tail (segment-parallel tables, walk list) that stays in global memory
 	uint32_t off_steps, off_bones, off_effs, off_fk, off_cones, off_pass, off_rest, off_chain, off_sched;
 	uint32_t off_step_path, off_path_refs, off_paths; // BlobPathRef tables of the team steps (see BlobSpan)
 };

@@ -340,7 +340,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 	const size_t nb = (size_t)F.n_bones, np = F.pins.size();
 	mbik::SolveArgs a;
 	a.blob = ds->blob;
-	a.blob_bytes = (uint32_t)F.blob.size();
+	a.blob_bytes = reinterpret_cast<const mbik::BlobHeader *>(F.blob.data())->resident_bytes; // what the kernel stages into shared memory
 	a.iterations = iterations;
 	a.n_poses = n_poses;
 	a.stabilize = F.stabilization_passes > 0 ? 1 : 0;
@@ -541,7 +541,7 @@ int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
 	rig->variant = mbik::kernel_variant_for(rig->n_solved, rig->flat.max_seg_len, rig->flat.max_stack, rig->flat.blob.size());
 	if (rig->variant < 0) {
 		delete rig;
-		return fail(MBIK_ERR_UNSUPPORTED, "rig exceeds the largest kernel variant (128 solved bones, walk stack depth 16)");
+		return fail(MBIK_ERR_UNSUPPORTED, "rig exceeds the largest kernel variant (256 solved bones, walk stack depth 32)");
 	}
 	{
 		std::string verr;
@@ -558,9 +558,9 @@ int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
 			}
 		}
 	}
-	if (rig->flat.blob.size() > 200 * 1024) {
+	if (reinterpret_cast<const mbik::BlobHeader *>(rig->flat.blob.data())->resident_bytes > mbik::kResidentBlobBudget) {
 		delete rig;
-		return fail(MBIK_ERR_UNSUPPORTED, "rig constants exceed the shared-memory budget (200 KiB)");
+		return fail(MBIK_ERR_UNSUPPORTED, "rig constants exceed the shared-memory budget (200 KiB without the walk list)");
 	}
 	*out_rig = rig;
 	return MBIK_OK;
@@ -1071,7 +1071,7 @@ int mbik_stream_submit(mbik_stream *st, const float *targets, float *out_pose, u
 	cudaStreamWaitEvent(st->s_solve, st->ev_up[slot], 0);
 	mbik::SolveArgs a;
 	a.blob = st->blob;
-	a.blob_bytes = (uint32_t)F.blob.size();
+	a.blob_bytes = reinterpret_cast<const mbik::BlobHeader *>(F.blob.data())->resident_bytes; // what the kernel stages into shared memory
 	a.iterations = iterations >= 0 ? iterations : F.iterations;
 	{
 		bool has_pins = false; // same early-out as mbik_solve_batch (reference src/many_bone_ik_3d.cpp:649-651, :671-680)

@@ -1165,24 +1165,40 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	hdr.sp_slots = R.sp_slots;
 	hdr.sp_team_bufs = R.sp_team_bufs;
 	hdr.sp_team_headings = R.sp_team_headings;
-	R.blob.clear();
-	R.blob.resize(sizeof(BlobHeader), 0);
-	hdr.off_steps = append_section(R.blob, R.steps);
-	hdr.off_bones = append_section(R.blob, R.bones);
-	hdr.off_effs = append_section(R.blob, R.effs);
-	hdr.off_fk = append_section(R.blob, R.fk);
-	hdr.off_cones = append_section(R.blob, R.cones);
-	hdr.off_pass = append_section(R.blob, R.pass);
-	hdr.off_chain = append_section(R.blob, R.chain);
 	std::vector<float> rest(nb * 12);
 	memcpy(rest.data(), d->rest_local, sizeof(float) * 12 * nb);
-	hdr.off_rest = append_section(R.blob, rest);
-	hdr.off_sched = append_section(R.blob, R.sched);
-	hdr.off_step_path = append_section(R.blob, R.step_path);
-	hdr.off_path_refs = append_section(R.blob, R.path_refs);
-	hdr.off_paths = append_section(R.blob, R.paths);
-	while (R.blob.size() % 16) {
-		R.blob.push_back(0);
+	auto assemble = [&](bool tail_layout) {
+		R.blob.clear();
+		R.blob.resize(sizeof(BlobHeader), 0);
+		hdr.off_steps = append_section(R.blob, R.steps);
+		hdr.off_bones = append_section(R.blob, R.bones);
+		hdr.off_effs = append_section(R.blob, R.effs);
+		if (!tail_layout) {
+			hdr.off_fk = append_section(R.blob, R.fk);
+		}
+		hdr.off_cones = append_section(R.blob, R.cones);
+		hdr.off_pass = append_section(R.blob, R.pass);
+		hdr.off_chain = append_section(R.blob, R.chain);
+		hdr.off_rest = append_section(R.blob, rest);
+		hdr.off_sched = append_section(R.blob, R.sched);
+		hdr.resident_bytes = hdr.off_sched; // tail layout: nothing from here on is staged into shared memory
+		hdr.off_step_path = append_section(R.blob, R.step_path);
+		hdr.off_path_refs = append_section(R.blob, R.path_refs);
+		hdr.off_paths = append_section(R.blob, R.paths);
+		if (tail_layout) {
+			hdr.off_fk = append_section(R.blob, R.fk);
+		}
+		while (R.blob.size() % 16) {
+			R.blob.push_back(0);
+		}
+		if (!tail_layout) {
+			hdr.resident_bytes = (uint32_t)R.blob.size();
+		}
+	};
+	assemble(false);
+	if (R.blob.size() > kResidentBlobBudget) {
+		// the walk list (quadratic in chain depth) and the segment-parallel tables stay in global memory
+		assemble(true);
 	}
 	hdr.total_bytes = (uint32_t)R.blob.size();
 	memcpy(R.blob.data(), &hdr, sizeof(hdr));

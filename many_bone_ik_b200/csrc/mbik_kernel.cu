@@ -11,6 +11,11 @@ int kernel_variant_for(int n_solved, int max_seg_len, int max_stack, size_t blob
 		if (v <= 2 && blob_bytes > 72 * 1024) {
 			continue;
 		}
+		// rigs in the tail layout (constants beyond the shared-memory budget) need the variant that reads the walk list
+		// from global memory
+		if (v <= 4 && blob_bytes > kResidentBlobBudget) {
+			continue;
+		}
 		if (n_solved <= kVariants[v][0] && max_seg_len <= kVariants[v][1] && max_stack <= kVariants[v][2]) {
 			return v;
 		}
@@ -28,7 +33,7 @@ int kernel_capacity_of_variant(int v) { return (v >= 0 && v < kNumVariants) ? kV
 // kernel's shared instruction stream is the better use of it (measured, humanoid22: 8192 poses 0.81 vs 1.55 ms,
 // 16384 poses 1.69 vs 1.58 ms; quad80: 8192 poses 6.3 vs 11.3 ms).
 int segment_parallel_choice(const SolveArgs &a, int variant, int sm_count) {
-	if (a.sched_mode == 1 || a.sp_roles < (a.sched_mode == 2 ? 1 : 2) || a.sp_roles > kMaxSpRoles || variant == 2) {
+	if (a.sched_mode == 1 || a.sp_roles < (a.sched_mode == 2 ? 1 : 2) || a.sp_roles > kMaxSpRoles || variant == 2 || variant == 5) {
 		return 0;
 	}
 	const size_t smem = sp_smem_bytes(a);
@@ -82,6 +87,8 @@ cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStre
 				return launch_lims_v3(a, stream);
 			case 4:
 				return launch_lims_v4(a, stream);
+			case 5:
+				return launch_lims_v5(a, stream);
 			default:
 				return cudaErrorInvalidValue;
 		}
@@ -133,6 +140,8 @@ cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStre
 			return launch_v3(a, threads, stream);
 		case 4:
 			return launch_v4(a, threads, stream);
+		case 5:
+			return launch_v5(a, threads, stream);
 		default:
 			return cudaErrorInvalidValue;
 	}

@@ -40,8 +40,8 @@ struct SolveArgs {
 
 // Compiled size variants {solved-bone capacity, longest segment, walk-stack depth}; per-pose thread-local state is
 // NB*12 + NSEG*12 + NSTK*12 floats, so tight variants keep more of it in L1/L2.
-constexpr int kNumVariants = 5;
-constexpr int kVariants[kNumVariants][3] = { { 20, 4, 2 }, { 32, 8, 4 }, { 64, 8, 1 }, { 64, 16, 8 }, { 128, 128, 16 } };
+constexpr int kNumVariants = 6;
+constexpr int kVariants[kNumVariants][3] = { { 20, 4, 2 }, { 32, 8, 4 }, { 64, 8, 1 }, { 64, 16, 8 }, { 128, 128, 16 }, { 256, 256, 32 } };
 
 // index of the smallest kernel variant that fits the rig, or -1 if none does
 int kernel_variant_for(int n_solved, int max_seg_len, int max_stack, size_t blob_bytes);
@@ -54,6 +54,7 @@ cudaError_t launch_v1(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v2(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v3(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v4(const SolveArgs &a, int threads, cudaStream_t stream);
+cudaError_t launch_v5(const SolveArgs &a, int threads, cudaStream_t stream);
 
 // per-pose limit sets (mbik_kernel_lims.cu): thread-per-pose mapping, 512-thread CTAs, no stabilisation
 cudaError_t launch_lims_v0(const SolveArgs &a, cudaStream_t stream);
@@ -61,6 +62,7 @@ cudaError_t launch_lims_v1(const SolveArgs &a, cudaStream_t stream);
 cudaError_t launch_lims_v2(const SolveArgs &a, cudaStream_t stream);
 cudaError_t launch_lims_v3(const SolveArgs &a, cudaStream_t stream);
 cudaError_t launch_lims_v4(const SolveArgs &a, cudaStream_t stream);
+cudaError_t launch_lims_v5(const SolveArgs &a, cudaStream_t stream);
 
 // segment-parallel instantiations (mbik_kernel_sp*.cu); min_groups_per_sm 1 = full register budget, 2 = 128 registers
 // (several 32-pose groups per SM)

@@ -638,7 +638,8 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	const BlobStep *steps = reinterpret_cast<const BlobStep *>(smem + H.off_steps);
 	const BlobBone *bones = reinterpret_cast<const BlobBone *>(smem + H.off_bones);
 	const BlobEff *effs = reinterpret_cast<const BlobEff *>(smem + H.off_effs);
-	const BlobFk *fk = reinterpret_cast<const BlobFk *>(smem + H.off_fk);
+	// large-rig variant (NB > 128): rigs in the tail layout keep the walk list in global memory (uniform loads through L1)
+	const BlobFk *fk = reinterpret_cast<const BlobFk *>((NB > 128 && H.resident_bytes < H.total_bytes ? a.blob : smem) + H.off_fk);
 	const BlobCone *cones = reinterpret_cast<const BlobCone *>(smem + H.off_cones);
 	const BlobPass *pass = reinterpret_cast<const BlobPass *>(smem + H.off_pass);
 	const int16_t *chain = reinterpret_cast<const int16_t *>(smem + H.off_chain);

@@ -1,0 +1,16 @@
+// mbik_kernel_l5.cu -- per-pose limit sets (mbik_solve_batch_limits) for the size variant {256 solved bones, segment 256,
+// stack 32}: the thread-per-pose kernel with the kusudama data read from the pose's limit-set record (solve_body LIMS).
+// large-rig variant: scalar formulations (see mbik_kernel_v5.cu)
+#define MBIK_F2_MAT 0
+#define MBIK_F2_VEC 0
+#define MBIK_F2_DOT 0
+#define MBIK_F2_DIV 0
+#include "mbik_kernel_body.cuh"
+
+namespace mbik {
+
+cudaError_t launch_lims_v5(const SolveArgs &a, cudaStream_t stream) {
+	return launch_variant_lims<256, 256, 32, kBlockThreads>(a, stream);
+}
+
+} // namespace mbik

@@ -1,0 +1,27 @@
+// mbik_kernel_v5.cu -- instantiations of the solve kernel for the size variant {256 solved bones, segment 256, stack 32}.
+// Thread-per-pose mapping only (the local poses of a 32-pose group, 384 KiB, do not fit shared memory).
+// The large-rig variants are register-starved at 128 registers (64+ local poses to address): with the packed FP32x2
+// composites they spill and run 2-3 % slower (chain64 71.6 vs 69.4 ms, quad80 13.8 vs 13.5 ms per 75776-pose launch),
+// so this translation unit keeps the scalar formulations (same bits either way).
+#define MBIK_F2_MAT 0
+#define MBIK_F2_VEC 0
+#define MBIK_F2_DOT 0
+#define MBIK_F2_DIV 0
+#include "mbik_kernel_body.cuh"
+
+namespace mbik {
+
+cudaError_t launch_v5(const SolveArgs &a, int threads, cudaStream_t stream) {
+	switch (threads) {
+		case 0: // stabilisation passes > 0: separate instantiation, the default path pays nothing for it
+			return launch_variant<256, 256, 32, kStabBlockThreads, true>(a, stream);
+		case 32: // small batches: one warp per SM (latency, not throughput)
+			return launch_variant<256, 256, 32, 32>(a, stream);
+		case 128:
+			return launch_variant<256, 256, 32, 128>(a, stream);
+		default:
+			return launch_variant<256, 256, 32, kBlockThreads>(a, stream);
+	}
+}
+
+} // namespace mbik

@@ -258,3 +258,50 @@ def big_tree120():
 
 
 EDGE_RIGS.update({f.__name__: f for f in [chain100, big_tree120]})
+
+
+def chain200():
+    """200-bone single chain, pins at bones 99 and 199: a 100-bone translating root segment under a 100-bone child
+    segment -- needs the {256, 256, 32} kernel variant, and its walk list (quadratic in chain depth, ~160 KB) puts the
+    rig constants past the shared-memory budget: tail layout, walk list read from global memory."""
+    n = 200
+    parent, rest = _chain(n, seg=0.02, curl=0.6)
+    r = Rig("chain200", [f"b{i}" for i in range(n)], parent, rest, iterations=2, config_id=34)
+    r.pins = [dict(bone=99, weight=0.5, mpf=1.0, priorities=(0.2, 0.0, 0.2)), dict(bone=n - 1, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2))]
+    _add_constraints(r, {b: (1 + b % 2, 35, 20, -40, 80) for b in range(1, n, 3)})
+    return r
+
+
+def chain150():
+    """150-bone chain, one pin: {256, 256, 32} variant with the ordinary (fully shared-memory resident) layout."""
+    n = 150
+    parent, rest = _chain(n, seg=0.02, curl=0.8)
+    r = Rig("chain150", [f"b{i}" for i in range(n)], parent, rest, iterations=2, config_id=36)
+    r.pins = [dict(bone=n - 1, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2))]
+    _add_constraints(r, {b: (1, 35, 20, -40, 80) for b in range(1, n, 5)})
+    return r
+
+
+def big_tree240():
+    """240-bone branching rig, every leaf pinned (mixed priorities, deep walks, walk stack beyond 16 is allowed): {256, 256, 32}."""
+    rng = np.random.default_rng(78)
+    n = 240
+    parent = np.full(n, -1, np.int32)
+    for b in range(1, n):
+        parent[b] = b - 1 if rng.random() < 0.85 else int(rng.integers(max(0, b - 60), b))
+    rest = np.zeros((n, 12))
+    for b in range(n):
+        rest[b] = _xf(_axis_angle(rng.normal(size=3), rng.uniform(0, 20) * DEG), rng.normal(size=3) * 0.05 + (0, 0.08, 0))
+    r = Rig("big_tree240", [f"b{i}" for i in range(n)], parent, rest.astype(np.float32), iterations=2, config_id=35)
+    leaves = [b for b in range(n) if not np.any(parent == b)]
+    inner = [int(b) for b in rng.choice(np.arange(5, n), size=6, replace=False) if int(b) not in leaves]
+    for b in sorted(set(leaves + inner)):  # every leaf pinned: (almost) every bone is solved
+        r.pins.append(dict(bone=int(b), weight=float(rng.uniform(0.3, 1.0)), mpf=float(rng.choice([0.5, 1.0])),
+                           priorities=(0.2, float(rng.choice([0.0, 0.1])), 0.2)))
+    _add_constraints(r, {int(b): (int(rng.integers(1, 4)), 40, 25, -30, 60) for b in range(1, n, 4)})
+    return r
+
+
+# rigs beyond 128 solved bones: their own dict (not part of the committed golden fixtures); compared live with the oracle
+# and, where it travelled, with the reference module's own code
+LARGE_RIGS = {f.__name__: f for f in [chain150, chain200, big_tree240]}

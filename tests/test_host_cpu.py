@@ -182,16 +182,36 @@ def test_rig_create_argument_errors():
 
 
 def test_rig_too_large_is_unsupported_not_truncated():
-    n = 200
+    n = 300
     parent = np.arange(-1, n - 1, dtype=np.int32)
     rest = np.zeros((n, 12), np.float32)
     rest[:, 0] = rest[:, 4] = rest[:, 8] = 1.0
     rest[1:, 10] = 0.05
-    r = rigs.Rig("chain200", [f"b{i}" for i in range(n)], parent, rest, iterations=2)
+    r = rigs.Rig("chain300", [f"b{i}" for i in range(n)], parent, rest, iterations=2)
     r.pins = [dict(bone=n - 1, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2))]
     with pytest.raises(MbikError) as ei:
         BatchedIKRig(r)
     assert ei.value.code == -3
+
+
+@pytest.mark.parametrize("name", sorted(rig_cases.LARGE_RIGS))
+def test_rigs_up_to_256_solved_bones_are_accepted(name):
+    """129..256 solved bones select the {256, 256, 32} kernel variant; the flattener's bone order and weights still
+    equal the oracle's setup."""
+    rig = rig_cases.LARGE_RIGS[name]()
+    R = BatchedIKRig(rig)
+    F = O.rig_facts(rig)
+    assert 128 < R.info["n_solved"] <= 256
+    assert R.info["kernel_capacity"] == 256
+    assert np.array_equal(R.bone_order(), F["bone_order"])
+    assert R.info["n_segments"] == F["n_segments"]
+    d, t = R.bone_frames()
+    assert np.array_equal(d, F["dir_basis"], equal_nan=True)
+    assert np.array_equal(t, F["twist_basis"], equal_nan=True)
+    for s in range(R.info["n_steps"]):
+        assert np.array_equal(R.step_weights(s), O.step_weights(rig, s)), f"step {s}"
+    assert np.array_equal(R.cone_geometry(), O.cone_geometry(rig), equal_nan=True)
+    R.close()
 
 
 def test_solve_without_a_gpu_fails_loudly():

@@ -84,6 +84,22 @@ def test_limit_set_zero_equals_the_plain_solve_and_indices_are_clamped():
     R.destroy_limit_sets(h)
 
 
+def test_limit_sets_on_a_rig_beyond_128_solved_bones():
+    """mbik_solve_batch_limits through the {256, 256, 32} variant (tail layout): per-set rigs in the oracle."""
+    rig = rig_cases.LARGE_RIGS["big_tree240"]()
+    R = BatchedIKRig(rig)
+    sets = LS.variants(rig, 3)
+    h = R.create_limit_sets(sets)
+    n = 96
+    T = rigs.random_targets(rig, 0, n)
+    idx = (np.arange(n) % 3).astype(np.int32)
+    want = _expected(rig, sets, idx, T, None, lambda r, t, **kw: O.solve_batch(r, t, threads=8, **kw))
+    got = R.solve_with_limits(h, idx, T, want_local=True)
+    for a, b in zip(got, want):
+        assert _same(a, b)
+    R.destroy_limit_sets(h)
+
+
 def test_limit_sets_device_io_equals_host_io():
     import torch
     rig = rigs.quad80()

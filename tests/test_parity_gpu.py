@@ -95,6 +95,22 @@ def test_bit_exact_edge_rigs(name):
         assert st.any(), "this rig is meant to exercise the non-finite reset path"
 
 
+@pytest.mark.parametrize("name", sorted(rig_cases.LARGE_RIGS))
+def test_bit_exact_rigs_beyond_128_solved_bones(name):
+    """129..256 solved bones: the {256, 256, 32} kernel variant (thread-per-pose mapping only), with the rig constants
+    fully shared-memory resident (chain150) and in the tail layout (chain200, big_tree240: walk list in global memory);
+    a batch larger than one CTA per SM's worth of poses is covered by the second call."""
+    rig = rig_cases.LARGE_RIGS[name]()
+    _compare(rig, 48)
+    R = BatchedIKRig(rig)
+    n = 700
+    T = rigs.random_targets(rig, 100, n)
+    idx = np.arange(0, n, 53)
+    ref = O.solve_batch(rig, T[idx], want_local=True, threads=8)
+    out, loc, st = R.solve(T, want_local=True)
+    _assert_same(rig, (out[idx], loc[idx], st[idx]), ref)
+
+
 @pytest.mark.parametrize("seed", range(24))
 def test_bit_exact_random_rigs(seed):
     """Fuzz: random trees, pins (zero weights, mpf cut-offs, 0-3 priority axes), 0-4 cones per row, per-bone damping,

@@ -80,6 +80,18 @@ def test_cuda_equals_live_reference(name, n):
 
 
 @needs_ref
+@pytest.mark.parametrize("name", sorted(rig_cases.LARGE_RIGS))
+def test_cuda_equals_live_reference_beyond_128_solved_bones(name):
+    """The {256, 256, 32} kernel variant vs the reference module's own code (which has no bone limit)."""
+    rig = rig_cases.LARGE_RIGS[name]()
+    R = BatchedIKRig(rig)
+    T = rigs.random_targets(rig, 7000, 32)
+    ref = Rf.solve_batch(rig, T, want_local=True, threads=Rf.hardware_threads())
+    out, loc, st = R.solve(T, want_local=True)
+    assert _same(loc, ref[1]) and _same(out, ref[0]) and np.array_equal(st, ref[2])
+
+
+@needs_ref
 def test_cuda_frame_sequence_equals_live_reference():
     """Five warm-started frames (each frame starts from the previous frame's solved locals, the reference's
     frame-to-frame seeding, src/many_bone_ik_3d.cpp:1084): CUDA and the reference's own code stay bit-identical."""
