@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmbik.so")
+# MBIK_LIB: an alternative build of the same library (kernel experiments, profiles/build_variant.py)
+LIB_PATH = os.environ.get("MBIK_LIB") or os.path.join(_HERE, "libmbik.so")
 
 
 class PinDesc(C.Structure):

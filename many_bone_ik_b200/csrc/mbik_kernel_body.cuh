@@ -54,12 +54,25 @@
 // by the demand loads of 16 warps per SM, so the knob stays 0.  Fewer resident poses do not pay either
 // (profiles/run_residency.py: 2 x 128 threads per SM 93 ms, 1 x 128 122 ms): the kernel then runs out of warps to hide
 // the dependent FP32 chains faster than the L2 hit rate recovers.
+// see solve_body: 0 = CTA-wide barrier per bone-step; 1..4 = cohort ring, released after (1) the bone's global, (2) the
+// heading walk, (3) the damped rotation, (4) the pose update before the snaps
+#ifndef MBIK_STAGGER
+#define MBIK_STAGGER 0
+#endif
+#ifndef MBIK_SKIP_TO
+#define MBIK_SKIP_TO 0
+#endif
 #ifndef MBIK_PREFETCH_DIST
 #define MBIK_PREFETCH_DIST 0
 #endif
 #ifndef MBIK_PREFETCH_LEVEL
 #define MBIK_PREFETCH_LEVEL 2
 #endif
+
+#define MBIK_RELEASE_AT(pt) \
+	if (MBIK_STAGGER == (pt) && stagger_release) { \
+		asm volatile("bar.arrive %0, %1;" ::"r"(1 + (cohort + 1 == n_cohorts ? 0 : cohort + 1)), "r"(256) : "memory"); \
+	}
 
 namespace mbik {
 
@@ -465,9 +478,13 @@ __device__ __forceinline__ M3 damp_and_slerp0_t(Q4 q, double cos_half_damp, cons
 	// branch of Quaternion::slerp (sin(w)/sin(w) == 1 exactly); the 0 * to terms are kept so that a
 	// non-finite global basis poisons the result exactly as it does in the reference.
 	Q4 from = m3_get_quat_t(R1, ops);
-	Q4 to = m3_get_quat_t(Gb, ops);
 	Q4 sl = from;
-	// finite `to`: from * 1 + to * 0 == from
+	// finite `to`: from * 1 + to * 0 == from.  A bounded Gb always has a finite quaternion (Shepperd's radicand is
+	// >= 1 - rounding on every branch, every entry < 1e18), so the conversion itself is skipped for it.
+	Q4 to = q4(0.0f, 0.0f, 0.0f, 1.0f);
+	if (!(MBIK_SKIP_TO && gb_bounded)) {
+		to = m3_get_quat_t(Gb, ops);
+	}
 	if (!(max3_abs_nan(max3_abs_nan(to.x, to.y, to.z), to.w, 0.0f) < kFiniteBound)) {
 		float cosom = q_dot(from, to);
 		if (cosom < 0.0f) {
@@ -704,6 +721,15 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 		__syncthreads();
 	}
 
+	// MBIK_STAGGER > 0 (thread-per-pose CTAs of >= 256 threads): instead of one CTA-wide barrier per bone-step, the CTA's
+	// warps form cohorts of four consecutive warps -- one per scheduler -- that follow each other through the step body at
+	// a fixed code distance: cohort c may enter a step once cohort c-1 has passed release point MBIK_STAGGER of that step
+	// (named barrier 1+c: 128 arriving + 128 waiting threads), and cohort 0 follows the last cohort of the previous step,
+	// which closes the ring and bounds the code window the CTA executes from.  The warps that share a scheduler are then
+	// in DIFFERENT stages of the step (heading accumulation = conversion / FP64 bound, snaps = FP32-chain bound) instead of
+	// all stalling on the same pipe at once, while the instruction stream stays one sliding window.
+	const int cohort = (int)(threadIdx.x >> 7), n_cohorts = (int)(blockDim.x >> 7);
+	const bool stagger = !SP && MBIK_STAGGER > 0 && n_cohorts >= 2 && (blockDim.x & 127u) == 0;
 	for (int it = 0; it < a.iterations; it++) {
 	for (int ph = 0; ph < sp_phases; ph++) {
 		if (SP && a.sp_trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
@@ -731,9 +757,15 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 #ifndef MBIK_SYNC_EVERY
 #define MBIK_SYNC_EVERY 1
 #endif
-			if (!SP && (MBIK_SYNC_EVERY == 1 || (s % MBIK_SYNC_EVERY) == 0)) {
+			if (!SP && stagger) {
+				// cohort ring (see MBIK_STAGGER): wait until the cohort ahead has passed its release point of this step
+				if (!(cohort == 0 && it == 0 && s == 0)) {
+					team_barrier(1 + cohort, 256);
+				}
+			} else if (!SP && (MBIK_SYNC_EVERY == 1 || (s % MBIK_SYNC_EVERY) == 0)) {
 				__syncthreads();
 			}
+			const bool stagger_release = stagger && !(cohort == n_cohorts - 1 && it == a.iterations - 1 && s == n_steps - 1);
 			if (SP && team > 1) {
 				team_barrier(team_bar, 32 * team); // the owner's previous step is in shared memory; the heading buffer is free
 			}
@@ -785,6 +817,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			Q4 q = q4(0.0f, 0.0f, 0.0f, 1.0f);
 			V3 translation = v3(0.0f, 0.0f, 0.0f);
 			const bool gb_bounded = m3_absmax(Gb.b) < kFiniteBound;
+			MBIK_RELEASE_AT(1)
 
 			if (!constraint_mode) {
 				const V3 bo = gb_bounded ? Gb.o : xform_zero(Gb); // origin of the solved bone's bone-direction frame
@@ -964,6 +997,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				translation = vsub(vneg(A.neg_tc), vneg(A.neg_mc));
 			}
 
+			MBIK_RELEASE_AT(2)
 			// re-read the parent global and the local pose (same values as above; the index is laundered so that the
 			// compiler reloads instead of keeping 24 registers alive across the walk)
 			int b_reload = b, pslot_reload = S.pslot;
@@ -995,6 +1029,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				}
 			}
 
+			MBIK_RELEASE_AT(3)
 			if (STAB && constraint_mode && (flags & STEP_STABILIZE)) {
 				// constraint mode skips the QCP passes, but the step's target headings still date from here (:135)
 				if (flags & STEP_SELF_EFF) {
@@ -1058,9 +1093,13 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						Lb.b = rotate_local_with_global(Pinv, m3_from_quat(rq), P.b, Lb.b);
 					}
 				}
+				MBIK_RELEASE_AT(4) // (steps without an IK parent release below)
 				if (flags & STEP_TWIST) {
 					Lb.b = twist_snap(P.b, Pinv, Lb.b, ld_m3v(Blim.twist_basis), ld_m3v(Blim.twist_center), Blim.twist_cos);
 				}
+			}
+			if (MBIK_STAGGER == 4 && !(flags & STEP_IK_PARENT)) {
+				MBIK_RELEASE_AT(4)
 			}
 			if (STAB) {
 				if (flags & STEP_STABILIZE) {
