@@ -86,16 +86,37 @@ typedef struct mbik_rig_desc {
 	int32_t constraint_mode;                  /* reference default false */
 } mbik_rig_desc;
 
-/* Per-call overrides.  Negative values mean "use the rig's". */
+/* Per-call overrides.  Negative values mean "use the rig's".  Zero-initialise the struct (`mbik_solve_params p = {0}`):
+ * fields added after `stream` default to the reference's behaviour at 0. */
 typedef struct mbik_solve_params {
 	int32_t iterations;   /* overrides iterations_per_frame (read every frame in the reference, :685) */
 	int32_t device;       /* CUDA device ordinal for this call; -1 = current device */
-	uint32_t flags;       /* MBIK_IO_* */
+	uint32_t flags;       /* MBIK_IO_* | MBIK_SCHED_* | MBIK_OUT_* | MBIK_LOCAL_RECOMPOSED */
 	void *stream;         /* cudaStream_t for MBIK_IO_DEVICE calls (NULL = default stream) */
+	int32_t newton_iters; /* Newton-Raphson steps on the QCP characteristic polynomial before the rotation is read off the
+	                         key matrix.  0 (and any negative value) = the reference: its QCP uses the upper bound
+	                         (Gt + Gm) / 2 as the eigenvalue and never refines it (reference src/math/qcp.cpp:205, :215), so
+	                         ONLY 0 is parity with the reference; > 0 gives the textbook Theobald fit (a different, usually
+	                         larger, rotation per bone-step) for callers who want it. */
+	int32_t reserved;     /* must be 0 */
 } mbik_solve_params;
 
 #define MBIK_IO_HOST 0u   /* buffers are host memory (pinned or pageable); the call copies, solves and returns when done */
 #define MBIK_IO_DEVICE 1u /* buffers are device memory on params->device; the call enqueues on params->stream and returns */
+
+/* Output layout.
+ *   MBIK_OUT_SOLVED_ONLY   out_pose is [n_poses][n_solved][10]: only the bones of ManyBoneIK3D::bone_list, in bone_list
+ *                          order (mbik_rig_get_bone_order) -- exactly the bones _update_skeleton_bones_transform hands to the
+ *                          skeleton (reference src/many_bone_ik_3d.cpp:104-116, src/ik_bone_3d.cpp:170-179).  Bones outside
+ *                          bone_list are never written by the reference, so a caller that owns a skeleton loses nothing
+ *                          and the device -> host copy shrinks by n_bones / n_solved.  Values are bit-identical to the
+ *                          same bones' rows of the default layout.
+ *   MBIK_LOCAL_RECOMPOSED  out_local holds, for the bones of bone_list, the pose Skeleton3D::get_bone_pose() returns once
+ *                          position / rotation / scale are in the skeleton -- Transform3D(Basis(rotation) * diag(scale),
+ *                          position), with the non-finite reset -- i.e. what the reference's NEXT frame seeds its IK
+ *                          bones from (src/many_bone_ik_3d.cpp:1084, :91-102), instead of the raw IK-bone transforms. */
+#define MBIK_OUT_SOLVED_ONLY 8u
+#define MBIK_LOCAL_RECOMPOSED 16u
 
 /* Kernel mapping (default: chosen by batch size).  Both mappings run the same per-pose arithmetic in the same order
  * and return identical bits; these flags exist for tests and measurements.
@@ -174,22 +195,29 @@ int mbik_solve_batch_multi(mbik_rig *rig, const mbik_solve_params *params, size_
 /*
  * Warm-start streaming.  The reference re-seeds its IK bones from the skeleton after
  * every frame (signal modification_processed -> _update_ik_bones_transform, reference src/many_bone_ik_3d.cpp:1084,
- * :91-102), so frame f+1 starts from frame f's solution.  A stream keeps that state ON THE DEVICE: the raw local
+ * :91-102), so frame f+1 starts from frame f's solution AS THE SKELETON HOLDS IT: IKBone3D::set_skeleton_bone_pose hands
+ * position / rotation quaternion / scale to the skeleton (with the non-finite basis reset, src/ik_bone_3d.cpp:170-179) and
+ * Skeleton3D::get_bone_pose() recomposes them, Transform3D(Basis(rotation) * diag(scale), position) (engine
+ * scene/3d/skeleton_3d.cpp, not in the module's tree).  A stream keeps that state ON THE DEVICE: the recomposed local
  * transforms of all `n_poses` skeletons live in a device-resident ping-pong pair, each submitted frame uploads only
- * the targets, solves with start = previous frame's locals, and (optionally) downloads out_pose.  Frame f+1's
- * target upload and frame f's pose download overlap the solves.  Results are bit-identical to calling
- * mbik_solve_batch per frame with start_pose = the previous frame's out_local.
+ * the targets, solves with start = previous frame's recomposed locals, and (optionally) downloads out_pose.  Frame
+ * f+1's target upload and frame f's pose download overlap the solves.  Results are bit-identical to calling
+ * mbik_solve_batch per frame with MBIK_LOCAL_RECOMPOSED and start_pose = the previous frame's out_local, and to the
+ * reference module's own node living across frames (oracle/_ref, tests/test_reference_gpu.py).
  */
 typedef struct mbik_stream mbik_stream;
 /* initial_pose: host [n_poses][n_bones][12] or NULL (= the rig's rest pose for every skeleton) */
 int mbik_stream_create(mbik_rig *rig, int32_t device, size_t n_poses, const float *initial_pose, mbik_stream **out_stream);
+/* flags: MBIK_OUT_SOLVED_ONLY = mbik_stream_submit's out_pose is [n_poses][n_solved][10] (bone_list order) */
+int mbik_stream_create_ex(mbik_rig *rig, int32_t device, size_t n_poses, const float *initial_pose, uint32_t flags, mbik_stream **out_stream);
 int mbik_stream_destroy(mbik_stream *stream);
 /* Enqueue one frame and return.  targets: host [n_poses][n_pins][12]; out_pose / out_status: host buffers or NULL
  * (NULL = leave the result on the device).  All three must stay valid until mbik_stream_sync(); use pinned memory
  * for true asynchrony.  iterations < 0 = the rig's iterations_per_frame. */
 int mbik_stream_submit(mbik_stream *stream, const float *targets, float *out_pose, uint32_t *out_status, int32_t iterations);
 int mbik_stream_sync(mbik_stream *stream); /* wait for every submitted frame; returns the first asynchronous error */
-/* Synchronous read-back of the current raw local transforms [n_poses][n_bones][12] (after all submitted frames). */
+/* Synchronous read-back of the current (recomposed) local transforms [n_poses][n_bones][12] (after all submitted frames):
+ * what the next frame will start from. */
 int mbik_stream_read_local(mbik_stream *stream, float *out_local);
 /* Re-seed every skeleton (NULL = rest pose), like _bone_list_changed() -> _update_ik_bones_transform(). */
 int mbik_stream_reset(mbik_stream *stream, const float *initial_pose);
@@ -205,14 +233,29 @@ int64_t mbik_stream_frames(const mbik_stream *stream); /* frames submitted so fa
  * the tangent-circle construction goes through libm sin / cos / acos / tan, which only the host evaluates bit-identically
  * to the reference) and uploads the resulting cone / tangent-circle geometry and twist frames as a device table;
  * mbik_solve_batch_limits then solves pose k with set set_index[k].  Result of pose k == mbik_solve_batch on a rig created
- * with that set's constraint values, bit for bit.  Thread-per-pose kernel mapping; rigs with stabilization_passes > 0
- * are not supported (MBIK_ERR_UNSUPPORTED).
+ * with that set's constraint values, bit for bit -- in both kernel mappings and with stabilization_passes > 0.
  */
 typedef struct mbik_limit_sets mbik_limit_sets;
 /* constraints: [n_sets][rig n_constraints] rows in the rig's row order (bone and n_cones must equal the rig's row;
  * cone_offset indexes the set's own block of `cones`); cones: [n_sets][cones_per_set]. */
 int mbik_limit_sets_create(mbik_rig *rig, int32_t n_sets, const mbik_constraint_desc *constraints, const mbik_cone_desc *cones,
 		int32_t cones_per_set, mbik_limit_sets **out_sets);
+/* The authoring of the sets runs on a pool of host threads (one set is one unit; MBIK_AUTHOR_THREADS overrides the
+ * thread count, default = all hardware threads).  mbik_limit_sets_create returns when the table is complete;
+ * mbik_limit_sets_create_async copies the caller's tables and returns at once -- the authoring overlaps whatever the
+ * caller does next (e.g. solving the previous crowd); mbik_solve_batch_limits / mbik_limit_sets_wait block until it is
+ * done and report its error, if any. */
+int mbik_limit_sets_create_async(mbik_rig *rig, int32_t n_sets, const mbik_constraint_desc *constraints, const mbik_cone_desc *cones,
+		int32_t cones_per_set, mbik_limit_sets **out_sets);
+int mbik_limit_sets_wait(mbik_limit_sets *sets);
+typedef struct mbik_limit_sets_info {
+	int32_t n_sets;
+	uint32_t bytes_per_set;  /* device table record: n_cones * 160 + n_solved * 208 */
+	int64_t table_bytes;
+	double author_seconds;   /* wall time of the host authoring of all sets */
+	int32_t author_threads;  /* host threads it ran on */
+} mbik_limit_sets_info;
+int mbik_limit_sets_get_info(mbik_limit_sets *sets, mbik_limit_sets_info *out_info); /* waits for the authoring */
 int mbik_limit_sets_destroy(mbik_limit_sets *sets);
 /* set_index: [n_poses] int32, host or device memory like the other buffers (params->flags); values are clamped to
  * [0, n_sets).  Other arguments as mbik_solve_batch. */
@@ -249,6 +292,9 @@ int mbik_selftest(int32_t device, int32_t rounds, uint64_t *out_checked, uint64_
  *                               the constraint on skeleton bone `bone` of `rig`; out[n][4] = point xyz + in_bounds
  */
 int mbik_stage_qcp(int32_t device, int32_t n, const float *moved, const float *target, const double *weight, int32_t translate, float *out7);
+/* the same stage with mbik_solve_params::newton_iters (0 = mbik_stage_qcp) */
+int mbik_stage_qcp_newton(int32_t device, int32_t n, const float *moved, const float *target, const double *weight, int32_t translate,
+		int32_t newton_iters, float *out7);
 int mbik_stage_clamp(int32_t device, int32_t n, const float *quats, const double *cos_half, float *out);
 int mbik_stage_point_in_limits(mbik_rig *rig, int32_t device, int32_t bone, int32_t n, const float *points, float *out);
 

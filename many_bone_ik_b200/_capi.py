@@ -40,7 +40,13 @@ class RigDesc(C.Structure):
 
 
 class SolveParams(C.Structure):
-    _fields_ = [("iterations", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p)]
+    _fields_ = [("iterations", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p),
+                ("newton_iters", C.c_int32), ("reserved", C.c_int32)]
+
+
+class LimitSetsInfo(C.Structure):
+    _fields_ = [("n_sets", C.c_int32), ("bytes_per_set", C.c_uint32), ("table_bytes", C.c_int64), ("author_seconds", C.c_double),
+                ("author_threads", C.c_int32)]
 
 
 class RigInfo(C.Structure):
@@ -55,6 +61,8 @@ MBIK_IO_HOST = 0
 MBIK_IO_DEVICE = 1
 MBIK_SCHED_THROUGHPUT = 2
 MBIK_SCHED_SEGMENT_PARALLEL = 4
+MBIK_OUT_SOLVED_ONLY = 8
+MBIK_LOCAL_RECOMPOSED = 16
 
 # every symbol include/mbik.h declares (tests check the library exports exactly these)
 EXPORTED_SYMBOLS = [
@@ -65,6 +73,7 @@ EXPORTED_SYMBOLS = [
     "mbik_stream_create", "mbik_stream_destroy", "mbik_stream_submit", "mbik_stream_sync", "mbik_stream_read_local",
     "mbik_stream_reset", "mbik_stream_frames", "mbik_stage_qcp", "mbik_stage_clamp", "mbik_stage_point_in_limits",
     "mbik_limit_sets_create", "mbik_limit_sets_destroy", "mbik_solve_batch_limits",
+    "mbik_limit_sets_create_async", "mbik_limit_sets_wait", "mbik_limit_sets_get_info", "mbik_stream_create_ex", "mbik_stage_qcp_newton",
 ]
 
 
@@ -183,6 +192,11 @@ def load_library():
     lib.mbik_stage_point_in_limits.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
     lib.mbik_limit_sets_create.argtypes = [vp, C.c_int32, C.POINTER(ConstraintDesc), C.POINTER(ConeDesc), C.c_int32, C.POINTER(vp)]
     lib.mbik_limit_sets_destroy.argtypes = [vp]
+    lib.mbik_limit_sets_create_async.argtypes = lib.mbik_limit_sets_create.argtypes
+    lib.mbik_limit_sets_wait.argtypes = [vp]
+    lib.mbik_limit_sets_get_info.argtypes = [vp, C.POINTER(LimitSetsInfo)]
+    lib.mbik_stream_create_ex.argtypes = [vp, C.c_int32, C.c_size_t, vp, C.c_uint32, C.POINTER(vp)]
+    lib.mbik_stage_qcp_newton.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, C.c_int32, vp]
     lib.mbik_solve_batch_limits.argtypes = [vp, vp, C.POINTER(SolveParams), C.c_size_t, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib

@@ -3,7 +3,7 @@
 // One contiguous, 16-byte aligned blob of rig constants.  The kernel stages it into shared memory
 // with one TMA bulk copy per CTA; every lane then reads the same words (broadcast).  Layout:
 //   BlobHeader | BlobStep[n_steps] | BlobBone[n_solved] | BlobEff[n_effs] | BlobFk[n_fk] |
-//   BlobCone[n_cones] | BlobPass[n_pass] | chain[n_chain] (int16) | rest_local[n_bones*12] | BlobSpan[sp_phases*sp_slots*sp_roles] |
+//   BlobCone[n_cones] | BlobPass[n_pass] | chain[n_chain] (int16) | list_row[n_solved] (int16) | rest_local[n_bones*12] | BlobSpan[sp_phases*sp_slots*sp_roles] |
 //   step_path[n_steps] (int32) | BlobPathRef[] | paths[] (int16)
 // Tail layout (large rigs, BlobHeader::resident_bytes < total_bytes): the walk list BlobFk[] -- quadratic in the depth of a
 // chain -- moves behind paths[] and is read from global memory by the {256, 256, 32} kernel variant; the segment-parallel
@@ -49,6 +49,7 @@ struct BlobHeader {
 	                         // the shared-memory budget -- the offset of the tail (segment-parallel tables, walk list) that stays in global memory
 	uint32_t off_steps, off_bones, off_effs, off_fk, off_cones, off_pass, off_rest, off_chain, off_sched;
 	uint32_t off_step_path, off_path_refs, off_paths; // BlobPathRef tables of the team steps (see BlobSpan)
+	uint32_t off_list_row; // int16 list_row[n_solved]: index of solved bone t in bone_list (row of the compact output layout)
 };
 
 struct BlobStep { // 64 bytes

@@ -7,7 +7,11 @@
 #include "mbik_kernel.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges are no-ops unless a profiler injects itself
 
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,6 +34,25 @@ int fail(int code, const std::string &msg) {
 int cuda_fail(cudaError_t e, const char *what) {
 	return fail(MBIK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
+
+// restores the caller's current device when an entry point had to switch (multi-GPU processes: a later call with
+// params->device = -1, or the caller's own CUDA work, must not silently move to another GPU)
+struct DeviceGuard {
+	int prev = -1;
+	DeviceGuard() { cudaGetDevice(&prev); }
+	~DeviceGuard() {
+		int cur = -1;
+		if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) {
+			cudaSetDevice(prev);
+		}
+	}
+};
+
+// NVTX range of one stage of the host pipeline (tracing): upload / solve / download per chunk
+struct NvtxRange {
+	explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+};
 
 constexpr int kLanes = 3; // host-I/O pipeline depth: H2D(i+1) | solve(i) | D2H(i-1) on three streams
 
@@ -119,6 +142,14 @@ struct mbik_limit_sets {
 	std::vector<unsigned char> table;
 	std::mutex mu;
 	std::map<int, unsigned char *> device_tables;
+	// authoring (host, thread pool): mbik_limit_sets_create waits for it, mbik_limit_sets_create_async returns while it runs
+	std::thread worker;
+	std::vector<mbik_constraint_desc> own_constraints; // async: the caller's tables are copied, it may free them at once
+	std::vector<mbik_cone_desc> own_cones;
+	int rc = MBIK_OK;
+	std::string error;
+	double author_seconds = 0.0;
+	int author_threads = 0;
 };
 
 struct mbik_stream {
@@ -138,6 +169,8 @@ struct mbik_stream {
 	cudaEvent_t ev_down[2] = { nullptr, nullptr };   // out slot downloaded (slot reusable)
 	bool slot_used[2] = { false, false };
 	int64_t frames = 0;
+	uint32_t flags = 0;  // MBIK_OUT_SOLVED_ONLY: out_pose rows of mbik_stream_submit
+	size_t out_rows = 0; // bones per pose in out_pose
 };
 
 namespace {
@@ -322,11 +355,12 @@ void sp_trace_launch(mbik::SolveArgs a, const mbik::FlatRig &F, int variant, int
 }
 
 // one shard on one device; host or device buffers
-int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user_stream, int iterations, size_t n_poses,
+int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user_stream, int iterations, int newton_iters, size_t n_poses,
 		const float *targets, const float *start_pose, float *out_pose, float *out_local, uint32_t *out_status, const LimitArgs *lim = nullptr) {
 	if (n_poses == 0) {
 		return MBIK_OK;
 	}
+	DeviceGuard guard;
 	cudaError_t e = cudaSetDevice(device);
 	if (e != cudaSuccess) {
 		return cuda_fail(e, "cudaSetDevice");
@@ -344,6 +378,9 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 	a.iterations = iterations;
 	a.n_poses = n_poses;
 	a.stabilize = F.stabilization_passes > 0 ? 1 : 0;
+	a.newton_iters = newton_iters > 0 ? newton_iters : 0;
+	a.out_flags = ((flags & MBIK_OUT_SOLVED_ONLY) ? mbik::OUT_COMPACT : 0u) | ((flags & MBIK_LOCAL_RECOMPOSED) ? mbik::OUT_LOCAL_RECOMPOSED : 0u);
+	const size_t out_rows = (flags & MBIK_OUT_SOLVED_ONLY) ? F.bones.size() : (size_t)F.n_bones; // rows of out_pose per pose
 	set_launch_hints(a, F, flags);
 
 	if (lim) {
@@ -363,6 +400,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 		if (trace) {
 			sp_trace_launch(a, F, rig->variant, ds->sm_count, user_stream);
 		}
+		NvtxRange range("mbik solve (device buffers)");
 		cudaEventRecord(ds->ev_start, user_stream);
 		e = mbik::launch_solve(a, rig->variant, ds->sm_count, user_stream);
 		cudaEventRecord(ds->ev_stop, user_stream);
@@ -391,7 +429,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 		Lane &ln = ds->lanes[c % kLanes];
 		const size_t b0 = c * chunk, cn = (b0 + chunk <= n_poses) ? chunk : n_poses - b0;
 		const size_t bt = cn * np * 12 * sizeof(float), bs = cn * nb * 12 * sizeof(float);
-		const size_t bo = cn * nb * 10 * sizeof(float), bl = cn * nb * 12 * sizeof(float), bst = cn * sizeof(uint32_t);
+		const size_t bo = cn * out_rows * 10 * sizeof(float), bl = cn * nb * 12 * sizeof(float), bst = cn * sizeof(uint32_t);
 		if ((rc = ensure_capacity(&ln.d_targets, &ln.cap_targets, bt ? bt : 16)) != MBIK_OK ||
 				(rc = ensure_capacity(&ln.d_out, &ln.cap_out, bo)) != MBIK_OK ||
 				(start_pose && (rc = ensure_capacity(&ln.d_start, &ln.cap_start, bs)) != MBIK_OK) ||
@@ -404,6 +442,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 			return rc;
 		}
 		cudaStream_t st = ln.stream;
+		nvtxRangePushA("mbik H2D chunk");
 		if (bt) {
 			cudaMemcpyAsync(ln.d_targets, targets + b0 * np * 12, bt, cudaMemcpyHostToDevice, st);
 		}
@@ -414,6 +453,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 			cudaMemcpyAsync(ln.d_index, lim->set_index + b0, cn * sizeof(int32_t), cudaMemcpyHostToDevice, st);
 			a.limit_index = ln.d_index;
 		}
+		nvtxRangePop();
 		a.n_poses = cn;
 		a.targets = ln.d_targets;
 		a.start_pose = start_pose ? ln.d_start : nullptr;
@@ -421,6 +461,7 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 		a.out_local = out_local ? ln.d_local : nullptr;
 		a.out_status = out_status ? ln.d_status : nullptr;
 		const bool last_of_lane = c + kLanes >= n_chunks;
+		nvtxRangePushA("mbik solve chunk");
 		if (last_of_lane) {
 			cudaEventRecord(ln.ev_start, st);
 		}
@@ -428,20 +469,24 @@ int solve_on_device(mbik_rig *rig, int device, uint32_t flags, cudaStream_t user
 		if (last_of_lane) {
 			cudaEventRecord(ln.ev_stop, st);
 		}
+		nvtxRangePop();
 		if (e != cudaSuccess) {
 			for (Lane &l2 : ds->lanes) {
 				cudaStreamSynchronize(l2.stream);
 			}
 			return cuda_fail(e, "kernel launch");
 		}
-		cudaMemcpyAsync(out_pose + b0 * nb * 10, ln.d_out, bo, cudaMemcpyDeviceToHost, st);
+		nvtxRangePushA("mbik D2H chunk");
+		cudaMemcpyAsync(out_pose + b0 * out_rows * 10, ln.d_out, bo, cudaMemcpyDeviceToHost, st);
 		if (out_local) {
 			cudaMemcpyAsync(out_local + b0 * nb * 12, ln.d_local, bl, cudaMemcpyDeviceToHost, st);
 		}
 		if (out_status) {
 			cudaMemcpyAsync(out_status + b0, ln.d_status, bst, cudaMemcpyDeviceToHost, st);
 		}
+		nvtxRangePop();
 	}
+	NvtxRange drain("mbik drain (stream synchronize)");
 	cudaError_t first_err = cudaSuccess;
 	for (Lane &ln : ds->lanes) {
 		cudaError_t e2 = cudaStreamSynchronize(ln.stream);
@@ -697,90 +742,195 @@ int mbik_solve_batch(mbik_rig *rig, const mbik_solve_params *params, size_t n_po
 	}
 	uint32_t flags = params ? params->flags : MBIK_IO_HOST;
 	cudaStream_t stream = params ? (cudaStream_t)params->stream : nullptr;
-	int prev = -1;
-	cudaGetDevice(&prev);
-	rc = solve_on_device(rig, device, flags, stream, iterations, n_poses, targets, start_pose, out_pose, out_local, out_status);
-	if (prev >= 0 && prev != device) {
-		cudaSetDevice(prev);
-	}
-	return rc;
+	return solve_on_device(rig, device, flags, stream, iterations, params ? params->newton_iters : 0, n_poses, targets, start_pose, out_pose, out_local, out_status);
 }
 
-int mbik_limit_sets_create(mbik_rig *rig, int32_t n_sets, const mbik_constraint_desc *constraints, const mbik_cone_desc *cones,
-		int32_t cones_per_set, mbik_limit_sets **out_sets) {
+namespace {
+
+// Runs the reference's constraint authoring (flatten_rig: IKKusudama3D::_update_constraint / set_axial_limits,
+// IKLimitCone3D::update_tangent_handles on the host libm) for every set, on a pool of host threads: sets are independent.
+int author_limit_sets(mbik_limit_sets *ls, const mbik_constraint_desc *constraints, const mbik_cone_desc *cones, int32_t cones_per_set) {
+	mbik_rig *rig = ls->rig;
+	const mbik::FlatRig &F = rig->flat;
+	const size_t n_rows = rig->desc.constraints.size();
+	const int32_t n_sets = ls->n_sets;
+	const size_t cone_bytes = F.cones.size() * sizeof(mbik::BlobCone), bone_bytes = F.bones.size() * sizeof(mbik::BlobBone);
+	int n_threads = (int)std::thread::hardware_concurrency();
+	if (const char *env = getenv("MBIK_AUTHOR_THREADS")) {
+		n_threads = atoi(env);
+	}
+	n_threads = n_threads < 1 ? 1 : (n_threads > n_sets ? n_sets : n_threads);
+	ls->author_threads = n_threads;
+	std::atomic<int32_t> next(0);
+	std::atomic<int> first_rc(MBIK_OK);
+	std::mutex err_mu;
+	auto work = [&]() {
+		for (;;) {
+			const int32_t s = next.fetch_add(1);
+			if (s >= n_sets || first_rc.load() != MBIK_OK) {
+				return;
+			}
+			auto set_fail = [&](int code, const std::string &msg) {
+				int expected = MBIK_OK;
+				if (first_rc.compare_exchange_strong(expected, code)) {
+					std::lock_guard<std::mutex> lock(err_mu);
+					ls->error = msg;
+				}
+			};
+			const mbik_constraint_desc *rows = constraints + (size_t)s * n_rows;
+			bool rows_ok = true;
+			for (size_t r = 0; r < n_rows && rows_ok; r++) {
+				const mbik_constraint_desc &mine = rig->desc.constraints[r];
+				if (rows[r].bone != mine.bone || rows[r].n_cones != mine.n_cones) {
+					set_fail(MBIK_ERR_INVALID_ARG, "limit set " + std::to_string(s) + ", row " + std::to_string(r) +
+							": bone and n_cones must equal the rig's constraint row (only values may vary)");
+					rows_ok = false;
+				} else if (rows[r].n_cones > 0 && (rows[r].cone_offset < 0 || rows[r].cone_offset + rows[r].n_cones > cones_per_set || !cones)) {
+					set_fail(MBIK_ERR_INVALID_ARG, "limit set " + std::to_string(s) + ", row " + std::to_string(r) + ": cone_offset out of range");
+					rows_ok = false;
+				}
+			}
+			if (!rows_ok) {
+				return;
+			}
+			mbik_rig_desc d = rig->desc.view();
+			d.constraints = rows;
+			d.cones = cones ? cones + (size_t)s * cones_per_set : nullptr;
+			mbik::FlatRig Fs;
+			int rc = mbik::flatten_rig(&d, Fs);
+			if (rc != MBIK_OK) {
+				set_fail(rc, "limit set " + std::to_string(s) + ": " + Fs.error);
+				return;
+			}
+			// the schedule must be the rig's: same steps, same limit flags, same cone ranges
+			bool same = Fs.steps.size() == F.steps.size() && Fs.cones.size() == F.cones.size() && Fs.bones.size() == F.bones.size();
+			for (size_t i = 0; same && i < F.steps.size(); i++) {
+				same = Fs.steps[i].bone == F.steps[i].bone && Fs.steps[i].flags == F.steps[i].flags && Fs.steps[i].cone_off == F.steps[i].cone_off &&
+						Fs.steps[i].cone_cnt == F.steps[i].cone_cnt;
+			}
+			if (!same) {
+				set_fail(MBIK_ERR_INVALID_ARG, "limit set " + std::to_string(s) + " changes the rig's schedule (which bones are limited, or cone counts)");
+				return;
+			}
+			unsigned char *rec = ls->table.data() + (size_t)s * ls->stride;
+			if (cone_bytes) {
+				memcpy(rec, Fs.cones.data(), cone_bytes);
+			}
+			memcpy(rec + cone_bytes, Fs.bones.data(), bone_bytes);
+		}
+	};
+	const auto t0 = std::chrono::steady_clock::now();
+	std::vector<std::thread> pool;
+	for (int t = 1; t < n_threads; t++) {
+		pool.emplace_back(work);
+	}
+	work();
+	for (auto &t : pool) {
+		t.join();
+	}
+	ls->author_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	return first_rc.load();
+}
+
+int limit_sets_new(mbik_rig *rig, int32_t n_sets, const mbik_constraint_desc *constraints, int32_t cones_per_set, mbik_limit_sets **out_sets) {
 	if (!rig || !out_sets || n_sets < 1 || cones_per_set < 0) {
 		return fail(MBIK_ERR_INVALID_ARG, "rig/out_sets is NULL or n_sets < 1");
 	}
 	*out_sets = nullptr;
 	const mbik::FlatRig &F = rig->flat;
-	const size_t n_rows = rig->desc.constraints.size();
-	if (n_rows > 0 && !constraints) {
+	if (!rig->desc.constraints.empty() && !constraints) {
 		return fail(MBIK_ERR_INVALID_ARG, "constraints is NULL");
-	}
-	if (F.stabilization_passes > 0) {
-		return fail(MBIK_ERR_UNSUPPORTED, "limit sets are not supported on rigs with stabilization_passes > 0");
 	}
 	std::unique_ptr<mbik_limit_sets> ls(new (std::nothrow) mbik_limit_sets());
 	if (!ls) {
 		return fail(MBIK_ERR_ALLOC, "out of memory");
 	}
-	const size_t cone_bytes = F.cones.size() * sizeof(mbik::BlobCone), bone_bytes = F.bones.size() * sizeof(mbik::BlobBone);
 	ls->rig = rig;
 	ls->n_sets = n_sets;
-	ls->stride = (uint32_t)(cone_bytes + bone_bytes);
+	ls->stride = (uint32_t)(F.cones.size() * sizeof(mbik::BlobCone) + F.bones.size() * sizeof(mbik::BlobBone));
 	ls->table.resize((size_t)n_sets * ls->stride);
-	for (int32_t s = 0; s < n_sets; s++) {
-		const mbik_constraint_desc *rows = constraints + (size_t)s * n_rows;
-		for (size_t r = 0; r < n_rows; r++) {
-			const mbik_constraint_desc &mine = rig->desc.constraints[r];
-			if (rows[r].bone != mine.bone || rows[r].n_cones != mine.n_cones) {
-				return fail(MBIK_ERR_INVALID_ARG, "limit set " + std::to_string(s) + ", row " + std::to_string(r) +
-						": bone and n_cones must equal the rig's constraint row (only values may vary)");
-			}
-			if (rows[r].n_cones > 0 && (rows[r].cone_offset < 0 || rows[r].cone_offset + rows[r].n_cones > cones_per_set || !cones)) {
-				return fail(MBIK_ERR_INVALID_ARG, "limit set " + std::to_string(s) + ", row " + std::to_string(r) + ": cone_offset out of range");
-			}
-		}
-		mbik_rig_desc d = rig->desc.view();
-		d.constraints = rows;
-		d.cones = cones ? cones + (size_t)s * cones_per_set : nullptr;
-		mbik::FlatRig Fs;
-		int rc = mbik::flatten_rig(&d, Fs);
-		if (rc != MBIK_OK) {
-			return fail(rc, "limit set " + std::to_string(s) + ": " + Fs.error);
-		}
-		// the schedule must be the rig's: same steps, same limit flags, same cone ranges
-		bool same = Fs.steps.size() == F.steps.size() && Fs.cones.size() == F.cones.size() && Fs.bones.size() == F.bones.size();
-		for (size_t i = 0; same && i < F.steps.size(); i++) {
-			same = Fs.steps[i].bone == F.steps[i].bone && Fs.steps[i].flags == F.steps[i].flags && Fs.steps[i].cone_off == F.steps[i].cone_off &&
-					Fs.steps[i].cone_cnt == F.steps[i].cone_cnt;
-		}
-		if (!same) {
-			return fail(MBIK_ERR_INVALID_ARG, "limit set " + std::to_string(s) + " changes the rig's schedule (which bones are limited, or cone counts)");
-		}
-		unsigned char *rec = ls->table.data() + (size_t)s * ls->stride;
-		if (cone_bytes) {
-			memcpy(rec, Fs.cones.data(), cone_bytes);
-		}
-		memcpy(rec + cone_bytes, Fs.bones.data(), bone_bytes);
-	}
 	*out_sets = ls.release();
 	return MBIK_OK;
+}
+
+} // namespace
+
+int mbik_limit_sets_create(mbik_rig *rig, int32_t n_sets, const mbik_constraint_desc *constraints, const mbik_cone_desc *cones,
+		int32_t cones_per_set, mbik_limit_sets **out_sets) {
+	int rc = limit_sets_new(rig, n_sets, constraints, cones_per_set, out_sets);
+	if (rc != MBIK_OK) {
+		return rc;
+	}
+	mbik_limit_sets *ls = *out_sets;
+	NvtxRange range("mbik limit-set authoring");
+	ls->rc = author_limit_sets(ls, constraints, cones, cones_per_set);
+	if (ls->rc != MBIK_OK) {
+		rc = fail(ls->rc, ls->error);
+		delete ls;
+		*out_sets = nullptr;
+		return rc;
+	}
+	return MBIK_OK;
+}
+
+int mbik_limit_sets_create_async(mbik_rig *rig, int32_t n_sets, const mbik_constraint_desc *constraints, const mbik_cone_desc *cones,
+		int32_t cones_per_set, mbik_limit_sets **out_sets) {
+	int rc = limit_sets_new(rig, n_sets, constraints, cones_per_set, out_sets);
+	if (rc != MBIK_OK) {
+		return rc;
+	}
+	mbik_limit_sets *ls = *out_sets;
+	const size_t n_rows = rig->desc.constraints.size();
+	ls->own_constraints.assign(constraints, constraints + (size_t)n_sets * n_rows);
+	if (cones && cones_per_set > 0) {
+		ls->own_cones.assign(cones, cones + (size_t)n_sets * cones_per_set);
+	}
+	ls->worker = std::thread([ls, cones_per_set]() {
+		ls->rc = author_limit_sets(ls, ls->own_constraints.data(), ls->own_cones.empty() ? nullptr : ls->own_cones.data(), cones_per_set);
+		ls->own_constraints = std::vector<mbik_constraint_desc>();
+		ls->own_cones = std::vector<mbik_cone_desc>();
+	});
+	return MBIK_OK;
+}
+
+int mbik_limit_sets_wait(mbik_limit_sets *sets) {
+	if (!sets) {
+		return fail(MBIK_ERR_INVALID_ARG, "sets is NULL");
+	}
+	{
+		std::lock_guard<std::mutex> lock(sets->mu);
+		if (sets->worker.joinable()) {
+			sets->worker.join();
+		}
+	}
+	return sets->rc == MBIK_OK ? MBIK_OK : fail(sets->rc, sets->error);
+}
+
+int mbik_limit_sets_get_info(mbik_limit_sets *sets, mbik_limit_sets_info *out) {
+	if (!sets || !out) {
+		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
+	}
+	int rc = mbik_limit_sets_wait(sets);
+	out->n_sets = sets->n_sets;
+	out->bytes_per_set = sets->stride;
+	out->table_bytes = (int64_t)sets->table.size();
+	out->author_seconds = sets->author_seconds;
+	out->author_threads = sets->author_threads;
+	return rc;
 }
 
 int mbik_limit_sets_destroy(mbik_limit_sets *sets) {
 	if (!sets) {
 		return MBIK_OK;
 	}
-	int prev = -1;
-	cudaGetDevice(&prev);
+	if (sets->worker.joinable()) {
+		sets->worker.join();
+	}
+	DeviceGuard guard;
 	for (auto &kv : sets->device_tables) {
 		if (cudaSetDevice(kv.first) == cudaSuccess) {
 			cudaFree(kv.second);
 		}
-	}
-	if (prev >= 0) {
-		cudaSetDevice(prev);
 	}
 	delete sets;
 	return MBIK_OK;
@@ -799,14 +949,16 @@ int mbik_solve_batch_limits(mbik_rig *rig, mbik_limit_sets *sets, const mbik_sol
 	if (n_poses > 0 && !set_index) {
 		return fail(MBIK_ERR_INVALID_ARG, "set_index must not be NULL");
 	}
+	if ((rc = mbik_limit_sets_wait(sets)) != MBIK_OK) { // asynchronous authoring still running / failed
+		return rc;
+	}
 	int device = -1;
 	if ((rc = resolve_device(params, &device)) != MBIK_OK) {
 		return rc;
 	}
 	uint32_t flags = params ? params->flags : MBIK_IO_HOST;
 	cudaStream_t stream = params ? (cudaStream_t)params->stream : nullptr;
-	int prev = -1;
-	cudaGetDevice(&prev);
+	DeviceGuard guard;
 	LimitArgs lim;
 	{
 		// per-device copy of the table, uploaded on first use
@@ -823,9 +975,6 @@ int mbik_solve_batch_limits(mbik_rig *rig, mbik_limit_sets *sets, const mbik_sol
 			}
 			if (e != cudaSuccess) {
 				cudaFree(d);
-				if (prev >= 0 && prev != device) {
-					cudaSetDevice(prev);
-				}
 				return cuda_fail(e, "limit-set table upload");
 			}
 			it = sets->device_tables.emplace(device, d).first;
@@ -835,11 +984,7 @@ int mbik_solve_batch_limits(mbik_rig *rig, mbik_limit_sets *sets, const mbik_sol
 	lim.stride = sets->stride;
 	lim.n_sets = sets->n_sets;
 	lim.set_index = set_index;
-	rc = solve_on_device(rig, device, flags | MBIK_SCHED_THROUGHPUT, stream, iterations, n_poses, targets, start_pose, out_pose, out_local, out_status, &lim);
-	if (prev >= 0 && prev != device) {
-		cudaSetDevice(prev);
-	}
-	return rc;
+	return solve_on_device(rig, device, flags, stream, iterations, params ? params->newton_iters : 0, n_poses, targets, start_pose, out_pose, out_local, out_status, &lim);
 }
 
 int mbik_solve_batch_multi(mbik_rig *rig, const mbik_solve_params *params, size_t n_poses, const float *targets, const float *start_pose,
@@ -867,6 +1012,9 @@ int mbik_solve_batch_multi(mbik_rig *rig, const mbik_solve_params *params, size_
 		}
 	}
 	const size_t nb = (size_t)rig->flat.n_bones, np = rig->flat.pins.size();
+	const uint32_t pass_flags = params ? params->flags & (MBIK_SCHED_THROUGHPUT | MBIK_SCHED_SEGMENT_PARALLEL | MBIK_OUT_SOLVED_ONLY | MBIK_LOCAL_RECOMPOSED) : 0u;
+	const size_t out_rows = (pass_flags & MBIK_OUT_SOLVED_ONLY) ? rig->flat.bones.size() : nb;
+	const int newton_iters = params ? params->newton_iters : 0;
 	std::vector<int> rcs(n_devices, MBIK_OK);
 	std::vector<std::string> msgs(n_devices);
 	std::vector<std::thread> workers;
@@ -874,8 +1022,8 @@ int mbik_solve_batch_multi(mbik_rig *rig, const mbik_solve_params *params, size_
 		// contiguous split of the pose index range: device g gets [g*n/G, (g+1)*n/G)
 		size_t b = n_poses * (size_t)g / (size_t)n_devices, e = n_poses * (size_t)(g + 1) / (size_t)n_devices;
 		workers.emplace_back([&, g, b, e]() {
-			rcs[g] = solve_on_device(rig, devs[g], MBIK_IO_HOST | (params ? params->flags & (MBIK_SCHED_THROUGHPUT | MBIK_SCHED_SEGMENT_PARALLEL) : 0u), nullptr, iterations, e - b, targets + b * np * 12,
-					start_pose ? start_pose + b * nb * 12 : nullptr, out_pose + b * nb * 10, out_local ? out_local + b * nb * 12 : nullptr,
+			rcs[g] = solve_on_device(rig, devs[g], MBIK_IO_HOST | pass_flags, nullptr, iterations, newton_iters, e - b, targets + b * np * 12,
+					start_pose ? start_pose + b * nb * 12 : nullptr, out_pose + b * out_rows * 10, out_local ? out_local + b * nb * 12 : nullptr,
 					out_status ? out_status + b : nullptr);
 			if (rcs[g] != MBIK_OK) {
 				msgs[g] = g_last_error;
@@ -897,6 +1045,7 @@ int mbik_stream_destroy(mbik_stream *st) {
 	if (!st) {
 		return MBIK_OK;
 	}
+	DeviceGuard guard;
 	if (st->device >= 0) {
 		cudaSetDevice(st->device);
 		if (st->s_solve) {
@@ -937,6 +1086,7 @@ int mbik_stream_reset(mbik_stream *st, const float *initial_pose) {
 	if (!st) {
 		return fail(MBIK_ERR_INVALID_ARG, "stream is NULL");
 	}
+	DeviceGuard guard;
 	cudaError_t e = cudaSetDevice(st->device);
 	if (e != cudaSuccess) {
 		return cuda_fail(e, "cudaSetDevice");
@@ -972,20 +1122,26 @@ int mbik_stream_reset(mbik_stream *st, const float *initial_pose) {
 }
 
 int mbik_stream_create(mbik_rig *rig, int32_t device, size_t n_poses, const float *initial_pose, mbik_stream **out_stream) {
+	return mbik_stream_create_ex(rig, device, n_poses, initial_pose, 0u, out_stream);
+}
+
+int mbik_stream_create_ex(mbik_rig *rig, int32_t device, size_t n_poses, const float *initial_pose, uint32_t flags, mbik_stream **out_stream) {
 	if (!rig || !out_stream || n_poses == 0) {
 		return fail(MBIK_ERR_INVALID_ARG, "rig/out_stream is NULL or n_poses is 0");
 	}
+	if (flags & ~MBIK_OUT_SOLVED_ONLY) {
+		return fail(MBIK_ERR_INVALID_ARG, "mbik_stream_create_ex: only MBIK_OUT_SOLVED_ONLY is a stream flag");
+	}
 	*out_stream = nullptr;
-	mbik_solve_params p;
+	mbik_solve_params p = {};
 	p.iterations = -1;
 	p.device = device;
-	p.flags = 0;
-	p.stream = nullptr;
 	int dev = -1;
 	int rc = resolve_device(&p, &dev);
 	if (rc != MBIK_OK) {
 		return rc;
 	}
+	DeviceGuard guard;
 	cudaError_t e = cudaSetDevice(dev);
 	if (e != cudaSuccess) {
 		return cuda_fail(e, "cudaSetDevice");
@@ -1005,13 +1161,15 @@ int mbik_stream_create(mbik_rig *rig, int32_t device, size_t n_poses, const floa
 	st->blob = ds->blob;
 	const mbik::FlatRig &F = rig->flat;
 	const size_t nb = (size_t)F.n_bones, np = F.pins.size();
+	st->flags = flags;
+	st->out_rows = (flags & MBIK_OUT_SOLVED_ONLY) ? F.bones.size() : nb;
 	for (int i = 0; i < 2 && e == cudaSuccess; i++) {
 		e = cudaMalloc((void **)&st->local[i], n_poses * nb * 12 * sizeof(float));
 		if (e == cudaSuccess) {
 			e = cudaMalloc((void **)&st->d_targets[i], (np ? n_poses * np * 12 : 4) * sizeof(float));
 		}
 		if (e == cudaSuccess) {
-			e = cudaMalloc((void **)&st->d_out[i], n_poses * nb * 10 * sizeof(float));
+			e = cudaMalloc((void **)&st->d_out[i], (st->out_rows ? n_poses * st->out_rows * 10 : 4) * sizeof(float));
 		}
 		if (e == cudaSuccess) {
 			e = cudaMalloc((void **)&st->d_status[i], n_poses * sizeof(uint32_t));
@@ -1052,6 +1210,8 @@ int mbik_stream_submit(mbik_stream *st, const float *targets, float *out_pose, u
 	if (!st || (!targets && !st->rig->flat.pins.empty())) {
 		return fail(MBIK_ERR_INVALID_ARG, "stream/targets is NULL");
 	}
+	DeviceGuard guard;
+	NvtxRange range("mbik stream submit");
 	cudaError_t e = cudaSetDevice(st->device);
 	if (e != cudaSuccess) {
 		return cuda_fail(e, "cudaSetDevice");
@@ -1090,6 +1250,9 @@ int mbik_stream_submit(mbik_stream *st, const float *targets, float *out_pose, u
 	a.out_pose = st->d_out[slot];
 	a.out_local = st->local[st->cur ^ 1];
 	a.out_status = st->d_status[slot];
+	// The next frame seeds from what the skeleton hands back after this frame's write-back: position / rotation / scale
+	// recomposed (with the non-finite reset), not the raw IK-bone transforms -- see MBIK_LOCAL_RECOMPOSED.
+	a.out_flags = mbik::OUT_LOCAL_RECOMPOSED | ((st->flags & MBIK_OUT_SOLVED_ONLY) ? mbik::OUT_COMPACT : 0u);
 	e = mbik::launch_solve(a, st->rig->variant, st->sm_count, st->s_solve);
 	if (e != cudaSuccess) {
 		return cuda_fail(e, "kernel launch");
@@ -1098,7 +1261,7 @@ int mbik_stream_submit(mbik_stream *st, const float *targets, float *out_pose, u
 	st->cur ^= 1;
 	cudaStreamWaitEvent(st->s_down, st->ev_solved[slot], 0);
 	if (out_pose) {
-		cudaMemcpyAsync(out_pose, st->d_out[slot], n * nb * 10 * sizeof(float), cudaMemcpyDeviceToHost, st->s_down);
+		cudaMemcpyAsync(out_pose, st->d_out[slot], n * st->out_rows * 10 * sizeof(float), cudaMemcpyDeviceToHost, st->s_down);
 	}
 	if (out_status) {
 		cudaMemcpyAsync(out_status, st->d_status[slot], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st->s_down);
@@ -1117,6 +1280,7 @@ int mbik_stream_sync(mbik_stream *st) {
 	if (!st) {
 		return fail(MBIK_ERR_INVALID_ARG, "stream is NULL");
 	}
+	DeviceGuard guard;
 	cudaError_t e = cudaSetDevice(st->device);
 	if (e == cudaSuccess) {
 		e = cudaStreamSynchronize(st->s_up);
@@ -1141,6 +1305,8 @@ int mbik_stream_read_local(mbik_stream *st, float *out_local) {
 	if (rc != MBIK_OK) {
 		return rc;
 	}
+	DeviceGuard guard;
+	cudaSetDevice(st->device);
 	cudaError_t e = cudaMemcpy(out_local, st->local[st->cur], st->n_poses * (size_t)st->rig->flat.n_bones * 12 * sizeof(float), cudaMemcpyDeviceToHost);
 	if (e != cudaSuccess) {
 		return cuda_fail(e, "read_local");
@@ -1160,12 +1326,18 @@ struct DevBuf {
 } // namespace
 
 int mbik_stage_qcp(int32_t device, int32_t n, const float *moved, const float *target, const double *weight, int32_t translate, float *out7) {
+	return mbik_stage_qcp_newton(device, n, moved, target, weight, translate, 0, out7);
+}
+
+int mbik_stage_qcp_newton(int32_t device, int32_t n, const float *moved, const float *target, const double *weight, int32_t translate,
+		int32_t newton_iters, float *out7) {
 	if (n < 0 || !out7 || (n > 0 && (!moved || !target || !weight))) {
 		return fail(MBIK_ERR_INVALID_ARG, "NULL argument");
 	}
 	if (mbik_device_count() <= 0) {
 		return fail(MBIK_ERR_NO_DEVICE, "no CUDA device: mbik has no CPU fallback");
 	}
+	DeviceGuard guard;
 	cudaError_t e = cudaSetDevice(device);
 	DevBuf dm, dt, dw, dout;
 	if (e == cudaSuccess) e = dm.alloc(sizeof(float) * 3 * n);
@@ -1175,7 +1347,7 @@ int mbik_stage_qcp(int32_t device, int32_t n, const float *moved, const float *t
 	if (e == cudaSuccess && n) e = cudaMemcpy(dm.p, moved, sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess && n) e = cudaMemcpy(dt.p, target, sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess && n) e = cudaMemcpy(dw.p, weight, sizeof(double) * n, cudaMemcpyHostToDevice);
-	if (e == cudaSuccess) e = mbik::launch_stage_qcp(n, (const float *)dm.p, (const float *)dt.p, (const double *)dw.p, translate, (float *)dout.p);
+	if (e == cudaSuccess) e = mbik::launch_stage_qcp(n, (const float *)dm.p, (const float *)dt.p, (const double *)dw.p, translate, newton_iters > 0 ? newton_iters : 0, (float *)dout.p);
 	if (e == cudaSuccess) e = cudaMemcpy(out7, dout.p, sizeof(float) * 7, cudaMemcpyDeviceToHost);
 	return e == cudaSuccess ? MBIK_OK : cuda_fail(e, "mbik_stage_qcp");
 }
@@ -1190,6 +1362,7 @@ int mbik_stage_clamp(int32_t device, int32_t n, const float *quats, const double
 	if (mbik_device_count() <= 0) {
 		return fail(MBIK_ERR_NO_DEVICE, "no CUDA device: mbik has no CPU fallback");
 	}
+	DeviceGuard guard;
 	cudaError_t e = cudaSetDevice(device);
 	DevBuf dq, dc, dout;
 	if (e == cudaSuccess) e = dq.alloc(sizeof(float) * 4 * n);
@@ -1225,6 +1398,7 @@ int mbik_stage_point_in_limits(mbik_rig *rig, int32_t device, int32_t bone, int3
 	if (mbik_device_count() <= 0) {
 		return fail(MBIK_ERR_NO_DEVICE, "no CUDA device: mbik has no CPU fallback");
 	}
+	DeviceGuard guard;
 	cudaError_t e = cudaSetDevice(device);
 	DevBuf dc, dp, dout;
 	if (e == cudaSuccess) e = dc.alloc(sizeof(mbik::BlobCone) * S->cone_cnt);
@@ -1265,6 +1439,7 @@ int mbik_last_kernel_ms(mbik_rig *rig, int32_t device, float *out_ms) {
 	if (it == rig->devices.end() || !it->second->timed) {
 		return fail(MBIK_ERR_INVALID_ARG, "no launch recorded on that device");
 	}
+	DeviceGuard guard;
 	cudaSetDevice(device);
 	cudaError_t e = cudaEventSynchronize(it->second->ev_stop);
 	if (e == cudaSuccess) {

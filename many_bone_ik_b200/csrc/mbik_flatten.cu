@@ -204,6 +204,17 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 		R.error = "rig description needs n_bones > 0, parent[] and rest_local[]";
 		return MBIK_ERR_INVALID_ARG;
 	}
+	if (d->n_pins < 0 || d->n_constraints < 0 || d->n_bone_damp < 0) {
+		R.error = "negative table count";
+		return MBIK_ERR_INVALID_ARG;
+	}
+	for (int ci = 0; ci < d->n_constraints && d->constraints; ci++) {
+		const mbik_constraint_desc &cd = d->constraints[ci];
+		if (cd.n_cones < 0 || cd.cone_offset < 0 || (cd.n_cones > 0 && !d->cones)) {
+			R.error = "constraint row " + std::to_string(ci) + ": negative n_cones / cone_offset, or cones is NULL";
+			return MBIK_ERR_INVALID_ARG;
+		}
+	}
 	if ((d->n_pins > 0 && !d->pins) || (d->n_constraints > 0 && !d->constraints) || (d->n_bone_damp > 0 && !d->bone_damp)) {
 		R.error = "null table with non-zero count";
 		return MBIK_ERR_INVALID_ARG;
@@ -1167,6 +1178,10 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	hdr.sp_team_headings = R.sp_team_headings;
 	std::vector<float> rest(nb * 12);
 	memcpy(rest.data(), d->rest_local, sizeof(float) * 12 * nb);
+	std::vector<int16_t> list_row(ns, 0); // t index -> position in bone_list
+	for (size_t i = 0; i < R.bone_order.size(); i++) {
+		list_row[(size_t)R.t_of_bone[R.bone_order[i]]] = (int16_t)i;
+	}
 	auto assemble = [&](bool tail_layout) {
 		R.blob.clear();
 		R.blob.resize(sizeof(BlobHeader), 0);
@@ -1179,6 +1194,7 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 		hdr.off_cones = append_section(R.blob, R.cones);
 		hdr.off_pass = append_section(R.blob, R.pass);
 		hdr.off_chain = append_section(R.blob, R.chain);
+		hdr.off_list_row = append_section(R.blob, list_row);
 		hdr.off_rest = append_section(R.blob, rest);
 		hdr.off_sched = append_section(R.blob, R.sched);
 		hdr.resident_bytes = hdr.off_sched; // tail layout: nothing from here on is staged into shared memory

@@ -70,12 +70,85 @@ int segment_parallel_choice(const SolveArgs &a, int variant, int sm_count) {
 }
 bool uses_segment_parallel(const SolveArgs &a, int variant, int sm_count) { return segment_parallel_choice(a, variant, sm_count) != 0; }
 
-cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStream_t stream) {
+// shared-memory scratch (segment chain + walk stack columns) a CTA of `threads` threads of `variant` asks for next to the
+// rig blob -- the rule of ScratchStride in mbik_kernel_body.cuh
+static size_t scratch_smem_bytes(int variant, int threads) {
+	const size_t bytes = (size_t)(kVariants[variant][1] + kVariants[variant][2]) * 12 * (size_t)threads * sizeof(float);
+	return bytes <= 150 * 1024 ? bytes : 0;
+}
+static bool cta_fits(const SolveArgs &a, int variant, int threads) {
+	const size_t scr = scratch_smem_bytes(variant, threads);
+	return scr == 0 ? (size_t)a.blob_bytes <= 227 * 1024 : (((size_t)a.blob_bytes + 127) & ~(size_t)127) + scr <= 227 * 1024;
+}
+
+int throughput_block_threads(const SolveArgs &a, int variant, int sm_count) {
+	if (a.stabilize) {
+		return 0;
+	}
+	static const int forced = getenv("MBIK_THREADS") ? atoi(getenv("MBIK_THREADS")) : 0; // tuning knob
+	if (forced > 0) {
+		return forced;
+	}
 	if (a.limit_table) {
-		// per-pose limit sets: thread-per-pose mapping only (mbik_kernel_l*.cu); the C ABI rejects stabilised rigs earlier
-		if (a.stabilize || !a.limit_index || a.n_limit_sets < 1) {
-			return cudaErrorInvalidValue;
+		return kBlockThreads; // limit-set instantiations exist at the full CTA size only
+	}
+	// Small batches: one CTA per SM with as few warps as cover the batch (a 4096-pose batch runs as 128 one-warp CTAs on
+	// 128 SMs instead of 8 sixteen-warp CTAs on 8 SMs) -- latency, not throughput.  Sizes whose shared-memory scratch does
+	// not fit beside this rig's blob are skipped (rigs with many cones / unsolved bones on the 64-bone variants).
+	const int cands_small[] = { 32, 64, 128, 256 }, cands_large[] = { 32, 128 }; // instantiated CTA sizes per variant
+	const int *cands = variant <= 1 ? cands_small : cands_large;
+	const int n_cands = variant <= 1 ? 4 : 2;
+	for (int i = 0; i < n_cands; i++) {
+		if ((a.n_poses + cands[i] - 1) / cands[i] <= (size_t)sm_count && cta_fits(a, variant, cands[i])) {
+			return cands[i];
 		}
+	}
+	// Large batches: every CTA is one SM's share of a wave (128 registers per thread: one CTA per SM), so a batch of
+	// 1.73 waves of 512-thread CTAs pays for 2.  Wave-balanced size: the smallest instantiated CTA with which the same
+	// number of waves covers the batch -- 131 072 poses on 148 SMs run as 2 full waves of 448 threads instead of one
+	// full and one 73 % wave of 512 (BASELINE config 3: a 1M batch sharded over 8 GPUs).
+	if (variant == 0 || variant == 1 || variant == 3) {
+		static const bool balanced = !(getenv("MBIK_WAVE_BALANCE") && atoi(getenv("MBIK_WAVE_BALANCE")) == 0);
+		if (balanced) {
+			const size_t per_wave = (size_t)sm_count * kBlockThreads;
+			const size_t waves = (a.n_poses + per_wave - 1) / per_wave;
+			const size_t need = (a.n_poses + (size_t)sm_count * waves - 1) / ((size_t)sm_count * waves);
+			const int sizes[] = { 384, 448 };
+			for (int t : sizes) {
+				if ((size_t)t >= need && cta_fits(a, variant, t)) {
+					return t;
+				}
+			}
+		}
+	}
+	return kBlockThreads;
+}
+
+cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStream_t stream) {
+	if (variant < 0 || variant >= kNumVariants) {
+		return cudaErrorInvalidValue;
+	}
+	const bool lims = a.limit_table != nullptr;
+	if (lims && (!a.limit_index || a.n_limit_sets < 1)) {
+		return cudaErrorInvalidValue;
+	}
+	// segment-parallel mapping with per-pose limit sets: compiled without stabilisation only
+	const int sp = (lims && a.stabilize) ? 0 : segment_parallel_choice(a, variant, sm_count);
+	if (sp != 0) {
+		switch (variant) {
+			case 0:
+				return lims ? launch_sp_lims_v0(a, sp, stream) : launch_sp_v0(a, sp, stream);
+			case 1:
+				return lims ? launch_sp_lims_v1(a, sp, stream) : launch_sp_v1(a, sp, stream);
+			case 3:
+				return lims ? launch_sp_lims_v3(a, sp, stream) : launch_sp_v3(a, sp, stream);
+			case 4:
+				return lims ? launch_sp_lims_v4(a, sp, stream) : launch_sp_v4(a, sp, stream);
+			default:
+				break;
+		}
+	}
+	if (lims) {
 		switch (variant) {
 			case 0:
 				return launch_lims_v0(a, stream);
@@ -87,48 +160,11 @@ cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStre
 				return launch_lims_v3(a, stream);
 			case 4:
 				return launch_lims_v4(a, stream);
-			case 5:
+			default:
 				return launch_lims_v5(a, stream);
-			default:
-				return cudaErrorInvalidValue;
 		}
 	}
-	const int sp = segment_parallel_choice(a, variant, sm_count);
-	if (sp != 0) {
-		switch (variant) {
-			case 0:
-				return launch_sp_v0(a, sp, stream);
-			case 1:
-				return launch_sp_v1(a, sp, stream);
-			case 3:
-				return launch_sp_v3(a, sp, stream);
-			case 4:
-				return launch_sp_v4(a, sp, stream);
-			default:
-				break;
-		}
-	}
-	int threads = kBlockThreads;
-	if (a.stabilize) {
-		threads = 0;
-	} else {
-		// Small batches: one CTA per SM with as few warps as cover the batch (a 4096-pose batch runs as 128
-		// one-warp CTAs on 128 SMs instead of 8 sixteen-warp CTAs on 8 SMs) -- latency, not throughput.
-		static const int forced = getenv("MBIK_THREADS") ? atoi(getenv("MBIK_THREADS")) : 0; // tuning knob
-		if (forced > 0) {
-			threads = forced;
-		} else {
-			const int cands_small[] = { 32, 64, 128, 256 }, cands_large[] = { 32, 128 }; // instantiated CTA sizes per variant
-			const int *cands = variant <= 1 ? cands_small : cands_large;
-			const int n_cands = variant <= 1 ? 4 : 2;
-			for (int i = 0; i < n_cands; i++) {
-				if ((a.n_poses + cands[i] - 1) / cands[i] <= (size_t)sm_count) {
-					threads = cands[i];
-					break;
-				}
-			}
-		}
-	}
+	const int threads = throughput_block_threads(a, variant, sm_count);
 	switch (variant) {
 		case 0:
 			return launch_v0(a, threads, stream);
@@ -140,10 +176,8 @@ cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStre
 			return launch_v3(a, threads, stream);
 		case 4:
 			return launch_v4(a, threads, stream);
-		case 5:
-			return launch_v5(a, threads, stream);
 		default:
-			return cudaErrorInvalidValue;
+			return launch_v5(a, threads, stream);
 	}
 }
 

@@ -36,6 +36,12 @@ struct SolveArgs {
 	const int32_t *limit_index = nullptr;
 	uint32_t limit_stride = 0;
 	int32_t n_limit_sets = 0;
+	int32_t newton_iters = 0;  // mbik_solve_params::newton_iters (0 = the reference's QCP: no eigenvalue refinement)
+	uint32_t out_flags = 0;    // OUT_* below
+};
+enum : uint32_t {
+	OUT_COMPACT = 1u,          // out_pose = [n_poses][n_solved][10] in bone_list order (MBIK_OUT_SOLVED_ONLY)
+	OUT_LOCAL_RECOMPOSED = 2u, // out_local = Skeleton3D::get_bone_pose() after the write-back (MBIK_LOCAL_RECOMPOSED)
 };
 
 // Compiled size variants {solved-bone capacity, longest segment, walk-stack depth}; per-pose thread-local state is
@@ -56,7 +62,7 @@ cudaError_t launch_v3(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v4(const SolveArgs &a, int threads, cudaStream_t stream);
 cudaError_t launch_v5(const SolveArgs &a, int threads, cudaStream_t stream);
 
-// per-pose limit sets (mbik_kernel_lims.cu): thread-per-pose mapping, 512-thread CTAs, no stabilisation
+// per-pose limit sets (mbik_kernel_l*.cu): thread-per-pose mapping, 512-thread CTAs (stabilisation: its own instantiation)
 cudaError_t launch_lims_v0(const SolveArgs &a, cudaStream_t stream);
 cudaError_t launch_lims_v1(const SolveArgs &a, cudaStream_t stream);
 cudaError_t launch_lims_v2(const SolveArgs &a, cudaStream_t stream);
@@ -70,6 +76,13 @@ cudaError_t launch_sp_v0(const SolveArgs &a, int min_groups_per_sm, cudaStream_t
 cudaError_t launch_sp_v1(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
 cudaError_t launch_sp_v3(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
 cudaError_t launch_sp_v4(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
+// ... with per-pose limit sets (mbik_kernel_l*.cu)
+cudaError_t launch_sp_lims_v0(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
+cudaError_t launch_sp_lims_v1(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
+cudaError_t launch_sp_lims_v3(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
+cudaError_t launch_sp_lims_v4(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream);
+// CTA size launch_solve picks for the one-thread-per-pose mapping (0 = the stabilisation instantiation); exported for tests
+int throughput_block_threads(const SolveArgs &a, int variant, int sm_count);
 // shared memory of one 32-pose group: rig blob + the group's local poses (n_solved x 12 words x 32 lanes) + team buffers
 inline size_t sp_smem_bytes(const SolveArgs &a) {
 	return (((size_t)a.blob_bytes + 127) & ~(size_t)127) + (size_t)a.n_solved * 12 * 32 * sizeof(float) + (size_t)a.sp_team_bytes;
@@ -79,7 +92,7 @@ bool uses_segment_parallel(const SolveArgs &a, int variant, int sm_count);
 
 // stage probes (mbik_selftest.cu): device pointers in, device pointers out
 struct BlobCone;
-cudaError_t launch_stage_qcp(int n, const float *d_moved, const float *d_target, const double *d_weight, int translate, float *d_out7);
+cudaError_t launch_stage_qcp(int n, const float *d_moved, const float *d_target, const double *d_weight, int translate, int newton_iters, float *d_out7);
 cudaError_t launch_stage_clamp(int n, const float *d_quats, const double *d_cos_half, float *d_out);
 cudaError_t launch_stage_point_in_limits(const BlobCone *d_cones, int n_cones, int n, const float *d_points, float *d_out);
 

@@ -55,12 +55,18 @@
 // (profiles/run_residency.py: 2 x 128 threads per SM 93 ms, 1 x 128 122 ms): the kernel then runs out of warps to hide
 // the dependent FP32 chains faster than the L2 hit rate recovers.
 // see solve_body: 0 = CTA-wide barrier per bone-step; 1..4 = cohort ring, released after (1) the bone's global, (2) the
-// heading walk, (3) the damped rotation, (4) the pose update before the snaps
+// heading walk, (3) the damped rotation, (4) the pose update before the snaps.  Measured (round 2, humanoid22, 2^20 poses,
+// profiles/r2_exp_stagger_640.log): barrier 31.84 ms; ring 45.2 / 75.4 / 78.7 / 84.5 ms for release points 1..4 -- the
+// further apart the cohorts run in the step body the slower, already at ~100 instructions of distance: instruction
+// delivery for this ~150 KB kernel only works when all warps of the SM fetch the same lines.  Stays 0.
 #ifndef MBIK_STAGGER
 #define MBIK_STAGGER 0
 #endif
+#ifndef MBIK_SCRATCH_LIMIT_KB
+#define MBIK_SCRATCH_LIMIT_KB 150
+#endif
 #ifndef MBIK_SKIP_TO
-#define MBIK_SKIP_TO 0
+#define MBIK_SKIP_TO 1
 #endif
 #ifndef MBIK_PREFETCH_DIST
 #define MBIK_PREFETCH_DIST 0
@@ -282,9 +288,51 @@ __device__ __forceinline__ void qcp_accumulate(QcpSums &s, V3 target, V3 moved, 
 	s.zy = r_add(s.zy, (double)py);
 	s.zz = r_add(s.zz, (double)r_mul(wc1.z, moved.z));
 }
+// mbik_solve_params::newton_iters > 0 only (never on the parity path: the reference uses the upper bound (Gt + Gm) / 2
+// as the eigenvalue, src/math/qcp.cpp:205,215).  Newton-Raphson on the characteristic polynomial of the 4x4 key matrix,
+// x^4 + C2 x^2 + C1 x + C0 (Theobald 2005), started from that bound; stops early at the reference's evaluation
+// precision (1e-11, src/math/qcp.h).  Out of line: cold, and the default path must not pay registers for it.
+static __device__ __noinline__ double qcp_newton_eigenvalue(const QcpSums *sp, double x, int iters) {
+	const QcpSums s = *sp;
+	const double xx2 = s.xx * s.xx, yy2 = s.yy * s.yy, zz2 = s.zz * s.zz;
+	const double xy2 = s.xy * s.xy, yz2 = s.yz * s.yz, xz2 = s.xz * s.xz;
+	const double yx2 = s.yx * s.yx, zy2 = s.zy * s.zy, zx2 = s.zx * s.zx;
+	const double syz_szy_m_syy_szz2 = 2.0 * (s.yz * s.zy - s.yy * s.zz);
+	const double sxx2syy2szz2syz2szy2 = yy2 + zz2 - xx2 + yz2 + zy2;
+	const double c2 = -2.0 * (xx2 + yy2 + zz2 + xy2 + yx2 + xz2 + zx2 + yz2 + zy2);
+	const double c1 = 8.0 * (s.xx * s.yz * s.zy + s.yy * s.zx * s.xz + s.zz * s.xy * s.yx - s.xx * s.yy * s.zz - s.yz * s.zx * s.xy - s.zy * s.yx * s.xz);
+	const double xz_p_zx = s.xz + s.zx, yz_p_zy = s.yz + s.zy, xy_p_yx = s.xy + s.yx;
+	const double yz_m_zy = s.yz - s.zy, xz_m_zx = s.xz - s.zx, xy_m_yx = s.xy - s.yx;
+	const double xx_p_yy = s.xx + s.yy, xx_m_yy = s.xx - s.yy;
+	const double sxy2sxz2syx2szx2 = xy2 + xz2 - yx2 - zx2;
+	const double c0 = sxy2sxz2syx2szx2 * sxy2sxz2syx2szx2 + (sxx2syy2szz2syz2szy2 + syz_szy_m_syy_szz2) * (sxx2syy2szz2syz2szy2 - syz_szy_m_syy_szz2) +
+			(-(xz_p_zx) * (yz_m_zy) + (xy_m_yx) * (xx_m_yy - s.zz)) * (-(xz_m_zx) * (yz_p_zy) + (xy_m_yx) * (xx_m_yy + s.zz)) +
+			(-(xz_p_zx) * (yz_p_zy) - (xy_p_yx) * (xx_p_yy - s.zz)) * (-(xz_m_zx) * (yz_m_zy) - (xy_p_yx) * (xx_p_yy + s.zz)) +
+			(+(xy_p_yx) * (yz_p_zy) + (xz_p_zx) * (xx_m_yy + s.zz)) * (-(xy_m_yx) * (yz_m_zy) + (xz_p_zx) * (xx_p_yy + s.zz)) +
+			(+(xy_p_yx) * (yz_m_zy) + (xz_m_zx) * (xx_m_yy - s.zz)) * (-(xy_m_yx) * (yz_p_zy) + (xz_m_zx) * (xx_p_yy - s.zz));
+	for (int i = 0; i < iters; i++) {
+		const double old = x;
+		const double x2 = x * x;
+		const double b = (x2 + c2) * x;
+		const double a = b + c1;
+		const double den = 2.0 * x2 * x + b + a;
+		if (den == 0.0) {
+			break;
+		}
+		x -= (a * x + c0) / den;
+		if (fabs(x - old) < fabs(1e-11 * x)) {
+			break;
+		}
+	}
+	return x;
+}
 // calculate_rotation, general branch (:80-123)
-__device__ __forceinline__ Q4 qcp_rotation(const QcpSums &s) {
+__device__ __forceinline__ Q4 qcp_rotation(const QcpSums &s, int newton_iters = 0) {
 	double max_eig = r_mul(r_add(s.ss1, s.ss2), 0.5);
+	if (newton_iters > 0) {
+		const QcpSums copy = s;
+		max_eig = qcp_newton_eigenvalue(&copy, max_eig, newton_iters);
+	}
 	double xz_p_zx = r_add(s.xz, s.zx), yz_p_zy = r_add(s.yz, s.zy), xy_p_yx = r_add(s.xy, s.yx);
 	double yz_m_zy = r_sub(s.yz, s.zy), xz_m_zx = r_sub(s.xz, s.zx), xy_m_yx = r_sub(s.xy, s.yx);
 	double xx_p_yy = r_add(s.xx, s.yy), xx_m_yy = r_sub(s.xx, s.yy);
@@ -517,7 +565,11 @@ __device__ __forceinline__ M3 damp_and_slerp0(Q4 q, double cos_half_damp, const 
 }
 
 // IKBone3D::set_skeleton_bone_pose (src/ik_bone_3d.cpp:170-179): position, rotation quaternion, scale
-__device__ __forceinline__ uint32_t write_bone_pose(const X34 &local, float *out10) {
+// recomposed != nullptr: also return the pose Skeleton3D::get_bone_pose() hands back once the three values are in the
+// skeleton -- Transform3D(Basis(rotation, scale), position), Basis::set_quaternion_scale = Basis(q) * diag(scale) (engine
+// core/math/basis.cpp, scene/3d/skeleton_3d.cpp update_pose_cache) -- which is what the next frame of the reference
+// re-seeds its IK bones from (src/many_bone_ik_3d.cpp:1084, :91-102, src/ik_bone_3d.cpp:161-168).
+__device__ __forceinline__ uint32_t write_bone_pose(const X34 &local, float *out10, X34 *recomposed = nullptr) {
 	uint32_t st = 0;
 	M3 b = local.b;
 	if (!m3_is_finite(b)) {
@@ -529,6 +581,15 @@ __device__ __forceinline__ uint32_t write_bone_pose(const X34 &local, float *out
 	float sgn = det > 0.0f ? 1.0f : (det < 0.0f ? -1.0f : 0.0f);
 	V3 sc = v3(vlen(m3_col(b, 0)), vlen(m3_col(b, 1)), vlen(m3_col(b, 2)));
 	sc = vmuls(sc, sgn);
+	if (recomposed) {
+		M3 dg = m3_identity();
+		dg.m[0] = sc.x; dg.m[4] = sc.y; dg.m[8] = sc.z;
+		recomposed->b = m3_mul(m3_from_quat(q), dg);
+		recomposed->o = local.o;
+	}
+	if (!out10) {
+		return st;
+	}
 	// streaming (evict-first) stores: the results are not read again, and must not push the per-pose state that
 	// lives in thread-local memory out of L2.  40-byte records are 8-byte aligned -> float2 stores.
 	float2 *o2 = reinterpret_cast<float2 *>(out10);
@@ -991,7 +1052,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					}
 				}
 				}
-				q = (S.n_headings == 1) ? qcp_rotation_single(A.csum_m, A.csum_t) : qcp_rotation(A.sums);
+				q = (S.n_headings == 1) ? qcp_rotation_single(A.csum_m, A.csum_t) : qcp_rotation(A.sums, a.newton_iters);
 				// translation = target_center - moved_center (src/math/qcp.cpp:135-137); the centres are the exact
 				// negations of neg_tc / neg_mc (zero when the segment does not translate)
 				translation = vsub(vneg(A.neg_tc), vneg(A.neg_mc));
@@ -1160,22 +1221,31 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	}
 
 	// write-back: ManyBoneIK3D::_update_skeleton_bones_transform (src/many_bone_ik_3d.cpp:104-116)
+	// OUT_COMPACT: out_pose holds only the bones of bone_list, [n_solved][10] per pose in bone_list order -- exactly the bones
+	// IKBone3D::set_skeleton_bone_pose writes (src/many_bone_ik_3d.cpp:104-116); the other bones are not the solver's to write.
+	// OUT_LOCAL_RECOMPOSED: out_local holds what Skeleton3D::get_bone_pose() returns after the write-back instead of the raw
+	// IK-bone transforms (see write_bone_pose); bones outside bone_list keep their start pose either way.
 	uint32_t status = 0;
-	float *my_out = a.out_pose + pose * (size_t)n_bones * 10;
+	const bool compact = (a.out_flags & OUT_COMPACT) != 0, recompose = (a.out_flags & OUT_LOCAL_RECOMPOSED) != 0;
+	const int16_t *list_row = reinterpret_cast<const int16_t *>(smem + H.off_list_row);
+	float *my_out = a.out_pose ? a.out_pose + pose * (size_t)(compact ? ns : n_bones) * 10 : nullptr;
 	float *my_loc = a.out_local ? a.out_local + pose * (size_t)n_bones * 12 : nullptr;
 	if (live) {
 		for (int t = role; t < ns; t += sp_roles) {
 			int sb = bones[t].skel_bone;
 			X34 l = L.ld(t);
-			status |= write_bone_pose(l, my_out + (size_t)sb * 10);
+			X34 rc;
+			status |= write_bone_pose(l, my_out ? my_out + (size_t)(compact ? (int)list_row[t] : sb) * 10 : nullptr, (my_loc && recompose) ? &rc : nullptr);
 			if (my_loc) {
-				stg_x34(my_loc + (size_t)sb * 12, l);
+				stg_x34(my_loc + (size_t)sb * 12, recompose ? rc : l);
 			}
 		}
 		for (int k = role; k < H.n_pass; k += sp_roles) {
 			int sb = pass[k].skel_bone;
 			X34 l = my_start ? ldg_x34(my_start + (size_t)sb * 12) : ld_x34(rest, sb);
-			status |= write_bone_pose(l, my_out + (size_t)sb * 10);
+			if (!compact) {
+				status |= write_bone_pose(l, my_out ? my_out + (size_t)sb * 10 : nullptr);
+			}
 			if (my_loc) {
 				stg_x34(my_loc + (size_t)sb * 12, l);
 			}
@@ -1207,20 +1277,20 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 // shared-memory scratch is used when it fits beside the largest rig blob (200 KiB budget checked at rig creation)
 template <int NSEG, int NSTK, int THREADS>
 struct ScratchStride {
-	static constexpr int value = ((NSEG + NSTK) * 12 * THREADS * 4 <= 150 * 1024) ? THREADS : 0;
+	static constexpr int value = ((NSEG + NSTK) * 12 * THREADS * 4 <= MBIK_SCRATCH_LIMIT_KB * 1024) ? THREADS : 0;
 };
 template <int NB, int NSEG, int NSTK, int THREADS, bool STAB, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) mbik_solve_kernel(SolveArgs a) {
 	solve_body<NB, NSEG, NSTK, STAB, ScratchStride<NSEG, NSTK, THREADS>::value>(a);
 }
-template <int NB, int NSEG, int NSTK, int THREADS>
+template <int NB, int NSEG, int NSTK, int THREADS, bool STAB>
 __global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel_lims(SolveArgs a) {
-	solve_body<NB, NSEG, NSTK, false, ScratchStride<NSEG, NSTK, THREADS>::value, false, true>(a);
+	solve_body<NB, NSEG, NSTK, STAB, ScratchStride<NSEG, NSTK, THREADS>::value, false, true>(a);
 }
 // ---------------------------------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------------------------------
-template <int NB, int NSEG, int NSTK, int THREADS>
+template <int NB, int NSEG, int NSTK, int THREADS, bool STAB = false>
 static cudaError_t launch_variant_lims(const SolveArgs &a, cudaStream_t stream) {
 	size_t smem = a.blob_bytes;
 	if (ScratchStride<NSEG, NSTK, THREADS>::value > 0) {
@@ -1229,12 +1299,12 @@ static cudaError_t launch_variant_lims(const SolveArgs &a, cudaStream_t stream) 
 			return cudaErrorInvalidValue;
 		}
 	}
-	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel_lims<NB, NSEG, NSTK, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel_lims<NB, NSEG, NSTK, THREADS, STAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) {
 		return e;
 	}
 	unsigned grid = (unsigned)((a.n_poses + THREADS - 1) / THREADS);
-	mbik_solve_kernel_lims<NB, NSEG, NSTK, THREADS><<<grid, THREADS, smem, stream>>>(a);
+	mbik_solve_kernel_lims<NB, NSEG, NSTK, THREADS, STAB><<<grid, THREADS, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 template <int NB, int NSEG, int NSTK, int THREADS, bool STAB = false, int MINB = 1>
@@ -1243,7 +1313,7 @@ static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 	if (ScratchStride<NSEG, NSTK, THREADS>::value > 0) {
 		smem = ((smem + 127) & ~(size_t)127) + (size_t)(NSEG + NSTK) * 12 * THREADS * sizeof(float);
 		if (smem > 227 * 1024) {
-			return cudaErrorInvalidValue; // cannot happen: blob <= 64 KiB for these variants (checked at rig creation)
+			return cudaErrorInvalidValue; // launch_solve only picks CTA sizes whose scratch fits beside the blob (scratch_smem_bytes)
 		}
 	}
 	// tuning knob: pad the dynamic shared memory request to cap how many CTAs of this size share an SM
@@ -1269,17 +1339,17 @@ static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------
 // segment-parallel (small-batch) kernel: one CTA = one group of 32 poses x sp_roles warps
 // ---------------------------------------------------------------------------------------------------
-template <int NB, int NSEG, int NSTK, bool STAB, int MINB>
+template <int NB, int NSEG, int NSTK, bool STAB, int MINB, bool LIMS>
 __global__ void __launch_bounds__(32 * kMaxSpRoles, MINB) mbik_solve_kernel_sp(SolveArgs a) {
-	solve_body<NB, NSEG, NSTK, STAB, 0, true>(a);
+	solve_body<NB, NSEG, NSTK, STAB, 0, true, LIMS>(a);
 }
-template <int NB, int NSEG, int NSTK, bool STAB, int MINB>
+template <int NB, int NSEG, int NSTK, bool STAB, int MINB, bool LIMS>
 static cudaError_t launch_variant_sp_m(const SolveArgs &a, cudaStream_t stream) {
 	const size_t smem = sp_smem_bytes(a);
 	if (smem > 227 * 1024 || a.sp_roles < 1 || a.sp_roles > kMaxSpRoles) {
 		return cudaErrorInvalidValue; // launch_solve checks both before choosing this mapping
 	}
-	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB, LIMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) {
 		return e;
 	}
@@ -1291,18 +1361,18 @@ static cudaError_t launch_variant_sp_m(const SolveArgs &a, cudaStream_t stream) 
 		const size_t resident = by_regs < by_smem ? by_regs : by_smem;
 		int pct = (int)((resident * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
 		pct = pct > 100 ? 100 : pct;
-		cudaFuncSetAttribute(mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB, LIMS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 	}
 	unsigned grid = (unsigned)((a.n_poses + 31) / 32);
-	mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB><<<grid, 32 * a.sp_roles, smem, stream>>>(a);
+	mbik_solve_kernel_sp<NB, NSEG, NSTK, STAB, MINB, LIMS><<<grid, 32 * a.sp_roles, smem, stream>>>(a);
 	return cudaGetLastError();
 }
-template <int NB, int NSEG, int NSTK, bool STAB>
+template <int NB, int NSEG, int NSTK, bool STAB, bool LIMS = false>
 static cudaError_t launch_variant_sp(const SolveArgs &a, int minb, cudaStream_t stream) {
 	if (minb == 2) {
-		return launch_variant_sp_m<NB, NSEG, NSTK, STAB, 2>(a, stream);
+		return launch_variant_sp_m<NB, NSEG, NSTK, STAB, 2, LIMS>(a, stream);
 	}
-	return launch_variant_sp_m<NB, NSEG, NSTK, STAB, 1>(a, stream);
+	return launch_variant_sp_m<NB, NSEG, NSTK, STAB, 1, LIMS>(a, stream);
 }
 
 } // namespace mbik

@@ -5,7 +5,15 @@
 namespace mbik {
 
 cudaError_t launch_lims_v1(const SolveArgs &a, cudaStream_t stream) {
+	if (a.stabilize) {
+		return launch_variant_lims<32, 8, 4, kStabBlockThreads, true>(a, stream);
+	}
 	return launch_variant_lims<32, 8, 4, kBlockThreads>(a, stream);
+}
+
+// segment-parallel (small-batch) mapping of the same: one 32-pose group per CTA, one warp per concurrently solvable segment
+cudaError_t launch_sp_lims_v1(const SolveArgs &a, int min_groups_per_sm, cudaStream_t stream) {
+	return launch_variant_sp<32, 8, 4, false, true>(a, min_groups_per_sm, stream);
 }
 
 } // namespace mbik

@@ -10,6 +10,9 @@
 namespace mbik {
 
 cudaError_t launch_lims_v2(const SolveArgs &a, cudaStream_t stream) {
+	if (a.stabilize) {
+		return launch_variant_lims<64, 8, 1, kStabBlockThreads, true>(a, stream);
+	}
 	return launch_variant_lims<64, 8, 1, kBlockThreads>(a, stream);
 }
 

@@ -10,6 +10,9 @@
 namespace mbik {
 
 cudaError_t launch_lims_v5(const SolveArgs &a, cudaStream_t stream) {
+	if (a.stabilize) {
+		return launch_variant_lims<256, 256, 32, kStabBlockThreads, true>(a, stream);
+	}
 	return launch_variant_lims<256, 256, 32, kBlockThreads>(a, stream);
 }
 

@@ -1,6 +1,11 @@
 // mbik_kernel_v0.cu -- instantiations of the solve kernel for the size variant {20 solved bones, segment 4, stack 2}.
 #include "mbik_kernel_body.cuh"
 
+// experiment knob (profiles/build_variant.py): CTA size of the large-batch instantiation
+#ifndef MBIK_V0_BIG
+#define MBIK_V0_BIG 512
+#endif
+
 namespace mbik {
 
 cudaError_t launch_v0(const SolveArgs &a, int threads, cudaStream_t stream) {
@@ -16,7 +21,11 @@ cudaError_t launch_v0(const SolveArgs &a, int threads, cudaStream_t stream) {
 		case 256:
 			return launch_variant<20, 4, 2, 256>(a, stream);
 		case 512:
-			return launch_variant<20, 4, 2, 512>(a, stream);
+			return launch_variant<20, 4, 2, MBIK_V0_BIG>(a, stream);
+		case 384: // wave-balanced sizes for large batches (launch_solve): the last wave of CTAs is as full as the others
+			return launch_variant<20, 4, 2, 384>(a, stream);
+		case 448:
+			return launch_variant<20, 4, 2, 448>(a, stream);
 		default:
 			return launch_variant<20, 4, 2, kBlockThreads>(a, stream);
 	}

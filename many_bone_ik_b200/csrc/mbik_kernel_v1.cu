@@ -15,6 +15,10 @@ cudaError_t launch_v1(const SolveArgs &a, int threads, cudaStream_t stream) {
 			return launch_variant<32, 8, 4, 128>(a, stream);
 		case 256:
 			return launch_variant<32, 8, 4, 256>(a, stream);
+		case 384: // wave-balanced sizes for large batches (launch_solve): the last wave of CTAs is as full as the others
+			return launch_variant<32, 8, 4, 384>(a, stream);
+		case 448:
+			return launch_variant<32, 8, 4, 448>(a, stream);
 		default:
 			return launch_variant<32, 8, 4, kBlockThreads>(a, stream);
 	}

@@ -208,7 +208,7 @@ __global__ void f2_cases(unsigned long long *bad, unsigned long long *n, uint32_
 	atomicAdd(n, cnt);
 }
 
-__global__ void stage_qcp_kernel(int n, const float *moved, const float *target, const double *weight, int translate, float *out7) {
+__global__ void stage_qcp_kernel(int n, const float *moved, const float *target, const double *weight, int translate, int newton_iters, float *out7) {
 	if (threadIdx.x != 0 || blockIdx.x != 0) {
 		return;
 	}
@@ -236,7 +236,7 @@ __global__ void stage_qcp_kernel(int n, const float *moved, const float *target,
 			A.neg_tc = vmuls(target_center, -1.0f);
 		}
 	}
-	Q4 q = (n == 1) ? qcp_rotation_single(A.csum_m, A.csum_t) : qcp_rotation(A.sums);
+	Q4 q = (n == 1) ? qcp_rotation_single(A.csum_m, A.csum_t) : qcp_rotation(A.sums, newton_iters);
 	V3 t = vsub(vneg(A.neg_tc), vneg(A.neg_mc));
 	out7[0] = q.x; out7[1] = q.y; out7[2] = q.z; out7[3] = q.w;
 	out7[4] = t.x; out7[5] = t.y; out7[6] = t.z;
@@ -264,8 +264,8 @@ __global__ void stage_point_in_limits_kernel(const BlobCone *cones, int n_cones,
 } // namespace
 
 namespace mbik {
-cudaError_t launch_stage_qcp(int n, const float *d_moved, const float *d_target, const double *d_weight, int translate, float *d_out7) {
-	stage_qcp_kernel<<<1, 32>>>(n, d_moved, d_target, d_weight, translate, d_out7);
+cudaError_t launch_stage_qcp(int n, const float *d_moved, const float *d_target, const double *d_weight, int translate, int newton_iters, float *d_out7) {
+	stage_qcp_kernel<<<1, 32>>>(n, d_moved, d_target, d_weight, translate, newton_iters, d_out7);
 	return cudaGetLastError();
 }
 cudaError_t launch_stage_clamp(int n, const float *d_quats, const double *d_cos_half, float *d_out) {

@@ -42,6 +42,10 @@ struct Vector4 {
 struct Transform3D {
 	float basis[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
 	float origin[3] = { 0, 0, 0 };
+	void to_floats(float *o) const { // the C ABI's 12-float record: basis rows, then origin
+		memcpy(o, basis, sizeof(basis));
+		memcpy(o + 9, origin, sizeof(origin));
+	}
 };
 using Variant = std::variant<std::monostate, bool, int64_t, double, std::string, Vector2, Vector3, Transform3D>;
 
@@ -768,7 +772,7 @@ public:
 
 	// ---- the hot path: ManyBoneIK3D::_process_modification for a batch of poses (:645-694) ----
 	//   targets     [n_poses][pin_count][12]   skeleton-space target of every pin row
-	//   start_pose  [n_poses][n_bones][12] or nullptr (= the skeleton's current poses)
+	//   start_pose  [n_poses][n_bones][12] or nullptr (= the skeleton's current bone poses, re-read at every call)
 	//   out_pose    [n_poses][n_bones][10]     position, rotation quaternion, scale per bone
 	// Early-outs of the reference (no skeleton, no pins, no named pin) leave the outputs untouched and return MBIK_OK.
 	int process_modification_batch(size_t n_poses, const float *targets, const float *start_pose, float *out_pose, float *out_local = nullptr,
@@ -793,18 +797,33 @@ public:
 			}
 			is_dirty = false;
 		}
-		mbik_solve_params p;
+		mbik_solve_params p = {};
 		if (params) {
 			p = *params;
 		} else {
 			p.iterations = -1;
 			p.device = -1;
 			p.flags = MBIK_IO_HOST;
-			p.stream = nullptr;
 		}
 		// iterations_per_frame and constraint_mode are read every frame without a rebuild in the reference (:685-689)
 		if (p.iterations < 0) {
 			p.iterations = iterations_per_frame;
+		}
+		// The reference re-reads the skeleton every frame (_update_ik_bones_transform -> IKBone3D::set_initial_pose,
+		// :91-102, src/ik_bone_3d.cpp:161-168), and Skeleton3D::set_bone_pose does not mark the IK dirty: with no explicit
+		// start poses every pose of the batch starts from the skeleton's CURRENT bone poses, not from the poses captured
+		// at the last rebuild.  (Host buffers only: a device-buffer call has nowhere to put them.)
+		std::vector<float> current;
+		if (!start_pose && !(p.flags & MBIK_IO_DEVICE)) {
+			const int32_t nb = skeleton->get_bone_count();
+			current.resize(n_poses * (size_t)nb * 12);
+			for (int32_t b = 0; b < nb && n_poses > 0; b++) {
+				skeleton->get_bone_pose(b).to_floats(&current[(size_t)b * 12]);
+			}
+			for (size_t k = 1; k < n_poses; k++) {
+				memcpy(&current[k * (size_t)nb * 12], current.data(), sizeof(float) * 12 * (size_t)nb);
+			}
+			start_pose = current.data();
 		}
 		return last_error = mbik_solve_batch(rig, &p, n_poses, targets, start_pose, out_pose, out_local, out_status);
 	}

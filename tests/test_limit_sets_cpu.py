@@ -31,12 +31,38 @@ def test_limit_sets_must_keep_the_rigs_rows():
             R.create_limit_sets([rig.constraints, bad])
 
 
-def test_limit_sets_rejected_on_stabilised_rigs():
+def test_limit_sets_accepted_on_stabilised_rigs():
     import rig_cases
     rig = rig_cases.humanoid_stabilized()
     R = BatchedIKRig(rig)
+    h = R.create_limit_sets([rig.constraints])
+    assert R.limit_sets_info(h)["n_sets"] == 1
+    R.destroy_limit_sets(h)
+
+
+def test_limit_sets_parallel_and_asynchronous_authoring_build_the_same_table(monkeypatch):
+    """The host authoring runs on a thread pool; one thread, all threads and the asynchronous entry point must describe
+    the same table (sizes here; the GPU tests compare the solves), and an invalid set is reported by the wait."""
+    rig = rigs.humanoid22()
+    R = BatchedIKRig(rig)
+    sets = LS.variants(rig, 24)
+    monkeypatch.setenv("MBIK_AUTHOR_THREADS", "1")
+    h1 = R.create_limit_sets(sets)
+    i1 = R.limit_sets_info(h1)
+    monkeypatch.delenv("MBIK_AUTHOR_THREADS")
+    h2 = R.create_limit_sets(sets, asynchronous=True)
+    i2 = R.limit_sets_info(h2)  # waits
+    assert i1["author_threads"] == 1 and i2["author_threads"] >= 1
+    assert i1["n_sets"] == i2["n_sets"] == 24 and i1["table_bytes"] == i2["table_bytes"] == 24 * i1["bytes_per_set"]
+    assert i1["bytes_per_set"] == R.info["n_cones"] * 160 + R.info["n_solved"] * 208
+    R.destroy_limit_sets(h1)
+    R.destroy_limit_sets(h2)
+    bad = copy.deepcopy(rig.constraints)
+    bad[0]["bone"] = bad[1]["bone"]
+    h3 = R.create_limit_sets([rig.constraints, bad], asynchronous=True)  # accepted: the rows are checked by the workers
     with pytest.raises(MbikError):
-        R.create_limit_sets([rig.constraints])
+        R.limit_sets_info(h3)
+    R.destroy_limit_sets(h3)
 
 
 def test_limit_set_solve_without_gpu_fails_loudly():

@@ -45,9 +45,25 @@ def test_limit_sets_equal_per_set_rigs(name):
     idx = rng.integers(0, 4, n).astype(np.int32)
     T = rigs.random_targets(rig, 40, n)
     for start in (None, rig_cases.perturbed_start_pose(rig, n, seed=9)):
-        got = R.solve_with_limits(h, idx, T, start_pose=start, want_local=True)
         want = _expected(rig, sets, idx, T, start, lambda r, t, **kw: O.solve_batch(r, t, threads=8, **kw))
-        assert _same(got[1], want[1]) and _same(got[0], want[0]) and np.array_equal(got[2], want[2])
+        for sched in ("auto", "throughput", "segment_parallel"):  # both kernel mappings read the pose's limit-set record
+            got = R.solve_with_limits(h, idx, T, start_pose=start, want_local=True, sched=sched)
+            assert _same(got[1], want[1]) and _same(got[0], want[0]) and np.array_equal(got[2], want[2]), sched
+    R.destroy_limit_sets(h)
+
+
+def test_limit_sets_with_stabilisation_passes():
+    """stabilization_passes > 0 and per-pose limit sets in one launch (the STAB x LIMS instantiation)."""
+    rig = rig_cases.humanoid_stabilized()
+    n = 400
+    R = BatchedIKRig(rig)
+    sets = LS.variants(rig, 3, seed=21)
+    h = R.create_limit_sets(sets, asynchronous=True)  # the solve waits for the authoring
+    idx = (np.arange(n) % 3).astype(np.int32)
+    T = rigs.random_targets(rig, 77, n)
+    want = _expected(rig, sets, idx, T, None, lambda r, t, **kw: O.solve_batch(r, t, threads=8, **kw))
+    got = R.solve_with_limits(h, idx, T, want_local=True)
+    assert _same(got[1], want[1]) and _same(got[0], want[0]) and np.array_equal(got[2], want[2])
     R.destroy_limit_sets(h)
 
 
