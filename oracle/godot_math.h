@@ -136,6 +136,7 @@ struct Basis {
 	Basis() {}
 	Basis(real_t xx, real_t xy, real_t xz, real_t yx, real_t yy, real_t yz, real_t zx, real_t zy, real_t zz) { set(xx, xy, xz, yx, yy, yz, zx, zy, zz); }
 	inline Basis(const Quaternion &q); // implicit, as in the engine
+	inline Basis(const Quaternion &q, const Vector3 &p_scale); // set_quaternion_scale (engine core/math/basis.cpp)
 	Basis(const Vector3 &p_axis, real_t p_angle) { set_axis_angle(p_axis, p_angle); }
 	void set(real_t xx, real_t xy, real_t xz, real_t yx, real_t yy, real_t yz, real_t zx, real_t zy, real_t zz) {
 		rows[0] = Vector3(xx, xy, xz);
@@ -383,6 +384,13 @@ inline Basis::Basis(const Quaternion &q) {
 	set(1.0f - (yy + zz), xy - wz, xz + wy,
 			xy + wz, 1.0f - (xx + zz), yz - wx,
 			xz - wy, yz + wx, 1.0f - (xx + yy));
+}
+
+// Basis::set_quaternion_scale: _set_diagonal(p_scale); rotate(p_quaternion);  rotate(q) is *this = Basis(q) * (*this)
+// (engine core/math/basis.cpp; what Skeleton3D::Bone::update_pose_cache builds get_bone_pose() from)
+inline Basis::Basis(const Quaternion &q, const Vector3 &p_scale) {
+	Basis diag(p_scale.x, 0, 0, 0, p_scale.y, 0, 0, 0, p_scale.z);
+	*this = Basis(q) * diag;
 }
 
 inline Quaternion Basis::get_quaternion() const {

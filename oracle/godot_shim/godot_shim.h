@@ -1197,7 +1197,8 @@ class Skeleton3D : public Node3D {
 		String name;
 		int parent = -1;
 		Transform3D rest;
-		Transform3D pose; // what get_bone_pose() returns (the engine composes it from position/rotation/scale)
+		Transform3D pose; // what get_bone_pose() returns (the engine's pose_cache, composed from position/rotation/scale)
+		bool pose_cache_dirty = false;
 		Vector3 pose_position;
 		Quaternion pose_rotation;
 		Vector3 pose_scale = Vector3(1, 1, 1);
@@ -1256,24 +1257,42 @@ public:
 	}
 	void set_bone_rest(int p_bone, const Transform3D &t) { bones[(size_t)p_bone].rest = t; }
 	Transform3D get_bone_rest(int p_bone) const { return bones[(size_t)p_bone].rest; }
-	// The harness seeds each bone with a raw local Transform3D (the C ABI's start_pose record) and the
-	// stand-in hands exactly that back, so the solver starts from the same bits as mbik_solve_batch.
+	// get_bone_pose() is the engine's pose cache (scene/3d/skeleton_3d.cpp, Bone::update_pose_cache): once one of the three
+	// component setters ran it is recomposed, Transform3D(Basis(pose_rotation, pose_scale), pose_position).  That is the
+	// pose the module's next frame re-seeds its IK bones from (src/many_bone_ik_3d.cpp:1084, :91-102, src/ik_bone_3d.cpp:166).
 	Transform3D get_bone_pose(int p_bone) const {
 		ERR_FAIL_INDEX_V(p_bone, (int)bones.size(), Transform3D());
-		return bones[(size_t)p_bone].pose;
+		BoneShim &b = const_cast<Skeleton3D *>(this)->bones[(size_t)p_bone];
+		if (b.pose_cache_dirty) {
+			b.pose = Transform3D(Basis(b.pose_rotation, b.pose_scale), b.pose_position);
+			b.pose_cache_dirty = false;
+		}
+		return b.pose;
 	}
+	// The harness seeds each bone with a raw local Transform3D -- the C ABI's start_pose record, i.e. "what get_bone_pose()
+	// returns" -- and the stand-in hands exactly those bits back (the engine would decompose and recompose them; a caller of
+	// the C ABI passes poses it read from get_bone_pose(), which already went through that).
 	void set_bone_pose(int p_bone, const Transform3D &t) {
 		BoneShim &b = bones[(size_t)p_bone];
 		b.pose = t;
+		b.pose_cache_dirty = false;
 		b.pose_position = t.origin;
 		b.pose_rotation = t.basis.get_rotation_quaternion();
 		b.pose_scale = t.basis.get_scale();
 	}
-	// the three setters IKBone3D::set_skeleton_bone_pose calls (src/ik_bone_3d.cpp:173-178): stored as
-	// written and read back by the harness; they do not feed get_bone_pose()
-	void set_bone_pose_position(int p_bone, const Vector3 &p) { bones[(size_t)p_bone].pose_position = p; }
-	void set_bone_pose_rotation(int p_bone, const Quaternion &q) { bones[(size_t)p_bone].pose_rotation = q; }
-	void set_bone_pose_scale(int p_bone, const Vector3 &s) { bones[(size_t)p_bone].pose_scale = s; }
+	// the three setters IKBone3D::set_skeleton_bone_pose calls (src/ik_bone_3d.cpp:173-178)
+	void set_bone_pose_position(int p_bone, const Vector3 &p) {
+		bones[(size_t)p_bone].pose_position = p;
+		bones[(size_t)p_bone].pose_cache_dirty = true;
+	}
+	void set_bone_pose_rotation(int p_bone, const Quaternion &q) {
+		bones[(size_t)p_bone].pose_rotation = q;
+		bones[(size_t)p_bone].pose_cache_dirty = true;
+	}
+	void set_bone_pose_scale(int p_bone, const Vector3 &s) {
+		bones[(size_t)p_bone].pose_scale = s;
+		bones[(size_t)p_bone].pose_cache_dirty = true;
+	}
 	Vector3 get_bone_pose_position(int p_bone) const { return bones[(size_t)p_bone].pose_position; }
 	Quaternion get_bone_pose_rotation(int p_bone) const { return bones[(size_t)p_bone].pose_rotation; }
 	Vector3 get_bone_pose_scale(int p_bone) const { return bones[(size_t)p_bone].pose_scale; }

@@ -342,6 +342,23 @@ void orc_swing_twist_y(const float *q4, float *out8) {
 //   op 9: Transform3D(in[0..11]).affine_inverse()            -> out[0..11]
 //   op 10: Basis(in[0..8]) * Basis(in[9..17])                -> out[0..8]
 //   op 11: Basis(in[0..8]).get_scale()                       -> out[0..2]
+//   op 12: Basis(Quaternion(in[0..3]), scale in[4..6])       -> out[0..8]   (set_quaternion_scale)
+// What Skeleton3D::get_bone_pose() returns once out10 = (position, rotation quaternion, scale) is in the skeleton:
+// Transform3D(Basis(rotation, scale), position) for n records (engine update_pose_cache; see oracle/godot_shim Skeleton3D).
+void orc_recompose_pose(size_t n, const float *out10, float *local12) {
+	for (size_t i = 0; i < n; i++) {
+		const float *o = out10 + 10 * i;
+		Basis b(Quaternion(o[3], o[4], o[5], o[6]), Vector3(o[7], o[8], o[9]));
+		float *l = local12 + 12 * i;
+		for (int r = 0; r < 3; r++) {
+			for (int c = 0; c < 3; c++) {
+				l[r * 3 + c] = b.rows[r][c];
+			}
+		}
+		l[9] = o[0]; l[10] = o[1]; l[11] = o[2];
+	}
+}
+
 int orc_math_probe(int op, const float *in, float *out) {
 	auto load_b = [](const float *p) {
 		Basis b;
@@ -363,6 +380,7 @@ int orc_math_probe(int op, const float *in, float *out) {
 		p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
 	};
 	switch (op) {
+		case 12: store_b(Basis(Quaternion(in[0], in[1], in[2], in[3]), Vector3(in[4], in[5], in[6])), out); return 0;
 		case 0: store_b(Basis(Quaternion(in[0], in[1], in[2], in[3])), out); return 0;
 		case 1: store_q(load_b(in).get_quaternion(), out); return 0;
 		case 2: store_q(load_b(in).get_rotation_quaternion(), out); return 0;

@@ -40,6 +40,8 @@ def lib():
         L.orc_clamp_to_cos_half_angle.argtypes = [vp, C.c_double, vp]
         L.orc_swing_twist_y.argtypes = [vp, vp]
         L.orc_math_probe.argtypes = [C.c_int, vp, vp]
+        L.orc_recompose_pose.argtypes = [C.c_size_t, vp, vp]
+        L.orc_recompose_pose.restype = None
         L.orc_hardware_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -77,6 +79,22 @@ def solve_batch(rig, targets, start_pose=None, iterations=-1, threads=1, rebuild
     if want_counters:
         res.append(dict(bone_steps=int(cnt[0]), swing_calls=int(cnt[1]), swing_rectified=int(cnt[2])))
     return tuple(res)
+
+
+def recompose_pose(rig, out_pose, start_pose=None):
+    """The skeleton state after a frame's write-back, [n, n_bones, 12]: for the bones of bone_list what
+    Skeleton3D::get_bone_pose() returns once out_pose's position / rotation / scale are in the skeleton
+    (Transform3D(Basis(rotation, scale), position)); the other bones keep start_pose (default: rest)."""
+    out_pose = np.ascontiguousarray(out_pose, np.float32)
+    n = out_pose.shape[0]
+    assert out_pose.shape == (n, rig.n_bones, 10)
+    rec = np.zeros((n, rig.n_bones, 12), np.float32)
+    lib().orc_recompose_pose(n * rig.n_bones, _p(out_pose), _p(rec))
+    base = np.ascontiguousarray(start_pose, np.float32).copy() if start_pose is not None else np.broadcast_to(
+        np.asarray(rig.rest_local, np.float32).reshape(1, rig.n_bones, 12), (n, rig.n_bones, 12)).copy()
+    solved = rig_facts(rig)["bone_order"]
+    base[:, solved] = rec[:, solved]
+    return base
 
 
 def rig_facts(rig):
@@ -144,8 +162,8 @@ def swing_twist_y(q):
 
 
 MATH_OPS = dict(basis_from_quat=0, get_quaternion=1, get_rotation_quaternion=2, orthonormalized=3, inverse=4, shortest_arc=5,
-                quat_xform=6, basis_slerp=7, quat_axis_angle=8, affine_inverse=9, basis_mul=10, get_scale=11)
-_MATH_OUT = {0: 9, 1: 4, 2: 4, 3: 9, 4: 9, 5: 4, 6: 3, 7: 9, 8: 4, 9: 12, 10: 9, 11: 3}
+                quat_xform=6, basis_slerp=7, quat_axis_angle=8, affine_inverse=9, basis_mul=10, get_scale=11, basis_from_quat_scale=12)
+_MATH_OUT = {0: 9, 1: 4, 2: 4, 3: 9, 4: 9, 5: 4, 6: 3, 7: 9, 8: 4, 9: 12, 10: 9, 11: 3, 12: 9}
 
 
 def math_probe(op, *args):

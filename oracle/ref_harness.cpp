@@ -63,6 +63,41 @@ int ref_solve_batch(const mbik_rig_desc *d, size_t n_poses, const float *targets
 	return 0;
 }
 
+// A node living across frames: per pose one scene; frame 0 starts from start_pose (or the rest pose), every later frame
+// from whatever the skeleton holds after the previous frame's write-back -- nothing re-seeds it from outside.
+//   targets [n_frames][n_poses][n_pins][12]; out_pose [n_frames][n_poses][n_bones][10]; out_local (raw IK-bone transforms
+//   captured at modification_processed) and out_skeleton (get_bone_pose() after the frame) [n_frames][n_poses][n_bones][12],
+//   both nullable; out_status [n_frames][n_poses] nullable.
+int ref_solve_frames(const mbik_rig_desc *d, size_t n_poses, int n_frames, const float *targets, const float *start_pose, float *out_pose,
+		float *out_local, float *out_skeleton, uint32_t *out_status, int iterations, int n_threads) {
+	if (!d || !targets || !out_pose || n_frames < 1) {
+		return -1;
+	}
+	auto range = [&](size_t begin, size_t end) {
+		for (size_t k = begin; k < end; k++) {
+			RefScene scene(d, iterations);
+			for (int f = 0; f < n_frames; f++) {
+				const size_t row = (size_t)f * n_poses + k;
+				scene.solve(d, targets + row * (size_t)d->n_pins * 12, start_pose ? start_pose + k * (size_t)d->n_bones * 12 : nullptr,
+						out_pose + row * (size_t)d->n_bones * 10, out_local ? out_local + row * (size_t)d->n_bones * 12 : nullptr,
+						out_status ? out_status + row : nullptr, f > 0, out_skeleton ? out_skeleton + row * (size_t)d->n_bones * 12 : nullptr);
+			}
+		}
+	};
+	if (n_threads <= 1 || n_poses < 2) {
+		range(0, n_poses);
+		return 0;
+	}
+	std::vector<std::thread> th;
+	for (int t = 0; t < n_threads; t++) {
+		th.emplace_back(range, n_poses * (size_t)t / (size_t)n_threads, n_poses * (size_t)(t + 1) / (size_t)n_threads);
+	}
+	for (auto &t : th) {
+		t.join();
+	}
+	return 0;
+}
+
 // Setup facts of the rig the reference builds (for the flattener / oracle cross-checks): solve order of the
 // bones, segment count, bone-direction and twist-axes bases per solved bone.  Returns the number of solved bones.
 int ref_rig_facts(const mbik_rig_desc *d, int32_t *bone_order, int32_t capacity, int32_t *n_segments, float *dir_basis, float *twist_basis) {

@@ -158,9 +158,27 @@ struct RefScene {
 		}
 	}
 
-	void solve(const mbik_rig_desc *d, const float *targets12, const float *start12, float *out10, float *out_local12, uint32_t *status) {
-		std::vector<Transform3D> start((size_t)d->n_bones);
+	// keep_skeleton: do not touch the skeleton's bone poses before the frame -- the node lives on from the previous frame,
+	// its IK bones re-seed from what the skeleton holds after the previous write-back (get_bone_pose(): recomposed from the
+	// position / rotation / scale IKBone3D::set_skeleton_bone_pose wrote).  out_skeleton12 (nullable): get_bone_pose() of
+	// every bone after the frame.
+	void solve(const mbik_rig_desc *d, const float *targets12, const float *start12, float *out10, float *out_local12, uint32_t *status,
+			bool keep_skeleton = false, float *out_skeleton12 = nullptr) {
+		begin_frame(d, targets12, start12, keep_skeleton);
+		end_frame(d, out10, out_local12, status, out_skeleton12);
+	}
+
+	std::vector<Transform3D> start; // the skeleton's bone poses at the start of the current frame
+	bool wrote = false;
+
+	// everything up to and including SkeletonModifier3D::process_modification() ...
+	void begin_frame(const mbik_rig_desc *d, const float *targets12, const float *start12, bool keep_skeleton = false) {
+		start.resize((size_t)d->n_bones);
 		for (int b = 0; b < d->n_bones; b++) {
+			if (keep_skeleton) {
+				start[(size_t)b] = skeleton->get_bone_pose(b);
+				continue;
+			}
 			start[(size_t)b] = load_xform(start12 ? start12 + 12 * b : d->rest_local + 12 * b);
 			skeleton->set_bone_pose(b, start[(size_t)b]);
 		}
@@ -170,8 +188,12 @@ struct RefScene {
 		// the frame boundary: the previous frame's "modification_processed" re-seeds IK bones and targets
 		ik->emit_signal(SNAME("modification_processed"));
 		std::fill(solved.begin(), solved.end(), 0);
-		bool wrote = frame_will_write(d);
+		wrote = frame_will_write(d);
 		ik->process_modification();
+	}
+
+	// ... and the read-back of what the frame left on the skeleton (a deferred binding writes between the two)
+	void end_frame(const mbik_rig_desc *d, float *out10, float *out_local12, uint32_t *status, float *out_skeleton12 = nullptr) {
 		bool have_locals = true;
 		if (solved_override) {
 			have_locals = false;
@@ -212,6 +234,11 @@ struct RefScene {
 		}
 		if (status) {
 			*status = st;
+		}
+		if (out_skeleton12) {
+			for (int b = 0; b < d->n_bones; b++) {
+				store_xform(out_skeleton12 + 12 * b, skeleton->get_bone_pose(b));
+			}
 		}
 	}
 

@@ -57,6 +57,7 @@ def lib():
         L = C.CDLL(LIB)
         vp = C.c_void_p
         L.ref_solve_batch.argtypes = [C.POINTER(RigDesc), C.c_size_t, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_uint]
+        L.ref_solve_frames.argtypes = [C.POINTER(RigDesc), C.c_size_t, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
         L.ref_rig_facts.argtypes = [C.POINTER(RigDesc), vp, C.c_int32, vp, vp, vp]
         L.ref_step_weights.argtypes = [C.POINTER(RigDesc), C.c_int32, vp, C.c_int32]
         L.ref_cone_geometry.argtypes = [C.POINTER(RigDesc), vp, C.c_int32]
@@ -94,6 +95,28 @@ def solve_batch(rig, targets, start_pose=None, iterations=-1, threads=1, rebuild
                            1 if rebuild_each else 0)
     assert rc == 0
     return (out, loc, st) if want_local else (out, st)
+
+
+def solve_frames(rig, targets, start_pose=None, iterations=-1, threads=1):
+    """One long-lived node per pose over a frame sequence: frame 0 starts from start_pose (or rest), every later frame
+    from what the skeleton holds after the previous write-back (the module's own modification_processed re-seed).
+    targets [frames, n, n_pins, 12] -> dict(out [frames, n, n_bones, 10], local (raw IK locals), skeleton
+    (get_bone_pose() after the frame) [frames, n, n_bones, 12], status [frames, n])."""
+    L = lib()
+    desc, keep = rig_to_desc(rig)
+    targets = np.ascontiguousarray(targets, np.float32)
+    f, n = targets.shape[:2]
+    assert targets.shape == (f, n, rig.n_pins, 12)
+    if start_pose is not None:
+        start_pose = np.ascontiguousarray(start_pose, np.float32)
+        assert start_pose.shape == (n, rig.n_bones, 12)
+    out = np.zeros((f, n, rig.n_bones, 10), np.float32)
+    loc = np.zeros((f, n, rig.n_bones, 12), np.float32)
+    skel = np.zeros((f, n, rig.n_bones, 12), np.float32)
+    st = np.zeros((f, n), np.uint32)
+    rc = L.ref_solve_frames(C.byref(desc), n, f, _p(targets), _p(start_pose), _p(out), _p(loc), _p(skel), _p(st), int(iterations), int(threads))
+    assert rc == 0
+    return dict(out=out, local=loc, skeleton=skel, status=st)
 
 
 def rig_facts(rig):
@@ -182,6 +205,51 @@ def binding_solve_batch(rig, targets, start_pose=None, iterations=-1, rebuild_ea
     st = np.zeros(n, np.uint32)
     rc = _blib.ref_binding_solve_batch(C.byref(desc), n, _p(targets), _p(start_pose), _p(out), _p(st), int(iterations), 1 if rebuild_each else 0)
     return int(rc), out, st
+
+
+class BindingCrowd:
+    """A scene of long-lived reference nodes (each its own Skeleton3D + ManyBoneIK3D) whose _process_modification is the
+    deferred binding mbik_godot::CrowdBinding: nodes sharing a rig are solved by ONE mbik_solve_batch per frame."""
+
+    def __init__(self):
+        global _blib
+        if not os.path.exists(BINDING_LIB) and build_binding() is None:
+            raise RuntimeError("oracle/_ref/libmbik_ref_binding.so is not built and the reference sources are not present")
+        self.L = C.CDLL(BINDING_LIB)
+        vp = C.c_void_p
+        self.L.ref_crowd_create.restype = vp
+        self.L.ref_crowd_destroy.argtypes = [vp]
+        self.L.ref_crowd_add.argtypes = [vp, C.POINTER(RigDesc), C.c_int, vp, C.c_int]
+        self.L.ref_crowd_frame.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int)]
+        self.h = C.c_void_p(self.L.ref_crowd_create())
+        self.parts = []  # (rig, n_nodes)
+
+    def add(self, rig, n_nodes, start_pose=None, iterations=-1):
+        desc, keep = rig_to_desc(rig)
+        if start_pose is not None:
+            start_pose = np.ascontiguousarray(start_pose, np.float32)
+            assert start_pose.shape == (n_nodes, rig.n_bones, 12)
+        rc = self.L.ref_crowd_add(self.h, C.byref(desc), int(n_nodes), _p(start_pose), int(iterations))
+        assert rc > 0, rc
+        self.parts.append((rig, int(n_nodes)))
+
+    def frame(self, targets_per_part):
+        """targets_per_part: one [n_nodes, n_pins, 12] array per add() call.  Returns (rc, [out_pose per part], launches)."""
+        flat = np.concatenate([np.ascontiguousarray(t, np.float32).reshape(-1) for t in targets_per_part])
+        total = sum(n * rig.n_bones * 10 for rig, n in self.parts)
+        out = np.zeros(total, np.float32)
+        launches = C.c_int(0)
+        rc = self.L.ref_crowd_frame(self.h, _p(flat), _p(out), None, C.byref(launches))
+        outs, at = [], 0
+        for rig, n in self.parts:
+            outs.append(out[at:at + n * rig.n_bones * 10].reshape(n, rig.n_bones, 10).copy())
+            at += n * rig.n_bones * 10
+        return int(rc), outs, int(launches.value)
+
+    def close(self):
+        if self.h:
+            self.L.ref_crowd_destroy(self.h)
+            self.h = None
 
 
 def run_doctests():

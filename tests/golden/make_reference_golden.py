@@ -11,7 +11,8 @@ Contents, for every benchmark and edge rig (rigs.RIGS + rig_cases.EDGE_RIGS) and
   <name>_status   [4]               non-finite-reset flag
   <name>_order / _dir / _twist / _cones   setup facts of the rig the reference builds (solve order of the bones,
                                     bone-direction and twist-axes bases, cone + tangent-circle geometry)
-plus warm-start frames (humanoid22, quad80: frame 2 started from frame 1's locals) and stage vectors (QCP fits,
+plus warm-start frames (humanoid22, quad80: frame 2 started from frame 1's locals), frame sequences of a long-lived node
+(4 frames, every frame re-seeded from the skeleton as the previous write-back left it) and stage vectors (QCP fits,
 kusudama point-in-limits, clamp, swing-twist on seeded random inputs).
 
     python tests/golden/make_reference_golden.py      (needs /root/reference; run in the build container)
@@ -97,6 +98,15 @@ def main():
         out[name + "_warm_out"] = o2
         out[name + "_warm_local"] = loc2
         out[name + "_warm_status"] = st2
+    # a node living across frames (ref_solve_frames): frame f+1 starts from what the skeleton holds after frame f's write-back
+    for name in ("humanoid22", "quad80", "chain_diverging"):
+        rig = all_cases()[name]()
+        Tf = np.stack([rigs.random_targets(rig, 5000 + 100 * f, 6) for f in range(4)])
+        fr = Rf.solve_frames(rig, Tf)
+        out[name + "_frames_targets"] = Tf
+        out[name + "_frames_out"] = fr["out"]
+        out[name + "_frames_skeleton"] = fr["skeleton"]
+        out[name + "_frames_status"] = fr["status"]
     qcp, kus, quats, cos_half = stage_inputs()
     out["stage_qcp"] = np.stack([np.concatenate(Rf.qcp_weighted_superpose(m, t, w, tr)) for m, t, w, tr in qcp])
     out["stage_kusudama"] = np.stack([np.concatenate([p, [ib]]).astype(np.float32) for p, ib in (Rf.kusudama_point_in_limits(c, pt) for c, pt in kus)])

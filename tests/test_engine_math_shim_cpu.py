@@ -125,3 +125,20 @@ def test_axis_angle_constructor_and_slerp():
     assert np.abs(O.math_probe("basis_slerp", A, B, [1.0]) - B).max() < 2e-6
     H = O.math_probe("basis_slerp", A, B, [0.5]).reshape(3, 3).astype(np.float64)
     assert np.abs(H @ H.T - np.eye(3)).max() < 1e-5
+
+
+def test_basis_from_quaternion_and_scale_scales_the_columns():
+    """Basis::set_quaternion_scale (what Skeleton3D::get_bone_pose() recomposes a pose from): R(q) * diag(scale), i.e. column
+    j of the rotation scaled by scale[j]; get_rotation_quaternion / get_scale take it apart again."""
+    rng = np.random.default_rng(12)
+    for _ in range(20):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        sc = rng.uniform(0.3, 2.5, 3)
+        R = O.math_probe("basis_from_quat", q).reshape(3, 3).astype(np.float64)
+        B = O.math_probe("basis_from_quat_scale", q, sc).reshape(3, 3)
+        assert np.allclose(B, R @ np.diag(sc), atol=2e-6)
+        assert np.allclose(O.math_probe("get_scale", B), sc, atol=1e-5)
+        assert same_rotation(O.math_probe("get_rotation_quaternion", B), q)
+    ident = O.math_probe("basis_from_quat_scale", [0, 0, 0, 1], [1, 1, 1]).reshape(3, 3)
+    assert np.array_equal(ident, np.eye(3, dtype=np.float32))

@@ -129,8 +129,9 @@ def test_bit_exact_with_start_pose(name):
 
 
 def test_frame_to_frame_warm_start_chain():
-    """Three consecutive frames, each seeded with the previous frame's raw local transforms, as the reference
-    re-seeds from the skeleton after every solve (src/many_bone_ik_3d.cpp:1084, :91-102)."""
+    """Three consecutive frames, each seeded with what the skeleton holds after the previous frame's write-back -- the
+    recomposed position / rotation / scale (MBIK_LOCAL_RECOMPOSED) -- as the reference re-seeds from the skeleton after
+    every solve (src/many_bone_ik_3d.cpp:1084, :91-102).  Oracle side: its out_pose recomposed by the engine stand-in."""
     rig = rigs.humanoid22()
     R = BatchedIKRig(rig)
     n = 64
@@ -138,10 +139,13 @@ def test_frame_to_frame_warm_start_chain():
     ref_start = None
     for frame in range(3):
         T = rigs.random_targets(rig, 1000 * frame, n)
-        got = R.solve(T, start_pose=start, want_local=True)
+        raw = R.solve(T, start_pose=start, want_local=True)
+        got = R.solve(T, start_pose=start, want_local=True, recomposed_local=True)
         ref = O.solve_batch(rig, T, start_pose=ref_start, want_local=True, threads=8)
-        _assert_same(rig, got, ref)
-        start, ref_start = got[1], ref[1]
+        _assert_same(rig, raw, ref)
+        ref_start = O.recompose_pose(rig, ref[0], ref_start)
+        assert np.array_equal(got[0], ref[0], equal_nan=True) and np.array_equal(got[1], ref_start, equal_nan=True), frame
+        start = got[1]
 
 
 @pytest.mark.parametrize("name", sorted(list(rigs.RIGS) + list(rig_cases.EDGE_RIGS)))
@@ -353,8 +357,8 @@ def test_cpp_facade_solve_equals_c_abi_solve(tmp_path, name):
 
 @pytest.mark.parametrize("name", ["humanoid22", "quad80"])
 def test_warm_start_stream_equals_per_frame_calls(name):
-    """mbik_stream_*: device-resident frame-to-frame warm start == per-frame mbik_solve_batch with
-    start_pose = previous out_local == the oracle re-seeded from the previous frame (5 frames, pipelined)."""
+    """mbik_stream_*: device-resident frame-to-frame warm start == per-frame mbik_solve_batch with MBIK_LOCAL_RECOMPOSED and
+    start_pose = previous out_local == the oracle re-seeded from the recomposed previous frame (5 frames, pipelined)."""
     from many_bone_ik_b200 import IKStream
     rig = rigs.RIGS[name]()
     R = BatchedIKRig(rig)
@@ -368,12 +372,15 @@ def test_warm_start_stream_equals_per_frame_calls(name):
     S.sync()
     assert S.frames == frames
     final_local = S.read_local()
-    start = None
+    start = cuda_start = None
     for f in range(frames):
         ref_out, ref_loc, ref_st = O.solve_batch(rig, Ts[f], start_pose=start, want_local=True, threads=8)
         assert np.array_equal(outs[f], ref_out, equal_nan=True), f"frame {f}"
         assert np.array_equal(sts[f], ref_st)
-        start = ref_loc
+        start = O.recompose_pose(rig, ref_out, start)
+        c_out, c_loc, c_st = R.solve(Ts[f], start_pose=cuda_start, want_local=True, recomposed_local=True)
+        assert np.array_equal(c_out, ref_out, equal_nan=True) and np.array_equal(c_loc, start, equal_nan=True), f"frame {f}"
+        cuda_start = c_loc
     assert np.array_equal(final_local, start, equal_nan=True)
     # reset -> rest pose again; and a caller-supplied initial pose
     S.reset()

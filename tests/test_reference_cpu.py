@@ -163,3 +163,22 @@ def test_module_binding_without_a_gpu_reports_and_leaves_the_pose_untouched():
     assert rc == -4  # MBIK_ERR_NO_DEVICE (include/mbik.h)
     untouched, _ = Rf.solve_batch(rig, T, start_pose=start, iterations=0)
     assert np.array_equal(out, untouched)
+
+
+@needs_ref
+def test_reference_node_across_frames_equals_oracle_reseeded_from_the_recomposed_pose():
+    """What the module's frame-to-frame seeding is: a long-lived ManyBoneIK3D re-seeds its IK bones from
+    Skeleton3D::get_bone_pose(), which -- once IKBone3D::set_skeleton_bone_pose wrote position / rotation / scale -- is
+    the recomposed Transform3D(Basis(rotation, scale), position), with the non-finite reset, NOT the raw IK transforms.
+    ref_solve_frames (no outside re-seeding) == per-frame oracle solves started from oracle_py.recompose_pose()."""
+    for name in ("humanoid22", "quad80", "chain_diverging", "scaled_bones"):
+        rig = CASES[name]()
+        n, frames = 8, 4
+        Tf = np.stack([rigs.random_targets(rig, 900 + 10 * f, n) for f in range(frames)])
+        ref = Rf.solve_frames(rig, Tf, threads=4)
+        start = None
+        for f in range(frames):
+            o, loc, st = O.solve_batch(rig, Tf[f], start_pose=start, want_local=True, threads=4)
+            assert _same(o, ref["out"][f]) and _same(loc, ref["local"][f]) and np.array_equal(st, ref["status"][f]), (name, f)
+            start = O.recompose_pose(rig, o, start)
+            assert _same(start, ref["skeleton"][f]), (name, f)

@@ -107,6 +107,48 @@ def test_cuda_frame_sequence_equals_live_reference():
         start_g, start_r = lg, lrf
 
 
+@pytest.mark.parametrize("name", ["humanoid22", "quad80", "chain_diverging"])
+def test_stream_reproduces_reference_frame_sequences(name, gold):
+    """mbik_stream_* against the committed fixtures of the reference module's own node living across frames
+    (ref_solve_frames: nothing re-seeds the skeleton from outside; chain_diverging goes non-finite and is reset)."""
+    from many_bone_ik_b200 import IKStream
+    rig = CASES[name]()
+    R = BatchedIKRig(rig)
+    Tf = gold[name + "_frames_targets"]
+    frames, n = Tf.shape[:2]
+    S = IKStream(R, n, device=0)
+    outs = [np.empty((n, rig.n_bones, 10), np.float32) for _ in range(frames)]
+    sts = [np.empty(n, np.uint32) for _ in range(frames)]
+    for f in range(frames):
+        S.submit(np.ascontiguousarray(Tf[f]), outs[f], sts[f])
+    S.sync()
+    for f in range(frames):
+        assert _same(outs[f], gold[name + "_frames_out"][f]), f
+        assert np.array_equal(sts[f], gold[name + "_frames_status"][f]), f
+    assert _same(S.read_local(), gold[name + "_frames_skeleton"][-1])
+
+
+@needs_ref
+def test_stream_equals_live_reference_node_across_frames():
+    """300 long-lived reference nodes over 5 frames vs one device-resident stream (solved-only output layout)."""
+    from many_bone_ik_b200 import IKStream
+    rig = rigs.humanoid22()
+    R = BatchedIKRig(rig)
+    n, frames = 300, 5
+    Tf = np.stack([rigs.random_targets(rig, 31 * f, n) for f in range(frames)])
+    sp = rig_cases.perturbed_start_pose(rig, n, seed=5)
+    ref = Rf.solve_frames(rig, Tf, start_pose=sp, threads=8)
+    order = R.bone_order()
+    S = IKStream(R, n, device=0, initial_pose=sp, solved_only=True)
+    outs = [np.empty((n, len(order), 10), np.float32) for _ in range(frames)]
+    for f in range(frames):
+        S.submit(np.ascontiguousarray(Tf[f]), outs[f], None)
+    S.sync()
+    for f in range(frames):
+        assert _same(outs[f], ref["out"][f][:, order]), f
+    assert _same(S.read_local(), ref["skeleton"][-1])
+
+
 needs_binding = pytest.mark.skipif(not os.path.exists(Rf.BINDING_LIB), reason="prebuilt oracle/_ref/libmbik_ref_binding.so did not travel to this box")
 
 
@@ -130,3 +172,29 @@ def test_module_binding_drop_in_equals_the_reference(name):
             rc, out, st = Rf.binding_solve_batch(rig, T, start_pose=sp, rebuild_each=rebuild)
             assert rc == 0
             assert _same(out, ref_out), (name, rebuild)
+
+
+@needs_ref
+@needs_binding
+def test_crowd_binding_one_launch_per_rig_equals_the_reference_nodes():
+    """mbik_godot::CrowdBinding (many_bone_ik_b200/host/godot_module_binding.h): 96 humanoid nodes and 70 quadruped nodes,
+    each a reference ManyBoneIK3D with its own Skeleton3D living across 4 frames, enqueue their frames; one flush per
+    frame solves every rig's nodes in ONE mbik_solve_batch (2 launches per frame instead of 166).  Every skeleton must
+    receive, bit for bit, what the reference's own _process_modification leaves on it -- frame after frame, i.e. including
+    the re-seed from the recomposed skeleton pose."""
+    parts = [(rigs.humanoid22(), 96), (rigs.quad80(), 70)]
+    frames = 4
+    crowd = Rf.BindingCrowd()
+    refs, Ts = [], []
+    for k, (rig, n) in enumerate(parts):
+        sp = rig_cases.perturbed_start_pose(rig, n, seed=40 + k)
+        crowd.add(rig, n, start_pose=sp)
+        Tf = np.stack([rigs.random_targets(rig, 7000 + 50 * f + k, n) for f in range(frames)])
+        Ts.append(Tf)
+        refs.append(Rf.solve_frames(rig, Tf, start_pose=sp, threads=8))
+    for f in range(frames):
+        rc, outs, launches = crowd.frame([T[f] for T in Ts])
+        assert rc == 0 and launches == len(parts), (rc, launches)
+        for k in range(len(parts)):
+            assert _same(outs[k], refs[k]["out"][f]), (f, parts[k][0].name)
+    crowd.close()
