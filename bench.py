@@ -79,25 +79,51 @@ def _time_cpu_solver(solve, cores, rig, budget_s, steps, warmup):
     return n, dt, n1, dt1
 
 
-def time_cpu_reference(rig, budget_s=12.0, steps=1, warmup=0):
+def _host_supports_x86_64_v3():
+    try:
+        flags = set()
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("flags"):
+                flags = set(ln.split(":", 1)[1].split())
+                break
+        return {"avx2", "bmi2", "fma", "movbe", "f16c"} <= flags
+    except Exception:
+        return False
+
+
+def time_cpu_reference(rig, budget_s=12.0, steps=1, warmup=0, with_port=True):
     from oracle import oracle_py as O
     from oracle import reference_py as Rf
     O.build()
     cores = O.hardware_threads()
     have_ref = os.path.exists(Rf.LIB) or Rf.available()
-    port_budget = budget_s * (0.35 if have_ref else 1.0)
-    n, dt, n1, dt1 = _time_cpu_solver(O.solve_batch, cores, rig, port_budget, steps, warmup)
-    port = {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} poses x {steps} pass(es) of the same workload, oracle restatement, all {cores} host threads, {dt:.1f} s",
-            "single_thread_value": n1 / dt1, "single_thread_us_per_solve": dt1 / n1 * 1e6}
+    port = None
+    if with_port or not have_ref:
+        port_budget = budget_s * (0.35 if have_ref else 1.0)
+        n, dt, n1, dt1 = _time_cpu_solver(O.solve_batch, cores, rig, port_budget, steps, warmup)
+        port = {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{n} poses x {steps} pass(es) of the same workload, oracle restatement, all {cores} host threads, {dt:.1f} s",
+                "single_thread_value": n1 / dt1, "single_thread_us_per_solve": dt1 / n1 * 1e6}
     if not have_ref:
         return port, dt / steps * 1e3
+    # oracle/_ref holds two builds of the same unmodified sources: -O2 (baseline x86-64) and -O2 -march=x86-64-v3.  The v3 build
+    # is the one timed when this host's CPU has the ISA (it is what SURVEY 8(d) asked for short of -march=native, which cannot
+    # travel between hosts); contraction is off in both, so they return the same bits.
+    v3_lib = os.path.join(os.path.dirname(Rf.LIB), "libmbik_ref_v3.so")
+    build_name = "-O2"
+    if os.path.exists(v3_lib) and _host_supports_x86_64_v3() and not os.environ.get("MBIK_REF_BASELINE_ISA"):
+        Rf.LIB = v3_lib
+        Rf._lib = None
+        build_name = "-O2 -march=x86-64-v3 -ffp-contract=off"
     n, dt, n1, dt1 = _time_cpu_solver(Rf.solve_batch, cores, rig, budget_s, steps, warmup)
     ref = {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "reference",
            "sample": f"{n} poses x {steps} pass(es) of the same workload, the reference module's own sources (oracle/_ref: /root/reference/src "
-                     f"compiled unmodified -O2 over the engine stand-in oracle/godot_shim), one long-lived ManyBoneIK3D per thread, all {cores} host threads, {dt:.1f} s",
-           "single_thread_value": n1 / dt1, "single_thread_us_per_solve": dt1 / n1 * 1e6,
-           "port": port}
+                     f"compiled unmodified {build_name} over the engine stand-in oracle/godot_shim -- reference sources on a stand-in engine, not Godot "
+                     f"headless), one long-lived ManyBoneIK3D per thread, all {cores} host threads, {dt:.1f} s",
+           "build": build_name,
+           "single_thread_value": n1 / dt1, "single_thread_us_per_solve": dt1 / n1 * 1e6}
+    if port:
+        ref["port"] = port
     return ref, dt / steps * 1e3
 
 
@@ -199,8 +225,8 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from many_bone_ik_b200 import BatchedIKRig, rigs, sharding
-    from many_bone_ik_b200._capi import MBIK_IO_DEVICE, MBIK_IO_HOST, MBIK_SCHED_THROUGHPUT
+    from many_bone_ik_b200 import BatchedIKRig, IKStream, rigs, sharding
+    from many_bone_ik_b200._capi import MBIK_IO_DEVICE, MBIK_IO_HOST, MBIK_OUT_SOLVED_ONLY, MBIK_SCHED_THROUGHPUT
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: many_bone_ik_b200 has no CPU fallback")
@@ -240,7 +266,7 @@ def main():
     total = args.poses * world
     lo, hi = sharding.shard_range(total, rank, world)
     n = hi - lo
-    nb, npins = rig.n_bones, rig.n_pins
+    nb, npins, nsolved = rig.n_bones, rig.n_pins, R.info["n_solved"]
 
     # synthetic inputs: this rank's slice, regenerated independently from the counter-based RNG
     t_host = torch.empty((n, npins, 12), dtype=torch.float32, pin_memory=True)
@@ -256,7 +282,16 @@ def main():
     def step_device():
         R.solve_raw(n, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
 
+    # The reference-facing call with HOST buffers.  Output layout of the headline e2e leg: MBIK_OUT_SOLVED_ONLY -- the
+    # position / rotation / scale of the bones of bone_list, exactly what _update_skeleton_bones_transform hands to the
+    # skeleton (src/many_bone_ik_3d.cpp:104-116; 20 of humanoid22's 22 bones: 800 B per pose).  The full-skeleton layout
+    # (all 22 bones, pass-through bones included: 880 B) is timed next to it.
+    o_host_c = o_host.view(-1)[: n * nsolved * 10].view(n, nsolved, 10)
+
     def step_host():
+        R.solve_raw(n, t_host.numpy(), o_host_c.numpy(), device=local_rank, flags=MBIK_IO_HOST | MBIK_OUT_SOLVED_ONLY)
+
+    def step_host_full():
         R.solve_raw(n, t_host.numpy(), o_host.numpy(), device=local_rank, flags=MBIK_IO_HOST)
 
     # ---- device-resident throughput (value) ----
@@ -271,84 +306,148 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         step_device()
-        # per-launch kernel time from the library's own event pair on the launching stream (read after sync below)
     ev1.record()
     torch.cuda.synchronize()
     dev_ms = ev0.elapsed_time(ev1)
     local_dev_ms = dev_ms
     barrier()
-    # average kernel duration: time K more launches individually (same stream, same inputs)
+    # cross-check: the library's own per-launch event pair on a few extra launches (same stream, same inputs)
     for _ in range(min(args.steps, 5)):
         step_device()
         torch.cuda.synchronize()
         kernel_ms.append(R.last_kernel_ms(local_rank))
-    clocks = sampler.stop() if rank == 0 else None
     dev_ms = max_over_ranks(dev_ms)
     value = total * args.steps / (dev_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers (e2e) ----
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    def time_host(step, steps):
+        for _ in range(max(1, min(args.warmup, 2))):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        s_ = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        return s_
+    e2e_s = time_host(step_host, args.steps)
     e2e_value = total * args.steps / e2e_s
+    clocks = sampler.stop() if rank == 0 else None
+    full_steps = max(1, min(args.steps, 4))
+    e2e_full_s = time_host(step_host_full, full_steps)
+    # correctness guard on a small sample of what was just computed (device path == host path)
+    chk = min(n, 1024)
+    same = bool(torch.equal(o_dev[:chk].cpu(), o_host[:chk]))
+
+    # ---- steady state of a crowd that lives on the device: mbik_stream_* (frame f+1 starts from frame f's solution as the
+    # skeleton holds it; only targets go up, only the solved bones' poses come down -- or nothing at all) ----
+    stream_e2e = None
+    frames = max(2, min(args.steps, 6))
+    stream_local = [float("inf"), float("inf")]  # seconds for `frames` frames with / without the pose download (this rank)
+    stream_err = None
+    try:
+        S = IKStream(R, n, device=local_rank, solved_only=True)
+        for k_, download in enumerate((True, False)):
+            for _ in range(2):
+                S.submit(t_host.numpy(), o_host_c.numpy() if download else None, None)
+            S.sync()
+            t0 = time.perf_counter()
+            for _ in range(frames):
+                S.submit(t_host.numpy(), o_host_c.numpy() if download else None, None)
+            S.sync()
+            stream_local[k_] = time.perf_counter() - t0
+        S.close()
+        del S
+    except Exception as e:  # no collective inside the try: a rank that fails must not leave the others waiting
+        stream_err = str(e)
+    barrier()
+    st_dl, st_no = max_over_ranks(stream_local[0]), max_over_ranks(stream_local[1])
+    stream_e2e = {"value_with_pose_download": total * frames / st_dl if np.isfinite(st_dl) else None,
+                  "value_targets_only": total * frames / st_no if np.isfinite(st_no) else None, "unit": UNIT, "frames": frames,
+                  "h2d_bytes_per_frame": int(n * npins * 48) * world, "d2h_bytes_per_frame_with_download": int(n * nsolved * 40) * world,
+                  "error": stream_err,
+                  "note": "mbik_stream_submit x frames, then mbik_stream_sync: warm-started frames of the same 2^20-pose crowd per GPU, pinned host targets; "
+                          "'targets_only' leaves the poses on the device (a renderer that skins on the GPU); ranks are not re-synchronised between frames"}
 
     # ---- side measurement: what the host link gives this rank while ALL ranks copy at once (plain pinned-memory copies of the
-    # same buffers, no solve): the ceiling of e2e at N GPUs is min(kernel rate, link rate / 1120 B per solve) ----
+    # same buffers, no solve): the ceiling of e2e at N GPUs is min(kernel rate, link rate / bytes per solve) ----
     host_link = None
+    link_local = [float("inf"), float("inf")]
     try:
-        for _ in range(1):
-            o_host.copy_(o_dev, non_blocking=True)
-            t_dev.copy_(t_host, non_blocking=True)
-        barrier()
+        o_dev_c = o_dev.view(-1)[: n * nsolved * 10].view(n, nsolved, 10)
+        o_host_c.copy_(o_dev_c, non_blocking=True)
+        t_dev.copy_(t_host, non_blocking=True)
+        torch.cuda.synchronize()
         h0, h1, h2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         reps = 3
         h0.record()
         for _ in range(reps):
-            o_host.copy_(o_dev, non_blocking=True)
+            o_host_c.copy_(o_dev_c, non_blocking=True)
         h1.record()
         for _ in range(reps):
             t_dev.copy_(t_host, non_blocking=True)
         h2.record()
         torch.cuda.synchronize()
-        d2h_ms, h2d_ms = max_over_ranks(h0.elapsed_time(h1)) / reps, max_over_ranks(h1.elapsed_time(h2)) / reps
-        barrier()
-        d2h_gbs, h2d_gbs = o_host.numel() * 4 / (d2h_ms * 1e-3) / 1e9, t_host.numel() * 4 / (h2d_ms * 1e-3) / 1e9
-        per_solve_s = (nb * 40) / (d2h_gbs * 1e9)  # D2H and H2D run on separate copy engines: the slower direction bounds
-        per_solve_s = max(per_solve_s, (npins * 48) / (h2d_gbs * 1e9))
+        link_local = [h0.elapsed_time(h1) / reps, h1.elapsed_time(h2) / reps]
+    except Exception as e:  # a side measurement must never break the headline line (and holds no collective)
+        host_link = {"error": str(e)}
+    barrier()
+    d2h_ms, h2d_ms = max_over_ranks(link_local[0]), max_over_ranks(link_local[1])
+    if np.isfinite(d2h_ms) and np.isfinite(h2d_ms):
+        d2h_gbs, h2d_gbs = n * nsolved * 40 / (d2h_ms * 1e-3) / 1e9, t_host.numel() * 4 / (h2d_ms * 1e-3) / 1e9
+        per_solve_s = max((nsolved * 40) / (d2h_gbs * 1e9), (npins * 48) / (h2d_gbs * 1e9))  # separate copy engines: the slower direction bounds
         host_link = {"d2h_gbs_per_gpu_all_ranks_copying": d2h_gbs, "h2d_gbs_per_gpu_all_ranks_copying": h2d_gbs,
                      "e2e_ceiling_solves_per_s": world / per_solve_s,
-                     "note": "slowest rank, pinned host buffers of the e2e leg, every rank copying simultaneously; ceiling = N / max(880 B / d2h, 240 B / h2d)"}
-    except Exception as e:  # a side measurement must never break the headline line
-        host_link = {"error": str(e)}
+                     "e2e_ceiling_full_layout_solves_per_s": world / max((nb * 40) / (d2h_gbs * 1e9), (npins * 48) / (h2d_gbs * 1e9)),
+                     "note": f"slowest rank, pinned host buffers of the e2e leg, every rank copying at about the same time, one direction at a time; ceiling = N / max({nsolved * 40} B / d2h, {npins * 48} B / h2d)"}
 
-    # ---- side measurement: BASELINE configs[2] read literally = ONE 2^20-pose batch sharded over the N GPUs (strong
-    # scaling; each rank solves the first 2^20/N poses of its buffer), device-resident ----
+    # ---- BASELINE configs[2] read literally: ONE 2^20-pose batch sharded over the N GPUs (strong scaling; each rank solves
+    # the first 2^20/N poses of its buffer), device-resident.  The launch picks a wave-balanced CTA size (mbik_kernel.cu) ----
     strong = None
-    if world > 1:
-        ns = min(n, (1 << 20) // world)
-        for _ in range(2):
-            R.solve_raw(ns, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(args.steps):
-            R.solve_raw(ns, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
-        s1.record()
-        torch.cuda.synchronize()
-        strong_ms = max_over_ranks(s0.elapsed_time(s1))
-        barrier()
-        strong = {"total_poses": ns * world, "poses_per_gpu": ns, "value": ns * world * args.steps / (strong_ms * 1e-3), "unit": UNIT,
-                  "ms_per_step": strong_ms / args.steps}
+    ns_ = min(n, (1 << 20) // world)
+    for _ in range(2):
+        R.solve_raw(ns_, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        R.solve_raw(ns_, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+    s1.record()
+    torch.cuda.synchronize()
+    strong_ms = max_over_ranks(s0.elapsed_time(s1))
+    barrier()
+    strong = {"total_poses": ns_ * world, "poses_per_gpu": ns_, "value": ns_ * world * args.steps / (strong_ms * 1e-3), "unit": UNIT,
+              "ms_per_step": strong_ms / args.steps, "scaling": "strong",
+              "note": "one 2^20-pose batch split contiguously over the N GPUs (BASELINE configs[2] literally); compare with N x the N=1 `value`"}
 
-    # correctness guard on a small sample of what was just computed (device path == host path, finite)
-    chk = min(n, 1024)
-    same = bool(torch.equal(o_dev[:chk].cpu(), o_host[:chk]))
+    # ---- side measurement (N > 1): the same host-buffer workload from ONE process -- mbik_solve_batch_multi, one worker thread
+    # per device, one pinned arena -- against the N-process arrangement above.  Rank 0 runs it while the other ranks wait. ----
+    single_process = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            try:
+                per = min(n, 1 << 19)
+                tot = per * world
+                th_ = torch.empty((tot, npins, 12), dtype=torch.float32, pin_memory=True)
+                for g in range(world):
+                    th_[g * per:(g + 1) * per] = t_host[:per]
+                oh_ = torch.empty((tot, nsolved, 10), dtype=torch.float32, pin_memory=True)
+                devs = list(range(world))
+                for _ in range(2):
+                    R.solve_raw(tot, th_.numpy(), oh_.numpy(), flags=MBIK_IO_HOST | MBIK_OUT_SOLVED_ONLY, devices=devs)
+                reps = max(2, min(args.steps, 5))
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    R.solve_raw(tot, th_.numpy(), oh_.numpy(), flags=MBIK_IO_HOST | MBIK_OUT_SOLVED_ONLY, devices=devs)
+                dt_ = time.perf_counter() - t0
+                single_process = {"value": tot * reps / dt_, "unit": UNIT, "total_poses": tot, "devices": world,
+                                  "note": "mbik_solve_batch_multi from rank 0's process (host buffers, solved-only layout), the other ranks idle"}
+                del th_, oh_
+            except Exception as e:
+                single_process = {"error": str(e)}
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -375,7 +474,8 @@ def main():
     p50_thread_per_pose = _p50(MBIK_SCHED_THROUGHPUT)
 
     # small batches, for scale (BASELINE configs[0] is ONE pose on the CPU: 0.41 ms in the reference): p50 of a device-resident
-    # call with 1 and 32 poses (one 32-pose group either way), and of a HOST-buffer call with 4096 poses (copies included)
+    # call with 1 and 32 poses (one 32-pose group either way), and of a HOST-buffer call with 1 / 64 / 4096 poses (copies
+    # included) -- 64 poses is what a CrowdBinding flush of 64 nodes costs, against 64 one-pose calls of the plain binding
     def _p50_n(n_small, host=False):
         lat = []
         th, oh = t_host[:n_small].contiguous().pin_memory(), torch.empty((n_small, nb, 10), dtype=torch.float32).pin_memory()
@@ -394,7 +494,8 @@ def main():
             if i >= 20:
                 lat.append(dt_)
         return float(np.median(lat))
-    small = {"p50_ms_1_pose_device": _p50_n(1), "p50_ms_32_poses_device": _p50_n(32), "p50_ms_4096_poses_host_buffers": _p50_n(LATENCY_BATCH, host=True)}
+    small = {"p50_ms_1_pose_device": _p50_n(1), "p50_ms_32_poses_device": _p50_n(32), "p50_ms_1_pose_host_buffers": _p50_n(1, host=True),
+             "p50_ms_64_poses_host_buffers": _p50_n(64, host=True), "p50_ms_4096_poses_host_buffers": _p50_n(LATENCY_BATCH, host=True)}
 
     # ---- roofline of the one kernel (FP32 CUDA cores; HBM shown as the sanity figure) ----
     import ctypes as C
@@ -411,13 +512,15 @@ def main():
     k_ms = float(local_dev_ms / args.steps)
     k_ms_single = float(np.mean(kernel_ms))
     # DRAM traffic of the kernel from the committed ncu --set full capture (bytes per pose x poses of one launch)
-    traffic, traffic_src = None, None
+    traffic_table = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        traffic = float(tj["dram_bytes"]) / float(tj["poses"]) * n
-        traffic_src = tj.get("source")
+        traffic_table = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
     except Exception:
         pass
+    traffic, traffic_src = None, None
+    if "dram_bytes" in traffic_table:
+        traffic = float(traffic_table["dram_bytes"]) / float(traffic_table["poses"]) * n
+        traffic_src = traffic_table.get("source")
     flops = R.info["flops_per_solve"]
     bytes_per_solve = npins * 48 + nb * 40
     ach_tf = flops * n / (k_ms * 1e-3) / 1e12
@@ -433,24 +536,36 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"},
     }
 
-    # ---- the other BASELINE configs (4: chain64, 30 iterations; 5: quad80, 15 iterations), device-resident, brief ----
-    other = {}
+    # ---- BASELINE configs[3] (chain64, 30 iterations) and configs[4] (quad80, 15 iterations): the same measurements as the
+    # headline on a 65 536-pose batch -- device-resident rate, e2e through host buffers, p50 of a 4096-pose
+    # batch, the reference CPU path on a bounded sample beside it, and the roofline that binds these rigs (HBM: the
+    # per-pose state does not fit on chip) with the FP32 figure next to it ----
+    configs = {}
     for name in ("chain64", "quad80"):
         try:
             rg = rigs.RIGS[name]()
             Rg = BatchedIKRig(rg)
-            m = 148 * 512
-            tg = torch.from_numpy(rigs.random_targets(rg, 0, m)).to(dev)
+            m = 65536
+            ns_g = Rg.info["n_solved"]
+            th_g = torch.from_numpy(rigs.random_targets(rg, 0, m)).pin_memory()
+            tg = th_g.to(dev)
             og = torch.empty((m, rg.n_bones, 10), dtype=torch.float32, device=dev)
+            oh_g = torch.empty((m, ns_g, 10), dtype=torch.float32, pin_memory=True)
             for _ in range(2):
                 Rg.solve_raw(m, tg, og, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
             a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps_g = 3
             a_.record()
-            for _ in range(3):
+            for _ in range(reps_g):
                 Rg.solve_raw(m, tg, og, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
             b_.record()
             torch.cuda.synchronize()
-            ms = a_.elapsed_time(b_) / 3
+            ms = a_.elapsed_time(b_) / reps_g
+            Rg.solve_raw(m, th_g.numpy(), oh_g.numpy(), device=local_rank, flags=MBIK_IO_HOST | MBIK_OUT_SOLVED_ONLY)
+            t0_ = time.perf_counter()
+            for _ in range(reps_g):
+                Rg.solve_raw(m, th_g.numpy(), oh_g.numpy(), device=local_rank, flags=MBIK_IO_HOST | MBIK_OUT_SOLVED_ONLY)
+            e2e_g = m * reps_g / (time.perf_counter() - t0_)
             lat_g = []
             for i in range(40):  # p50 of a 4096-pose batch (the mapping is the library's choice), 30 calls after 10 warm-ups
                 c_, d_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -460,31 +575,51 @@ def main():
                 torch.cuda.synchronize()
                 if i >= 10:
                     lat_g.append(c_.elapsed_time(d_))
-            other[name] = {"solves_per_s": m / (ms * 1e-3), "poses": m, "iterations": rg.iterations, "ms_per_launch": ms,
-                           "latency_p50_ms_4096": float(np.median(lat_g)), "segment_parallel_warps": Rg.info["sp_roles"],
-                           "flops_per_solve": Rg.info["flops_per_solve"],
-                           "fp32_roofline_frac": Rg.info["flops_per_solve"] * m / (ms * 1e-3) / 1e12 / float(tf.value) if tf.value else None}
-            try:  # DRAM traffic of this rig's kernel from the committed ncu capture -> fraction of the measured HBM peak
-                tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["other_rigs"][name]
-                gbs = float(tr["dram_bytes"]) / float(tr["poses"]) * m / (ms * 1e-3) / 1e9
-                other[name]["hbm"] = {"traffic_bytes_per_launch": float(tr["dram_bytes"]) / float(tr["poses"]) * m, "achieved_gbs": gbs,
-                                      "frac_of_measured_peak": gbs / hbm_peak, "source": tr["source"]}
-            except Exception:
-                pass
-            del Rg, tg, og
+            fl = Rg.info["flops_per_solve"]
+            alg_bytes = rg.n_pins * 48 + rg.n_bones * 40
+            fp32 = {"achieved": fl * m / (ms * 1e-3) / 1e12, "peak": float(tf.value), "unit": "TFLOP/s",
+                    "frac": fl * m / (ms * 1e-3) / 1e12 / float(tf.value) if tf.value else None, "flops_per_solve": fl}
+            roof = {"bound": "hbm", "kernel": "mbik_solve_kernel<64,16,8,*>", "unit": "GB/s", "peak": hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
+                    "algorithmic_bytes_per_solve": alg_bytes, "algorithmic_gbs": alg_bytes * m / (ms * 1e-3) / 1e9, "fp32": fp32}
+            tr = traffic_table.get("other_rigs", {}).get(name)
+            if tr:  # DRAM bytes per pose of this rig's kernel from the committed ncu --set full capture x the poses of this launch
+                t_bytes = float(tr["dram_bytes"]) / float(tr["poses"]) * m
+                roof.update({"achieved": t_bytes / (ms * 1e-3) / 1e9, "frac": t_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": t_bytes,
+                             "traffic_source": tr["source"],
+                             "note": "achieved = measured DRAM traffic of the launch / its duration: the walk re-reads the per-pose local transforms "
+                                     "(they do not fit L2), so the kernel is bound by HBM on bytes the algorithm would not need on chip"})
+            cfg = {"workload": f"{name}: {rg.n_bones} bones, {rg.n_pins} effectors, {rg.iterations} iterations, {m} random-target poses",
+                   "value": m / (ms * 1e-3), "unit": UNIT, "poses": m, "iterations": rg.iterations, "ms_per_launch": ms,
+                   "e2e": {"value": e2e_g, "unit": UNIT, "h2d_bytes_per_step": int(m * rg.n_pins * 48), "d2h_bytes_per_step": int(m * ns_g * 40)},
+                   "latency_p50_ms_4096": float(np.median(lat_g)), "segment_parallel_warps": Rg.info["sp_roles"], "roofline": roof}
+            if not args.no_cpu_baseline and world == 1:
+                cb_g, _ = time_cpu_reference(rg, budget_s=6.0, with_port=False)
+                cfg["cpu_baseline"] = cb_g
+                cfg["e2e_over_cpu_baseline"] = e2e_g / cb_g["value"] if cb_g.get("value") else None
+                cfg["cpu_baseline"]["latency_ms_4096"] = LATENCY_BATCH / cb_g["value"] * 1e3 if cb_g.get("value") else None
+            configs[name] = cfg
+            del Rg, tg, og, th_g, oh_g
         except Exception as e:  # never let the side measurements break the headline line
-            other[name] = {"error": str(e)}
+            configs[name] = {"error": str(e)}
 
-    # ---- side measurement: per-pose limit sets: 4 alternative fills of the constraint tables, pose k uses set k % 4 ----
+    # ---- side measurement: per-pose limit sets: alternative fills of the constraint tables authored on a
+    # pool of host threads (sets per second), then pose k solved with set k % 4 ----
     limit_sets = None
     try:
         import copy
-        cs = [copy.deepcopy(rig.constraints) for _ in range(4)]
-        for s_i, cset in enumerate(cs):
+
+        def variant(s_i):
+            cset = copy.deepcopy(rig.constraints)
             for c in cset:
-                c["twist_range"] = float(np.float32(c["twist_range"] * (1.0 - 0.15 * s_i)))
-                c["cones"] = [(cx, cy, cz, float(np.float32(r * (1.0 - 0.1 * s_i)))) for (cx, cy, cz, r) in c["cones"]]
-        hs = R.create_limit_sets(cs)
+                c["twist_range"] = float(np.float32(c["twist_range"] * (1.0 - 0.15 * (s_i % 4))))
+                c["cones"] = [(cx, cy, cz, float(np.float32(r * (1.0 - 0.1 * (s_i % 4) - 1e-4 * (s_i // 4))))) for (cx, cy, cz, r) in c["cones"]]
+            return cset
+        many = [variant(k) for k in range(2048)]
+        hm = R.create_limit_sets(many)
+        info_m = R.limit_sets_info(hm)
+        R.destroy_limit_sets(hm)
+        hs = R.create_limit_sets(many[:4])
         idx_dev = (torch.arange(n, device=dev, dtype=torch.int32) % 4).contiguous()
         for _ in range(2):
             R.solve_with_limits_raw(hs, n, idx_dev, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
@@ -495,8 +630,21 @@ def main():
         l1.record()
         torch.cuda.synchronize()
         lms = l0.elapsed_time(l1) / 3
-        limit_sets = {"sets": 4, "poses": n, "ms_per_launch": lms, "solves_per_s": n / (lms * 1e-3),
-                      "note": "mbik_solve_batch_limits, device-resident: kusudama data read per pose from a device table instead of the rig blob"}
+        lat_l = []
+        for i in range(60):  # a 4096-pose crowd with per-pose limits: the segment-parallel mapping reads the limit-set record too
+            c_, d_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c_.record()
+            R.solve_with_limits_raw(hs, LATENCY_BATCH, idx_dev, lt, lo_, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+            d_.record()
+            torch.cuda.synchronize()
+            if i >= 10:
+                lat_l.append(c_.elapsed_time(d_))
+        limit_sets = {"sets": 4, "poses": n, "ms_per_launch": lms, "solves_per_s": n / (lms * 1e-3), "latency_p50_ms_4096": float(np.median(lat_l)),
+                      "authoring": {"sets": info_m["n_sets"], "seconds": info_m["author_seconds"], "host_threads": info_m["author_threads"],
+                                    "sets_per_s": info_m["n_sets"] / info_m["author_seconds"] if info_m["author_seconds"] > 0 else None,
+                                    "table_bytes": info_m["table_bytes"], "bytes_per_set": info_m["bytes_per_set"]},
+                      "note": "mbik_limit_sets_create (host authoring on all host threads) / mbik_solve_batch_limits, device-resident: kusudama data read per pose "
+                              "from a device table instead of the rig blob"}
         R.destroy_limit_sets(hs)
     except Exception as e:
         limit_sets = {"error": str(e)}
@@ -512,17 +660,21 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(world, args.poses),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * npins * 48) * world, "d2h_bytes_per_step": int(n * nb * 40) * world,
-                "ms_per_step": e2e_s / args.steps * 1e3},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * npins * 48) * world, "d2h_bytes_per_step": int(n * nsolved * 40) * world,
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                "output_layout": f"MBIK_OUT_SOLVED_ONLY: position / rotation / scale of the {nsolved} bones of bone_list (what the reference writes to the skeleton)",
+                "full_skeleton_layout": {"value": total * full_steps / e2e_full_s, "unit": UNIT, "d2h_bytes_per_step": int(n * nb * 40) * world, "steps": full_steps}},
         "gpu_launches": args.steps * world,
+        "strong_scaling_1M_batch": strong,
         "latency_p50_ms_4096": p50,
         "latency_p50_ms_4096_thread_per_pose_mapping": p50_thread_per_pose,
         "latency_small_batches": small,
         "latency_mapping": "segment-parallel: 32 poses per CTA, %d warps (one per concurrently solvable segment), %d phases per iteration" % (R.info["sp_roles"], R.info["sp_phases"]),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "other_rigs_device_resident": other,
-        "strong_scaling_1M_batch": strong,
+        "configs": configs,
+        "stream_e2e": stream_e2e,
+        "single_process_multi_gpu_e2e": single_process,
         "host_link": host_link,
         "numa_binding_rank0": numa_binding,
         "limit_sets_device_resident": limit_sets,

@@ -107,7 +107,7 @@ int throughput_block_threads(const SolveArgs &a, int variant, int sm_count) {
 	// 1.73 waves of 512-thread CTAs pays for 2.  Wave-balanced size: the smallest instantiated CTA with which the same
 	// number of waves covers the batch -- 131 072 poses on 148 SMs run as 2 full waves of 448 threads instead of one
 	// full and one 73 % wave of 512 (BASELINE config 3: a 1M batch sharded over 8 GPUs).
-	if (variant == 0 || variant == 1 || variant == 3) {
+	if (variant <= 3) {
 		static const bool balanced = !(getenv("MBIK_WAVE_BALANCE") && atoi(getenv("MBIK_WAVE_BALANCE")) == 0);
 		if (balanced) {
 			const size_t per_wave = (size_t)sm_count * kBlockThreads;

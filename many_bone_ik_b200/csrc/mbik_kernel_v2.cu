@@ -18,6 +18,10 @@ cudaError_t launch_v2(const SolveArgs &a, int threads, cudaStream_t stream) {
 			return launch_variant<64, 8, 1, 32>(a, stream);
 		case 128:
 			return launch_variant<64, 8, 1, 128>(a, stream);
+		case 384: // wave-balanced sizes for large batches (launch_solve): the last wave of CTAs is as full as the others
+			return launch_variant<64, 8, 1, 384>(a, stream);
+		case 448:
+			return launch_variant<64, 8, 1, 448>(a, stream);
 		default:
 			return launch_variant<64, 8, 1, kBlockThreads>(a, stream);
 	}
