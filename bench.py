@@ -343,7 +343,7 @@ def main():
     # ---- steady state of a crowd that lives on the device: mbik_stream_* (frame f+1 starts from frame f's solution as the
     # skeleton holds it; only targets go up, only the solved bones' poses come down -- or nothing at all) ----
     stream_e2e = None
-    frames = max(2, min(args.steps, 6))
+    frames = 16  # enough frames that the pipeline's fill (first upload) and drain (last download) do not dominate
     stream_local = [float("inf"), float("inf")]  # seconds for `frames` frames with / without the pose download (this rank)
     stream_err = None
     try:
