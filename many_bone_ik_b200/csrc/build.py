@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libmbik.so")
 SOURCES = ["mbik_capi.cu", "mbik_flatten.cu", "mbik_kernel.cu", "mbik_kernel_v0.cu", "mbik_kernel_v1.cu", "mbik_kernel_v2.cu", "mbik_kernel_v3.cu",
-           "mbik_kernel_v4.cu", "mbik_kernel_v5.cu", "mbik_kernel_l0.cu", "mbik_kernel_l1.cu", "mbik_kernel_l2.cu", "mbik_kernel_l3.cu", "mbik_kernel_l4.cu", "mbik_kernel_l5.cu", "mbik_kernel_sp0.cu", "mbik_kernel_sp1.cu", "mbik_kernel_sp3.cu", "mbik_kernel_sp4.cu", "mbik_peak.cu", "mbik_selftest.cu"]
+           "mbik_kernel_v4.cu", "mbik_kernel_v5.cu", "mbik_kernel_v6.cu", "mbik_kernel_l0.cu", "mbik_kernel_l1.cu", "mbik_kernel_l2.cu", "mbik_kernel_l3.cu", "mbik_kernel_l4.cu", "mbik_kernel_l5.cu", "mbik_kernel_sp0.cu", "mbik_kernel_sp1.cu", "mbik_kernel_sp3.cu", "mbik_kernel_sp4.cu", "mbik_peak.cu", "mbik_selftest.cu"]
 HEADERS = ["mbik_blob.h", "mbik_flatten.h", "mbik_kernel.h", "mbik_kernel_body.cuh", "mbik_math.cuh", os.path.join("..", "..", "include", "mbik.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",

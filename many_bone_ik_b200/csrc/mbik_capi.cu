@@ -294,6 +294,10 @@ int resolve_device(const mbik_solve_params *params, int *device) {
 // what launch_solve needs to know about the rig's segment-parallel schedule (mbik_blob.h: BlobSpan)
 void set_launch_hints(mbik::SolveArgs &a, const mbik::FlatRig &F, uint32_t flags) {
 	a.n_solved = (int32_t)F.bones.size();
+	a.n_bones = F.n_bones;
+	a.n_pins = (int32_t)F.pins.size();
+	a.max_seg_len = F.max_seg_len;
+	a.max_stack = F.max_stack;
 	a.sp_roles = F.sp_roles;
 	a.sp_team_bytes = (int32_t)((size_t)F.sp_team_bufs * F.sp_team_headings * 6 * 32 * sizeof(float));
 	a.sp_gain = F.sp_critical_cost > 0 ? (float)(F.sp_serial_cost / F.sp_critical_cost) : 1.0f;
@@ -584,9 +588,12 @@ int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
 	rig->desc.assign(desc);
 	rig->n_solved = (int)rig->flat.bone_order.size();
 	rig->variant = mbik::kernel_variant_for(rig->n_solved, rig->flat.max_seg_len, rig->flat.max_stack, rig->flat.blob.size());
+	if (rig->variant == 5 && reinterpret_cast<const mbik::BlobHeader *>(rig->flat.blob.data())->resident_bytes > mbik::kResidentBlobBudget) {
+		rig->variant = mbik::kDynVariant; // constants beyond the shared-memory budget even without the walk list: read in place
+	}
 	if (rig->variant < 0) {
 		delete rig;
-		return fail(MBIK_ERR_UNSUPPORTED, "rig exceeds the largest kernel variant (256 solved bones, walk stack depth 32)");
+		return fail(MBIK_ERR_UNSUPPORTED, "rig exceeds the index types of the schedule (16383 solved bones, walk stack depth 127)");
 	}
 	{
 		std::string verr;
@@ -603,7 +610,7 @@ int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
 			}
 		}
 	}
-	if (reinterpret_cast<const mbik::BlobHeader *>(rig->flat.blob.data())->resident_bytes > mbik::kResidentBlobBudget) {
+	if (rig->variant != mbik::kDynVariant && reinterpret_cast<const mbik::BlobHeader *>(rig->flat.blob.data())->resident_bytes > mbik::kResidentBlobBudget) {
 		delete rig;
 		return fail(MBIK_ERR_UNSUPPORTED, "rig constants exceed the shared-memory budget (200 KiB without the walk list)");
 	}

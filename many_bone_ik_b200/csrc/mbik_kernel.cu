@@ -7,6 +7,9 @@ namespace mbik {
 
 int kernel_variant_for(int n_solved, int max_seg_len, int max_stack, size_t blob_bytes) {
 	for (int v = 0; v < kNumVariants; v++) {
+		if (v == kDynVariant) { // nothing compiled fits: the unbounded variant, within the blob's index types
+			return (n_solved <= kVariants[v][0] && max_stack <= kVariants[v][2]) ? v : -1;
+		}
 		// the small variants keep their scratch transforms in shared memory (up to 150 KiB) next to the rig blob
 		if (v <= 2 && blob_bytes > 72 * 1024) {
 			continue;
@@ -33,7 +36,7 @@ int kernel_capacity_of_variant(int v) { return (v >= 0 && v < kNumVariants) ? kV
 // kernel's shared instruction stream is the better use of it (measured, humanoid22: 8192 poses 0.81 vs 1.55 ms,
 // 16384 poses 1.69 vs 1.58 ms; quad80: 8192 poses 6.3 vs 11.3 ms).
 int segment_parallel_choice(const SolveArgs &a, int variant, int sm_count) {
-	if (a.sched_mode == 1 || a.sp_roles < (a.sched_mode == 2 ? 1 : 2) || a.sp_roles > kMaxSpRoles || variant == 2 || variant == 5) {
+	if (a.sched_mode == 1 || a.sp_roles < (a.sched_mode == 2 ? 1 : 2) || a.sp_roles > kMaxSpRoles || variant == 2 || variant >= 5) {
 		return 0;
 	}
 	const size_t smem = sp_smem_bytes(a);
@@ -131,6 +134,9 @@ cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStre
 	const bool lims = a.limit_table != nullptr;
 	if (lims && (!a.limit_index || a.n_limit_sets < 1)) {
 		return cudaErrorInvalidValue;
+	}
+	if (variant == kDynVariant) {
+		return launch_v6(a, sm_count, stream);
 	}
 	// segment-parallel mapping with per-pose limit sets: compiled without stabilisation only
 	const int sp = (lims && a.stabilize) ? 0 : segment_parallel_choice(a, variant, sm_count);

@@ -36,6 +36,9 @@ struct SolveArgs {
 	const int32_t *limit_index = nullptr;
 	uint32_t limit_stride = 0;
 	int32_t n_limit_sets = 0;
+	// unbounded-rig variant only (solve_body DYN): sizes of the rig for the launch loop, and this launch's workspace
+	int32_t n_bones = 0, n_pins = 0, max_seg_len = 0, max_stack = 0;
+	float *workspace = nullptr;
 	int32_t newton_iters = 0;  // mbik_solve_params::newton_iters (0 = the reference's QCP: no eigenvalue refinement)
 	uint32_t out_flags = 0;    // OUT_* below
 };
@@ -46,8 +49,11 @@ enum : uint32_t {
 
 // Compiled size variants {solved-bone capacity, longest segment, walk-stack depth}; per-pose thread-local state is
 // NB*12 + NSEG*12 + NSTK*12 floats, so tight variants keep more of it in L1/L2.
-constexpr int kNumVariants = 6;
-constexpr int kVariants[kNumVariants][3] = { { 20, 4, 2 }, { 32, 8, 4 }, { 64, 8, 1 }, { 64, 16, 8 }, { 128, 128, 16 }, { 256, 256, 32 } };
+// The last entry is the unbounded variant (solve_body DYN: nothing sized at compile time); its limits are those of the blob's
+// index types (int16 bone indices, int8 stack slots).
+constexpr int kNumVariants = 7;
+constexpr int kDynVariant = 6;
+constexpr int kVariants[kNumVariants][3] = { { 20, 4, 2 }, { 32, 8, 4 }, { 64, 8, 1 }, { 64, 16, 8 }, { 128, 128, 16 }, { 256, 256, 32 }, { 16383, 16383, 127 } };
 
 // index of the smallest kernel variant that fits the rig, or -1 if none does
 int kernel_variant_for(int n_solved, int max_seg_len, int max_stack, size_t blob_bytes);
@@ -69,6 +75,8 @@ cudaError_t launch_lims_v2(const SolveArgs &a, cudaStream_t stream);
 cudaError_t launch_lims_v3(const SolveArgs &a, cudaStream_t stream);
 cudaError_t launch_lims_v4(const SolveArgs &a, cudaStream_t stream);
 cudaError_t launch_lims_v5(const SolveArgs &a, cudaStream_t stream);
+// unbounded-rig variant (mbik_kernel_v6.cu): plain / stabilisation / limit sets / both
+cudaError_t launch_v6(const SolveArgs &a, int sm_count, cudaStream_t stream);
 
 // segment-parallel instantiations (mbik_kernel_sp*.cu); min_groups_per_sm 1 = full register budget, 2 = 128 registers
 // (several 32-pose groups per SM)

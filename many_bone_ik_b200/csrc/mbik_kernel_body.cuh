@@ -145,17 +145,22 @@ __device__ __forceinline__ void st_x34(float *A, int i, const X34 &t) {
 }
 // Per-pose scratch transforms (segment parent-global chain, walk stack): either a thread-local array or, when
 // STRIDE > 0, a column of a [word][thread] shared-memory matrix (conflict-free: consecutive lanes, consecutive words).
+// STRIDE < 0: a column of a [slot][word][thread] matrix in GLOBAL memory whose thread count `ds` is only known at launch
+// (the unbounded-rig variant's workspace).
 template <int STRIDE>
 struct Scratch {
 	float *p;
+	int ds; // STRIDE < 0 only
+	__device__ __forceinline__ size_t stride() const { return STRIDE > 0 ? (size_t)STRIDE : (STRIDE < 0 ? (size_t)ds : (size_t)1); }
 	__device__ __forceinline__ X34 ld(int i) const {
 		X34 t;
-		const float *q = p + i * 12 * (STRIDE > 0 ? STRIDE : 1);
+		const size_t st_ = stride();
+		const float *q = p + (size_t)i * 12 * st_;
 #pragma unroll
 		for (int k = 0; k < 9; k++) {
-			t.b.m[k] = q[k * (STRIDE > 0 ? STRIDE : 1)];
+			t.b.m[k] = q[k * st_];
 		}
-		t.o = v3(q[9 * (STRIDE > 0 ? STRIDE : 1)], q[10 * (STRIDE > 0 ? STRIDE : 1)], q[11 * (STRIDE > 0 ? STRIDE : 1)]);
+		t.o = v3(q[9 * st_], q[10 * st_], q[11 * st_]);
 		return t;
 	}
 	// thread-local arrays only: ask L2 for the 48 bytes of transform i (three 16-byte vectors = three interleaved lines)
@@ -180,14 +185,15 @@ struct Scratch {
 		}
 	}
 	__device__ __forceinline__ void st(int i, const X34 &t) const {
-		float *q = p + i * 12 * (STRIDE > 0 ? STRIDE : 1);
+		const size_t st_ = stride();
+		float *q = p + (size_t)i * 12 * st_;
 #pragma unroll
 		for (int k = 0; k < 9; k++) {
-			q[k * (STRIDE > 0 ? STRIDE : 1)] = t.b.m[k];
+			q[k * st_] = t.b.m[k];
 		}
-		q[9 * (STRIDE > 0 ? STRIDE : 1)] = t.o.x;
-		q[10 * (STRIDE > 0 ? STRIDE : 1)] = t.o.y;
-		q[11 * (STRIDE > 0 ? STRIDE : 1)] = t.o.z;
+		q[9 * st_] = t.o.x;
+		q[10 * st_] = t.o.y;
+		q[11 * st_] = t.o.z;
 	}
 };
 
@@ -689,43 +695,52 @@ __device__ __forceinline__ void team_barrier(int id, int n_threads) { asm volati
 // of the rig blob.  The records are built by the same host code as the blob (bit-exact: the tangent-circle construction
 // goes through the host libm, like the reference), and the schedule (which bones carry limits, cone counts) is the
 // rig's: only values vary per pose.  Separate instantiations; the default path does not see any of it.
-template <int NB, int NSEG, int NSTK, bool STAB, int SCR_STRIDE, bool SP = false, bool LIMS = false>
+// DYN (the unbounded-rig variant, mbik_kernel_v6.cu): the reference has no bone limit (src/ik_bone_segment_3d.cpp:352-427), so
+// rigs past the largest compiled capacity -- more than 256 solved bones, a walk stack deeper than 32, or constants that do
+// not fit shared memory -- run this instantiation: nothing is sized at compile time.  The rig constants are read in place
+// from global memory (uniform loads, L1-resident; no staging), and ALL per-pose state -- local poses, segment chain, walk
+// stack -- lives in [slot][word][thread] columns of a global workspace sized at launch (SolveArgs::workspace).  Same
+// arithmetic, same order, same bits; it is slow (every state access is a global access) and exists for completeness.
+template <int NB, int NSEG, int NSTK, bool STAB, int SCR_STRIDE, bool SP = false, bool LIMS = false, bool DYN = false>
 __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t bar;
 
 	// stage the rig constants: one elected thread arms the mbarrier and issues the bulk copy
-	if (threadIdx.x == 0) {
-		mbar_init(&bar, 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		mbar_expect_tx(&bar, a.blob_bytes);
-		uint32_t done = 0;
-		while (done < a.blob_bytes) { // bulk copies are issued in <= 64 KiB pieces
-			uint32_t n = a.blob_bytes - done;
-			n = n > 65536u ? 65536u : n;
-			tma_bulk_g2s(smem + done, a.blob + done, n, &bar);
-			done += n;
+	if (!DYN) {
+		if (threadIdx.x == 0) {
+			mbar_init(&bar, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			mbar_expect_tx(&bar, a.blob_bytes);
+			uint32_t done = 0;
+			while (done < a.blob_bytes) { // bulk copies are issued in <= 64 KiB pieces
+				uint32_t n = a.blob_bytes - done;
+				n = n > 65536u ? 65536u : n;
+				tma_bulk_g2s(smem + done, a.blob + done, n, &bar);
+				done += n;
+			}
+		}
+		mbar_wait(&bar, 0);
 	}
-	mbar_wait(&bar, 0);
 
-	const BlobHeader &H = *reinterpret_cast<const BlobHeader *>(smem);
-	const BlobStep *steps = reinterpret_cast<const BlobStep *>(smem + H.off_steps);
-	const BlobBone *bones = reinterpret_cast<const BlobBone *>(smem + H.off_bones);
-	const BlobEff *effs = reinterpret_cast<const BlobEff *>(smem + H.off_effs);
+	const unsigned char *base = DYN ? a.blob : smem;
+	const BlobHeader &H = *reinterpret_cast<const BlobHeader *>(base);
+	const BlobStep *steps = reinterpret_cast<const BlobStep *>(base + H.off_steps);
+	const BlobBone *bones = reinterpret_cast<const BlobBone *>(base + H.off_bones);
+	const BlobEff *effs = reinterpret_cast<const BlobEff *>(base + H.off_effs);
 	// large-rig variant (NB > 128): rigs in the tail layout keep the walk list in global memory (uniform loads through L1)
-	const BlobFk *fk = reinterpret_cast<const BlobFk *>((NB > 128 && H.resident_bytes < H.total_bytes ? a.blob : smem) + H.off_fk);
-	const BlobCone *cones = reinterpret_cast<const BlobCone *>(smem + H.off_cones);
-	const BlobPass *pass = reinterpret_cast<const BlobPass *>(smem + H.off_pass);
-	const int16_t *chain = reinterpret_cast<const int16_t *>(smem + H.off_chain);
-	const float *rest = reinterpret_cast<const float *>(smem + H.off_rest);
-	const BlobSpan *spans = reinterpret_cast<const BlobSpan *>(smem + H.off_sched);
-	const int32_t *step_path = reinterpret_cast<const int32_t *>(smem + H.off_step_path);
-	const BlobPathRef *path_refs = reinterpret_cast<const BlobPathRef *>(smem + H.off_path_refs);
-	const int16_t *paths = reinterpret_cast<const int16_t *>(smem + H.off_paths);
+	const BlobFk *fk = reinterpret_cast<const BlobFk *>((DYN || (NB > 128 && H.resident_bytes < H.total_bytes) ? a.blob : smem) + H.off_fk);
+	const BlobCone *cones = reinterpret_cast<const BlobCone *>(base + H.off_cones);
+	const BlobPass *pass = reinterpret_cast<const BlobPass *>(base + H.off_pass);
+	const int16_t *chain = reinterpret_cast<const int16_t *>(base + H.off_chain);
+	const float *rest = reinterpret_cast<const float *>(base + H.off_rest);
+	const BlobSpan *spans = reinterpret_cast<const BlobSpan *>(base + H.off_sched);
+	const int32_t *step_path = reinterpret_cast<const int32_t *>(base + H.off_step_path);
+	const BlobPathRef *path_refs = reinterpret_cast<const BlobPathRef *>(base + H.off_path_refs);
+	const int16_t *paths = reinterpret_cast<const int16_t *>(base + H.off_paths);
 	const int sp_roles = SP ? H.sp_roles : 1, sp_phases = SP ? H.sp_phases : 1, sp_slots = SP ? H.sp_slots : 1;
 	const int role = SP ? (int)(threadIdx.x >> 5) : 0;
 
@@ -752,16 +767,20 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	}
 
 	// Per-pose state (thread-local, lane-interleaved):
-	float L_local[SP ? 1 : NB * 12]; // local transform of every solved bone (t order) -- the only state carried between steps
+	float L_local[(SP || DYN) ? 1 : NB * 12]; // local transform of every solved bone (t order) -- the only state carried between steps
+	// DYN: this thread's column of the launch's global workspace: [ns local poses | max_seg_len chain slots | max_stack stack slots]
+	const int ws_threads = DYN ? (int)(gridDim.x * blockDim.x) : 0;
+	float *ws_col = DYN ? a.workspace + (size_t)blockIdx.x * blockDim.x + threadIdx.x : nullptr;
 	// SP: the group's local poses in shared memory behind the rig blob, [bone][word][lane]
-	const Scratch<SP ? 32 : 0> L{ SP ? reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + (threadIdx.x & 31) : L_local };
+	const Scratch<DYN ? -1 : (SP ? 32 : 0)> L{ DYN ? ws_col : (SP ? reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + (threadIdx.x & 31) : L_local), ws_threads };
 	// globals of the parents of the current segment's bones (ancestors do not move while a segment is being solved,
 	// so this replaces the reference's lazy global-transform cache) and of the branch points of the current walk
-	float Pseg_local[SCR_STRIDE > 0 ? 1 : NSEG * 12];
-	float Gstk_local[SCR_STRIDE > 0 ? 1 : NSTK * 12];
+	float Pseg_local[(SCR_STRIDE > 0 || DYN) ? 1 : NSEG * 12];
+	float Gstk_local[(SCR_STRIDE > 0 || DYN) ? 1 : NSTK * 12];
 	float *scr = reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + threadIdx.x; // (SP: SCR_STRIDE == 0, unused)
-	const Scratch<SCR_STRIDE> Pseg{ SCR_STRIDE > 0 ? scr : Pseg_local };
-	const Scratch<SCR_STRIDE> Gstk{ SCR_STRIDE > 0 ? scr + NSEG * 12 * SCR_STRIDE : Gstk_local };
+	const Scratch<DYN ? -1 : SCR_STRIDE> Pseg{ DYN ? ws_col + (size_t)H.n_solved * 12 * ws_threads : (SCR_STRIDE > 0 ? scr : Pseg_local), ws_threads };
+	const Scratch<DYN ? -1 : SCR_STRIDE> Gstk{ DYN ? ws_col + (size_t)(H.n_solved + H.max_seg_len) * 12 * ws_threads
+	                                                  : (SCR_STRIDE > 0 ? scr + NSEG * 12 * SCR_STRIDE : Gstk_local), ws_threads };
 	// stabilisation only (STAB variants): effector-bone origins from before the step (what the step's target
 	// headings were built from) and the segment's previous_deviation (src/ik_bone_segment_3d.h:63)
 	float TipO[STAB ? kMaxStabEffectors * 3 : 1];
@@ -1227,7 +1246,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	// IK-bone transforms (see write_bone_pose); bones outside bone_list keep their start pose either way.
 	uint32_t status = 0;
 	const bool compact = (a.out_flags & OUT_COMPACT) != 0, recompose = (a.out_flags & OUT_LOCAL_RECOMPOSED) != 0;
-	const int16_t *list_row = reinterpret_cast<const int16_t *>(smem + H.off_list_row);
+	const int16_t *list_row = reinterpret_cast<const int16_t *>(base + H.off_list_row);
 	float *my_out = a.out_pose ? a.out_pose + pose * (size_t)(compact ? ns : n_bones) * 10 : nullptr;
 	float *my_loc = a.out_local ? a.out_local + pose * (size_t)n_bones * 12 : nullptr;
 	if (live) {
@@ -1335,6 +1354,52 @@ static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 	return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// unbounded-rig variant (solve_body DYN): 128-thread CTAs, state in a stream-ordered global workspace, the batch cut into
+// launches of at most `ws_threads` poses that reuse it (launches on one stream run in order)
+// ---------------------------------------------------------------------------------------------------
+template <bool STAB, bool LIMS>
+__global__ void __launch_bounds__(128) mbik_solve_kernel_dyn(SolveArgs a) {
+	solve_body<32767, 1, 1, STAB, 0, false, LIMS, true>(a);
+}
+template <bool STAB, bool LIMS>
+static cudaError_t launch_variant_dyn(const SolveArgs &a0, int sm_count, cudaStream_t stream) {
+	const size_t per_thread = (size_t)(a0.n_solved + a0.max_seg_len + a0.max_stack) * 12 * sizeof(float);
+	size_t threads = ((a0.n_poses + 127) / 128) * 128;
+	const size_t resident = (size_t)(sm_count > 0 ? sm_count : 148) * 128 * 4;
+	threads = threads < resident ? threads : resident;
+	if (const char *env = getenv("MBIK_DYN_THREADS")) { // test knob: poses per launch of the unbounded variant
+		const size_t v = (size_t)atoll(env);
+		if (v >= 128) {
+			threads = (v / 128) * 128;
+		}
+	}
+	while (threads > 128 && threads * per_thread > ((size_t)2 << 30)) { // cap the workspace at 2 GiB
+		threads = ((threads / 2 + 127) / 128) * 128;
+	}
+	float *ws = nullptr;
+	cudaError_t e = cudaMallocAsync((void **)&ws, threads * per_thread, stream);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	const size_t out_rows = (a0.out_flags & OUT_COMPACT) ? (size_t)a0.n_solved : (size_t)a0.n_bones;
+	for (size_t first = 0; first < a0.n_poses && e == cudaSuccess; first += threads) {
+		SolveArgs a = a0;
+		a.workspace = ws;
+		a.n_poses = a0.n_poses - first < threads ? a0.n_poses - first : threads;
+		a.targets = a0.targets ? a0.targets + first * (size_t)a0.n_pins * 12 : nullptr;
+		a.start_pose = a0.start_pose ? a0.start_pose + first * (size_t)a0.n_bones * 12 : nullptr;
+		a.out_pose = a0.out_pose ? a0.out_pose + first * out_rows * 10 : nullptr;
+		a.out_local = a0.out_local ? a0.out_local + first * (size_t)a0.n_bones * 12 : nullptr;
+		a.out_status = a0.out_status ? a0.out_status + first : nullptr;
+		a.limit_index = a0.limit_index ? a0.limit_index + first : nullptr;
+		mbik_solve_kernel_dyn<STAB, LIMS><<<(unsigned)((a.n_poses + 127) / 128), 128, 0, stream>>>(a);
+		e = cudaGetLastError();
+	}
+	cudaFreeAsync(ws, stream);
+	return e;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // segment-parallel (small-batch) kernel: one CTA = one group of 32 poses x sp_roles warps

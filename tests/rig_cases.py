@@ -304,4 +304,19 @@ def big_tree240():
 
 # rigs beyond 128 solved bones: their own dict (not part of the committed golden fixtures); compared live with the oracle
 # and, where it travelled, with the reference module's own code
+def chain300():
+    """300 solved bones in one chain with three pins: beyond the {256, 256, 32} kernel variant -> the unbounded variant."""
+    n = 300
+    parent = np.arange(-1, n - 1, dtype=np.int32)
+    rest = np.zeros((n, 12), np.float32)
+    rest[:, 0] = rest[:, 4] = rest[:, 8] = 1.0
+    rest[1:, 10] = 0.05
+    r = rigs.Rig("chain300", [f"b{i}" for i in range(n)], parent, rest, iterations=2)
+    r.pins = [dict(bone=0, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2)), dict(bone=140, weight=0.5, mpf=0.5, priorities=(0.2, 0.0, 0.2)),
+              dict(bone=n - 1, weight=1.0, mpf=1.0, priorities=(0.2, 0.1, 0.2))]
+    rigs._add_constraints(r, {b: (1 + b % 3, 20, 0, -20, 40) for b in range(10, n, 10)})
+    return r
+
+
 LARGE_RIGS = {f.__name__: f for f in [chain150, chain200, big_tree240]}
+UNBOUNDED_RIGS = {f.__name__: f for f in [chain300]}

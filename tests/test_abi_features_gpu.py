@@ -153,3 +153,43 @@ def test_large_blob_on_the_64_bone_variant_runs_at_every_batch_size(n):
     assert _same(out[:96], small)
     ref, ref_st = O.solve_batch(rig, T[-48:], threads=8)
     assert _same(out[-48:], ref) and np.array_equal(st[-48:], ref_st)
+
+
+def test_unbounded_variant_equals_the_oracle(monkeypatch):
+    """Rigs past every compiled capacity (here 300 solved bones; the reference has no limit) run the variant that sizes
+    nothing at compile time -- constants read in place, per-pose state in a stream-ordered global workspace, the batch cut
+    into launches that reuse it.  Same bits as the oracle: plain, with a start pose, through the host and the device path,
+    with several launches per call, with per-pose limit sets."""
+    import torch
+    import limit_set_cases as LS
+    from many_bone_ik_b200._capi import MBIK_IO_DEVICE
+    rig = rig_cases.chain300()
+    R = BatchedIKRig(rig)
+    assert R.info["kernel_capacity"] == 16383
+    n = 200
+    T = rigs.random_targets(rig, 3, n)
+    sp = rig_cases.perturbed_start_pose(rig, n, seed=8)
+    for start in (None, sp):
+        ref = O.solve_batch(rig, T, start_pose=start, want_local=True, threads=8)
+        got = R.solve(T, start_pose=start, want_local=True)
+        for a, b in zip(got, ref):
+            assert _same(a, b)
+    monkeypatch.setenv("MBIK_DYN_THREADS", "128")  # 200 poses = two launches sharing one workspace
+    got2 = R.solve(T, start_pose=sp, want_local=True)
+    for a, b in zip(got2, got):
+        assert _same(a, b)
+    t_dev = torch.from_numpy(T).cuda()
+    s_dev = torch.from_numpy(sp).cuda()
+    o_dev = torch.empty((n, R.info["n_solved"], 10), dtype=torch.float32, device="cuda")
+    R.solve_raw(n, t_dev, o_dev, start_pose=s_dev, device=0, flags=MBIK_IO_DEVICE | _capi.MBIK_OUT_SOLVED_ONLY, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert _same(o_dev.cpu().numpy(), got[0][:, R.bone_order()])
+    monkeypatch.delenv("MBIK_DYN_THREADS")
+    sets = LS.variants(rig, 2)
+    h = R.create_limit_sets(sets)
+    idx = (np.arange(64) % 2).astype(np.int32)
+    out, st = R.solve_with_limits(h, idx, T[:64])
+    for s_i in range(2):
+        want, _ = O.solve_batch(LS.rig_with(rig, sets[s_i]), T[:64], threads=8)
+        assert _same(out[idx == s_i], want[idx == s_i])
+    R.destroy_limit_sets(h)

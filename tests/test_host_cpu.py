@@ -181,17 +181,15 @@ def test_rig_create_argument_errors():
     assert lib.mbik_rig_destroy(None) == 0
 
 
-def test_rig_too_large_is_unsupported_not_truncated():
-    n = 300
-    parent = np.arange(-1, n - 1, dtype=np.int32)
-    rest = np.zeros((n, 12), np.float32)
-    rest[:, 0] = rest[:, 4] = rest[:, 8] = 1.0
-    rest[1:, 10] = 0.05
-    r = rigs.Rig("chain300", [f"b{i}" for i in range(n)], parent, rest, iterations=2)
-    r.pins = [dict(bone=n - 1, weight=1.0, mpf=1.0, priorities=(0.2, 0.0, 0.2))]
-    with pytest.raises(MbikError) as ei:
-        BatchedIKRig(r)
-    assert ei.value.code == -3
+def test_rigs_beyond_every_compiled_capacity_select_the_unbounded_variant():
+    """The reference has no bone limit (src/ik_bone_segment_3d.cpp:352-427).  300 solved bones are past the largest compiled
+    variant {256, 256, 32}: the rig is accepted and runs the unbounded variant (state in a global workspace), whose
+    capacity is that of the schedule's index types."""
+    r = rig_cases.chain300()
+    R = BatchedIKRig(r)
+    assert R.info["n_solved"] == 300 and R.info["kernel_capacity"] == 16383
+    ref = O.rig_facts(r)
+    assert np.array_equal(R.bone_order(), ref["bone_order"])
 
 
 @pytest.mark.parametrize("name", sorted(rig_cases.LARGE_RIGS))
