@@ -426,6 +426,9 @@ def main():
     single_process = None
     if world > 1:
         barrier()
+        # the other ranks wait on the CPU (a key of the rendezvous store), not inside a NCCL kernel that would share their GPU
+        # with rank 0's launches
+        store = dist.distributed_c10d._get_default_store()
         if rank == 0:
             try:
                 per = min(n, 1 << 19)
@@ -447,6 +450,9 @@ def main():
                 del th_, oh_
             except Exception as e:
                 single_process = {"error": str(e)}
+            store.set("mbik_single_process_done", "1")
+        else:
+            store.wait(["mbik_single_process_done"])
         barrier()
 
     if rank != 0:
