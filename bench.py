@@ -361,12 +361,34 @@ def main():
         del S
     except Exception as e:  # no collective inside the try: a rank that fails must not leave the others waiting
         stream_err = str(e)
+    # the per-frame kernel of a warm-started crowd (start = the previous frame's recomposed poses, same targets): its per-pose
+    # work differs from the cold, rest-pose start the headline times (other snaps trigger), so it is timed on its own
+    warm_ms = None
+    try:
+        from many_bone_ik_b200._capi import MBIK_LOCAL_RECOMPOSED
+        loc_a = torch.empty((n, nb, 12), dtype=torch.float32, device=dev)
+        loc_b = torch.empty((n, nb, 12), dtype=torch.float32, device=dev)
+        R.solve_raw(n, t_dev, o_dev, out_local=loc_a, device=local_rank, flags=MBIK_IO_DEVICE | MBIK_LOCAL_RECOMPOSED, stream=stream)
+        for _ in range(3):
+            R.solve_raw(n, t_dev, o_dev, start_pose=loc_a, out_local=loc_b, device=local_rank, flags=MBIK_IO_DEVICE | MBIK_LOCAL_RECOMPOSED, stream=stream)
+            loc_a, loc_b = loc_b, loc_a
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(4):
+            R.solve_raw(n, t_dev, o_dev, start_pose=loc_a, out_local=loc_b, device=local_rank, flags=MBIK_IO_DEVICE | MBIK_LOCAL_RECOMPOSED, stream=stream)
+            loc_a, loc_b = loc_b, loc_a
+        w1.record()
+        torch.cuda.synchronize()
+        warm_ms = w0.elapsed_time(w1) / 4
+        del loc_a, loc_b
+    except Exception as e:
+        stream_err = (stream_err or "") + f" warm kernel: {e}"
     barrier()
     st_dl, st_no = max_over_ranks(stream_local[0]), max_over_ranks(stream_local[1])
     stream_e2e = {"value_with_pose_download": total * frames / st_dl if np.isfinite(st_dl) else None,
                   "value_targets_only": total * frames / st_no if np.isfinite(st_no) else None, "unit": UNIT, "frames": frames,
                   "h2d_bytes_per_frame": int(n * npins * 48) * world, "d2h_bytes_per_frame_with_download": int(n * nsolved * 40) * world,
-                  "error": stream_err,
+                  "error": stream_err, "kernel_ms_per_warm_started_frame_rank0": warm_ms,
                   "note": "mbik_stream_submit x frames, then mbik_stream_sync: warm-started frames of the same 2^20-pose crowd per GPU, pinned host targets; "
                           "'targets_only' leaves the poses on the device (a renderer that skins on the GPU); ranks are not re-synchronised between frames"}
 
@@ -625,6 +647,11 @@ def main():
         hm = R.create_limit_sets(many)
         info_m = R.limit_sets_info(hm)
         R.destroy_limit_sets(hm)
+        os.environ["MBIK_AUTHOR_THREADS"] = "1"  # the same authoring on one host thread, for the scaling of the pool
+        h1_ = R.create_limit_sets(many[:512])
+        info_1 = R.limit_sets_info(h1_)
+        R.destroy_limit_sets(h1_)
+        del os.environ["MBIK_AUTHOR_THREADS"]
         hs = R.create_limit_sets(many[:4])
         idx_dev = (torch.arange(n, device=dev, dtype=torch.int32) % 4).contiguous()
         for _ in range(2):
@@ -648,7 +675,8 @@ def main():
         limit_sets = {"sets": 4, "poses": n, "ms_per_launch": lms, "solves_per_s": n / (lms * 1e-3), "latency_p50_ms_4096": float(np.median(lat_l)),
                       "authoring": {"sets": info_m["n_sets"], "seconds": info_m["author_seconds"], "host_threads": info_m["author_threads"],
                                     "sets_per_s": info_m["n_sets"] / info_m["author_seconds"] if info_m["author_seconds"] > 0 else None,
-                                    "table_bytes": info_m["table_bytes"], "bytes_per_set": info_m["bytes_per_set"]},
+                                    "table_bytes": info_m["table_bytes"], "bytes_per_set": info_m["bytes_per_set"],
+                                    "sets_per_s_one_thread": info_1["n_sets"] / info_1["author_seconds"] if info_1["author_seconds"] > 0 else None},
                       "note": "mbik_limit_sets_create (host authoring on all host threads) / mbik_solve_batch_limits, device-resident: kusudama data read per pose "
                               "from a device table instead of the rig blob"}
         R.destroy_limit_sets(hs)
