@@ -1090,7 +1090,14 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			}
 
 			if (!constraint_mode) {
-				M3 R2 = damp_and_slerp0(q, S.cos_half_damp, Gb.b, gb_bounded);
+				// the global basis of the bone before the step is read by the slerp only where it can poison (non-finite / huge
+				// entries): there it is recomputed from the re-read operands -- the same product, the same bits -- instead of
+				// being carried across the heading walk in 9 registers
+				M3 Gb_late = m3_identity();
+				if (!gb_bounded) {
+					Gb_late = node_parent ? m3_mul(P.b, Lb.b) : Lb.b;
+				}
+				M3 R2 = damp_and_slerp0(q, S.cos_half_damp, Gb_late, gb_bounded);
 				if (node_parent) {
 					Lb.b = rotate_local_with_global(Pinv, R2, P.b, Lb.b);
 				}

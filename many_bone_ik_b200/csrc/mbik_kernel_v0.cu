@@ -1,7 +1,11 @@
 // mbik_kernel_v0.cu -- instantiations of the solve kernel for the size variant {20 solved bones, segment 4, stack 2}.
 #include "mbik_kernel_body.cuh"
 
-// experiment knob (profiles/build_variant.py): CTA size of the large-batch instantiation
+// experiment knob (profiles/build_variant.py): CTA size of the large-batch instantiation.  640 threads (5 warps per scheduler,
+// 96 registers) was re-measured in round 2 after the register diet of the step (profiles/r2_exp_640_threads_lean.log): 27.4 M solves/s
+// as is, 29.3 M without the walk's child prefetch, 30.7 M with scalar Vector3 ops on top (112 B / 252 B of spill stores / loads left),
+// 28.9 M with every packed composite off (76 B / 164 B) -- against 33.3 M at 512 threads: per full wave the 20-warp builds deliver what
+// the 16-warp build does (the 96-register schedule is ~25 % slower per warp), and 2^20 poses quantise worse (11.07 waves -> 12).
 #ifndef MBIK_V0_BIG
 #define MBIK_V0_BIG 512
 #endif
