@@ -171,19 +171,21 @@ cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStre
 		}
 	}
 	const int threads = throughput_block_threads(a, variant, sm_count);
+	SolveArgs b = a;
+	b.sm_count = sm_count;
 	switch (variant) {
 		case 0:
 			return launch_v0(a, threads, stream);
 		case 1:
 			return launch_v1(a, threads, stream);
 		case 2:
-			return launch_v2(a, threads, stream);
+			return launch_v2(b, threads, stream);
 		case 3:
-			return launch_v3(a, threads, stream);
+			return launch_v3(b, threads, stream);
 		case 4:
-			return launch_v4(a, threads, stream);
+			return launch_v4(b, threads, stream);
 		default:
-			return launch_v5(a, threads, stream);
+			return launch_v5(b, threads, stream);
 	}
 }
 

@@ -39,6 +39,8 @@ struct SolveArgs {
 	// unbounded-rig variant only (solve_body DYN): sizes of the rig for the launch loop, and this launch's workspace
 	int32_t n_bones = 0, n_pins = 0, max_seg_len = 0, max_stack = 0;
 	float *workspace = nullptr;
+	// streamed-walk instantiation (solve_body GLW): chosen by the host for rigs with long effector walks; sm_count sizes its workspace
+	int32_t use_glw = 0, sm_count = 0;
 	int32_t newton_iters = 0;  // mbik_solve_params::newton_iters (0 = the reference's QCP: no eigenvalue refinement)
 	uint32_t out_flags = 0;    // OUT_* below
 };

@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 // Software pipelining of the effector walk (tuning knobs): request the local pose of walk child k+1 before the
 // products / headings of child k (on: +2 % humanoid22, +7 % quad80, +11 % chain64); hoist the effector's target
@@ -195,6 +196,81 @@ struct Scratch {
 		q[10 * st_] = t.o.y;
 		q[11 * st_] = t.o.z;
 	}
+};
+
+// GLW ("streamed walk", the large-batch instantiation of rigs whose effector walks are long -- chains): the local poses
+// live in a GLOBAL workspace as three float4 per bone instead of thread-local memory, so that the walks can stream them
+// through a small shared-memory ring with cp.async: the child poses of the next MBIK_GLW_DEPTH products are in flight while
+// the current product runs -- no registers held, no scoreboard stall -- where thread-local loads can only be one product
+// ahead (the registers they land in are live until used).  The per-pose state of such rigs (3 KB x 75 776 resident poses)
+// does not fit L2, every walk read is an HBM access, and with one product of look-ahead the kernel waits for HBM latency
+// (chain64: stall_long_sb 50 %, issue slots 43 % busy, 4.3 TB/s); with the ring it is bound by HBM bandwidth instead
+// (stall_long_sb 20 %, issue 62 %, 5.4 TB/s = 82 % of the measured peak; 69.3 -> 55.4 ms per 75 776 poses under ncu,
+// profiles/r2_exp_glw_kernel_chain64_75776.txt).  Rigs with short walks (quad80: L2 hit rate 55 %) lose 8-17 % to the
+// extra address arithmetic of the global path and keep thread-local state: the host picks per rig (FlatRig walk density).
+#ifndef MBIK_GLW_DEPTH
+#define MBIK_GLW_DEPTH 4
+#endif
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Workspace layout: warp-tiled, [warp of the launch][bone][vector 0..2][lane] float4 -- the 48 bytes x 32 lanes of one bone of
+// one warp are 1536 contiguous bytes (three 512-byte lines), so one 64-bit multiply-add gives the address of a bone and the
+// three vectors are immediate offsets from it.  RT = threads of the CTA (compile time: the ring offsets are immediates too).
+// float4 per warp tile: n_solved bones x 96, padded by one 512-byte line so that the same bone of consecutive warps -- which
+// lockstepped warps touch at the same time -- does not sit a multiple of 96 KB apart (measured: 91.9 ms unpadded vs 56 ms for
+// chain64 at 448 threads: DRAM partition camping)
+__host__ __device__ __forceinline__ size_t glw_tile_float4(int n_solved) { return (size_t)n_solved * 96 + 32; }
+template <int RT>
+struct GStore {
+	const char *col; // this thread's base: workspace + (warp-of-launch * n_solved * 96 + lane) * 16
+	uint32_t ring;   // shared-memory address of this thread's ring column: (slot, v) at ring + ((slot * 3 + v) * RT) * 16
+	static __device__ __forceinline__ X34 unpack(float4 a, float4 b, float4 c) {
+		X34 t;
+		t.b.m[0] = a.x; t.b.m[1] = a.y; t.b.m[2] = a.z; t.b.m[3] = a.w;
+		t.b.m[4] = b.x; t.b.m[5] = b.y; t.b.m[6] = b.z; t.b.m[7] = b.w;
+		t.b.m[8] = c.x;
+		t.o = v3(c.y, c.z, c.w);
+		return t;
+	}
+	__device__ __forceinline__ X34 ld(int i) const {
+		const float4 *q = reinterpret_cast<const float4 *>(col + (size_t)(uint32_t)i * 1536u);
+		return unpack(q[0], q[32], q[64]);
+	}
+	__device__ __forceinline__ void st(int i, const X34 &t) const {
+		float4 *q = reinterpret_cast<float4 *>(const_cast<char *>(col) + (size_t)(uint32_t)i * 1536u);
+		q[0] = make_float4(t.b.m[0], t.b.m[1], t.b.m[2], t.b.m[3]);
+		q[32] = make_float4(t.b.m[4], t.b.m[5], t.b.m[6], t.b.m[7]);
+		q[64] = make_float4(t.b.m[8], t.o.x, t.o.y, t.o.z);
+	}
+	__device__ __forceinline__ void prefetch_l2(int) const {}
+	// asynchronous copy of bone i into ring slot `slot` (this thread's column only: no other thread reads it)
+	__device__ __forceinline__ void fetch(int i, int slot) const {
+		const char *q = col + (size_t)(uint32_t)i * 1536u;
+		const uint32_t d = ring + (uint32_t)slot * (48u * RT);
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q) : "memory");
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * RT), "l"(q + 512) : "memory");
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 32u * RT), "l"(q + 1024) : "memory");
+	}
+	__device__ __forceinline__ X34 slot_ld(int slot) const {
+		const uint32_t d = ring + (uint32_t)slot * (48u * RT);
+		float4 a, b, c;
+		asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(d));
+		asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(d + 16u * RT));
+		asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(d + 32u * RT));
+		return unpack(a, b, c);
+	}
+};
+
+template <bool G>
+struct PickStore {
+	template <class A, class B>
+	static __device__ __forceinline__ const A &get(const A &a, const B &) { return a; }
+};
+template <>
+struct PickStore<true> {
+	template <class A, class B>
+	static __device__ __forceinline__ const B &get(const A &, const B &b) { return b; }
 };
 
 // 3x3 from a 16-byte aligned, 12-float padded record (BlobBone matrices): three 128-bit loads
@@ -701,8 +777,10 @@ __device__ __forceinline__ void team_barrier(int id, int n_threads) { asm volati
 // from global memory (uniform loads, L1-resident; no staging), and ALL per-pose state -- local poses, segment chain, walk
 // stack -- lives in [slot][word][thread] columns of a global workspace sized at launch (SolveArgs::workspace).  Same
 // arithmetic, same order, same bits; it is slow (every state access is a global access) and exists for completeness.
-template <int NB, int NSEG, int NSTK, bool STAB, int SCR_STRIDE, bool SP = false, bool LIMS = false, bool DYN = false>
+template <int NB, int NSEG, int NSTK, bool STAB, int SCR_STRIDE, bool SP = false, bool LIMS = false, bool DYN = false, int GLWT = 0>
 __device__ __forceinline__ void solve_body(const SolveArgs &a) {
+	constexpr bool GLW = GLWT > 0; // GLWT = CTA size of the GLW instantiation
+	static_assert(!GLW || (!SP && !DYN && SCR_STRIDE == 0), "GLW: thread-per-pose mapping with thread-local scratch only");
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t bar;
 
@@ -767,12 +845,17 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	}
 
 	// Per-pose state (thread-local, lane-interleaved):
-	float L_local[(SP || DYN) ? 1 : NB * 12]; // local transform of every solved bone (t order) -- the only state carried between steps
+	float L_local[(SP || DYN || GLW) ? 1 : NB * 12]; // local transform of every solved bone (t order) -- the only state carried between steps
 	// DYN: this thread's column of the launch's global workspace: [ns local poses | max_seg_len chain slots | max_stack stack slots]
 	const int ws_threads = DYN ? (int)(gridDim.x * blockDim.x) : 0;
 	float *ws_col = DYN ? a.workspace + (size_t)blockIdx.x * blockDim.x + threadIdx.x : nullptr;
 	// SP: the group's local poses in shared memory behind the rig blob, [bone][word][lane]
-	const Scratch<DYN ? -1 : (SP ? 32 : 0)> L{ DYN ? ws_col : (SP ? reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + (threadIdx.x & 31) : L_local), ws_threads };
+	const Scratch<DYN ? -1 : (SP ? 32 : 0)> L_plain{ DYN ? ws_col : (SP ? reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + (threadIdx.x & 31) : L_local), ws_threads };
+	const GStore<GLW ? GLWT : 32> L_glw{
+		reinterpret_cast<const char *>(a.workspace) +
+				(GLW ? ((((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * glw_tile_float4(H.n_solved) + (threadIdx.x & 31)) * 16 : 0),
+		smem_u32(smem + ((a.blob_bytes + 127u) & ~127u)) + threadIdx.x * 16u };
+	const auto &L = PickStore<GLW>::get(L_plain, L_glw);
 	// globals of the parents of the current segment's bones (ancestors do not move while a segment is being solved,
 	// so this replaces the reference's lazy global-transform cache) and of the branch points of the current walk
 	float Pseg_local[(SCR_STRIDE > 0 || DYN) ? 1 : NSEG * 12];
@@ -810,6 +893,15 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	// all stalling on the same pipe at once, while the instruction stream stays one sliding window.
 	const int cohort = (int)(threadIdx.x >> 7), n_cohorts = (int)(blockDim.x >> 7);
 	const bool stagger = !SP && MBIK_STAGGER > 0 && n_cohorts >= 2 && (blockDim.x & 127u) == 0;
+	int glw_step = 0;
+	if constexpr (GLW) {
+		// the solved bone's own pose comes through two extra ring slots: step s reads slot D + (s & 1), which was requested at
+		// the start of step s - 1 (its value is final by then: a bone is only written by its own step)
+		if (n_steps > 0) {
+			L.fetch(steps[0].bone, MBIK_GLW_DEPTH);
+		}
+		cp_async_commit();
+	}
 	for (int it = 0; it < a.iterations; it++) {
 	for (int ph = 0; ph < sp_phases; ph++) {
 		if (SP && a.sp_trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
@@ -865,13 +957,30 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				}
 				X34 g = x_identity();
 				X34 l_next = x_identity();
-				if (S.chain_cnt > 0) {
+				if constexpr (GLW) {
+#pragma unroll
+					for (int j = 0; j < MBIK_GLW_DEPTH; j++) { // the same ring as the effector walk (idle here)
+						if (j < S.chain_cnt) {
+							L.fetch(chain[S.chain_off + j], j);
+						}
+						cp_async_commit();
+					}
+				} else if (S.chain_cnt > 0) {
 					l_next = L.ld(chain[S.chain_off]);
 				}
 				for (int k = 0; k < S.chain_cnt; k++) {
 					const int t = chain[S.chain_off + k];
+					if constexpr (GLW) {
+						cp_async_wait<MBIK_GLW_DEPTH - 1>();
+						l_next = L.slot_ld(k % MBIK_GLW_DEPTH);
+					}
 					const X34 l = l_next; // software-pipelined like the effector walk below
-					if (k + 1 < S.chain_cnt) {
+					if constexpr (GLW) {
+						if (k + MBIK_GLW_DEPTH < S.chain_cnt) {
+							L.fetch(chain[S.chain_off + k + MBIK_GLW_DEPTH], k % MBIK_GLW_DEPTH);
+						}
+						cp_async_commit();
+					} else if (k + 1 < S.chain_cnt) {
 						l_next = L.ld(chain[S.chain_off + k + 1]);
 					}
 					if (k == 0) {
@@ -891,7 +1000,18 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			X34 Gb;
 			{
 				const X34 P0 = S.parent >= 0 ? Pseg.ld(S.pslot) : x_identity();
-				const X34 L0 = L.ld(b);
+				X34 L0;
+				if constexpr (GLW) {
+					cp_async_wait<0>(); // requested a whole step ago
+					L0 = L.slot_ld(MBIK_GLW_DEPTH + (glw_step & 1));
+					if (n_steps > 1) { // (a one-bone rig re-reads the bone this step writes: requested after the store below)
+						const int s_next = s + 1 < n_steps ? s + 1 : 0;
+						L.fetch(steps[s_next].bone, MBIK_GLW_DEPTH + ((glw_step + 1) & 1));
+					}
+					cp_async_commit();
+				} else {
+					L0 = L.ld(b);
+				}
 				Gb = node_parent ? x_mul(P0, L0) : L0;
 			}
 			Q4 q = q4(0.0f, 0.0f, 0.0f, 1.0f);
@@ -999,7 +1119,17 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					// (lockstepped) warps of the CTA at once.
 					X34 run = Gb;
 					X34 child = x_identity();
-					if (MBIK_PIPE_CHILD && S.fk_cnt > 0) {
+					if constexpr (GLW) {
+						// ring prologue: the first MBIK_GLW_DEPTH children in flight; one group per product, empty past the end of
+						// the walk so that the group count stays uniform (cp.async.wait_group takes an immediate)
+#pragma unroll
+						for (int j = 0; j < MBIK_GLW_DEPTH; j++) {
+							if (j < S.fk_cnt) {
+								L.fetch(fk[S.fk_off + j].child, j);
+							}
+							cp_async_commit();
+						}
+					} else if (MBIK_PIPE_CHILD && S.fk_cnt > 0) {
 						child = L.ld(fk[S.fk_off].child);
 					}
 #if MBIK_PIPE_CHILD >= 2
@@ -1018,13 +1148,23 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						if (MBIK_PIPE_T && op.eff >= 0) {
 							T = ldg_x34(my_targets + (size_t)effs[S.eff_off + op.eff].pin * 12);
 						}
-						if (!MBIK_PIPE_CHILD) {
+						if constexpr (GLW) {
+							cp_async_wait<MBIK_GLW_DEPTH - 1>(); // group k has landed
+							child = L.slot_ld(k % MBIK_GLW_DEPTH);
+						} else if (!MBIK_PIPE_CHILD) {
 							child = L.ld(op.child);
 						}
 						if (op.src_slot >= 0) {
 							run = Gstk.ld(op.src_slot);
 						}
 						run = x_mul(run, child);
+						if constexpr (GLW) {
+							// refill the slot just consumed (after the product: its operands are in registers by now)
+							if (k + MBIK_GLW_DEPTH < S.fk_cnt) {
+								L.fetch(fk[S.fk_off + k + MBIK_GLW_DEPTH].child, k % MBIK_GLW_DEPTH);
+							}
+							cp_async_commit();
+						}
 #if MBIK_PIPE_CHILD >= 2
 						if (!SP) {
 							child = child2;
@@ -1033,7 +1173,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 							}
 						} else
 #endif
-						if (MBIK_PIPE_CHILD && k + 1 < S.fk_cnt) {
+						if (!GLW && MBIK_PIPE_CHILD && k + 1 < S.fk_cnt) {
 							child = L.ld(fk[S.fk_off + k + 1].child);
 						}
 						if (!SP && MBIK_PREFETCH_DIST > 0 && k + MBIK_PREFETCH_DIST < S.fk_cnt) {
@@ -1083,7 +1223,13 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 			int b_reload = b, pslot_reload = S.pslot;
 			asm volatile("" : "+r"(b_reload), "+r"(pslot_reload));
 			const X34 P = S.parent >= 0 ? Pseg.ld(pslot_reload) : x_identity();
-			X34 Lb = L.ld(b_reload);
+			X34 Lb;
+			if constexpr (GLW) {
+				Lb = L.slot_ld(MBIK_GLW_DEPTH + (glw_step & 1)); // still this step's slot: the next step's pose went to the other one
+				glw_step++;
+			} else {
+				Lb = L.ld(b_reload);
+			}
 			M3 Pinv = m3_identity();
 			if (node_parent) {
 				Pinv = m3_inverse(P.b);
@@ -1235,6 +1381,12 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				}
 			}
 			L.st(b, Lb);
+			if constexpr (GLW) {
+				if (n_steps == 1) {
+					L.fetch(b, MBIK_GLW_DEPTH + (glw_step & 1));
+					cp_async_commit();
+				}
+			}
 		}
 	}
 		if (SP) {
@@ -1332,6 +1484,53 @@ static cudaError_t launch_variant_lims(const SolveArgs &a, cudaStream_t stream) 
 	unsigned grid = (unsigned)((a.n_poses + THREADS - 1) / THREADS);
 	mbik_solve_kernel_lims<NB, NSEG, NSTK, THREADS, STAB><<<grid, THREADS, smem, stream>>>(a);
 	return cudaGetLastError();
+}
+// GLW instantiation (large rigs, MBIK_GLW): local poses in a global float4 workspace, walk through a cp.async ring
+template <int NB, int NSEG, int NSTK, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel_glw(SolveArgs a) {
+	solve_body<NB, NSEG, NSTK, false, 0, false, false, false, THREADS>(a);
+}
+// true if the ring of this CTA size fits beside the rig blob (else the caller launches the thread-local instantiation)
+template <int THREADS>
+static bool glw_fits(const SolveArgs &a) {
+	return (((size_t)a.blob_bytes + 127) & ~(size_t)127) + (size_t)(MBIK_GLW_DEPTH + 2) * 3 * sizeof(float4) * THREADS <= 227 * 1024;
+}
+template <int NB, int NSEG, int NSTK, int THREADS>
+static cudaError_t launch_variant_glw(const SolveArgs &a0, int sm_count, cudaStream_t stream) {
+	static_assert(ScratchStride<NSEG, NSTK, THREADS>::value == 0, "GLW expects thread-local scratch");
+	const size_t smem = (((size_t)a0.blob_bytes + 127) & ~(size_t)127) + (size_t)(MBIK_GLW_DEPTH + 2) * 3 * sizeof(float4) * THREADS;
+	if (smem > 227 * 1024) {
+		return cudaErrorInvalidValue;
+	}
+	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel_glw<NB, NSEG, NSTK, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	// the workspace is stream-ordered and sized for at most four waves of CTAs; larger batches run as several launches that
+	// reuse it (launches on one stream run in order; with one CTA per SM a launch boundary at a whole number of waves costs nothing)
+	const size_t wave = (size_t)(sm_count > 0 ? sm_count : 148) * THREADS;
+	const size_t per_launch = a0.n_poses < 4 * wave ? a0.n_poses : 4 * wave;
+	const unsigned max_grid = (unsigned)((per_launch + THREADS - 1) / THREADS);
+	float *ws = nullptr;
+	e = cudaMallocAsync((void **)&ws, (size_t)max_grid * (THREADS / 32) * glw_tile_float4(a0.n_solved) * sizeof(float4), stream);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	const size_t out_rows = (a0.out_flags & OUT_COMPACT) ? (size_t)a0.n_solved : (size_t)a0.n_bones;
+	for (size_t first = 0; first < a0.n_poses && e == cudaSuccess; first += per_launch) {
+		SolveArgs a = a0;
+		a.workspace = ws;
+		a.n_poses = a0.n_poses - first < per_launch ? a0.n_poses - first : per_launch;
+		a.targets = a0.targets ? a0.targets + first * (size_t)a0.n_pins * 12 : nullptr;
+		a.start_pose = a0.start_pose ? a0.start_pose + first * (size_t)a0.n_bones * 12 : nullptr;
+		a.out_pose = a0.out_pose ? a0.out_pose + first * out_rows * 10 : nullptr;
+		a.out_local = a0.out_local ? a0.out_local + first * (size_t)a0.n_bones * 12 : nullptr;
+		a.out_status = a0.out_status ? a0.out_status + first : nullptr;
+		mbik_solve_kernel_glw<NB, NSEG, NSTK, THREADS><<<(unsigned)((a.n_poses + THREADS - 1) / THREADS), THREADS, smem, stream>>>(a);
+		e = cudaGetLastError();
+	}
+	cudaFreeAsync(ws, stream);
+	return e;
 }
 template <int NB, int NSEG, int NSTK, int THREADS, bool STAB = false, int MINB = 1>
 static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {

@@ -20,6 +20,9 @@ cudaError_t launch_v5(const SolveArgs &a, int threads, cudaStream_t stream) {
 		case 128:
 			return launch_variant<256, 256, 32, 128>(a, stream);
 		default:
+			if (a.use_glw && glw_fits<kBlockThreads>(a)) { // long effector walks: local poses streamed from a global workspace
+				return launch_variant_glw<256, 256, 32, kBlockThreads>(a, a.sm_count, stream);
+			}
 			return launch_variant<256, 256, 32, kBlockThreads>(a, stream);
 	}
 }

@@ -193,3 +193,33 @@ def test_unbounded_variant_equals_the_oracle(monkeypatch):
         want, _ = O.solve_batch(LS.rig_with(rig, sets[s_i]), T[:64], threads=8)
         assert _same(out[idx == s_i], want[idx == s_i])
     R.destroy_limit_sets(h)
+
+
+@pytest.mark.parametrize("name,n", [("chain64", 19000), ("chain64", 148 * 512 * 4 + 1000), ("chain150", 19000), ("chain200", 19000)])
+def test_streamed_walk_instantiation_keeps_every_pose_bit_identical(name, n):
+    """Large batches of rigs with long effector walks (chains) run the streamed-walk instantiation: local poses in a global
+    float4 workspace, walk children through a cp.async ring (mbik_kernel_body.cuh, GLW); more than four waves = several
+    launches sharing one workspace.  A pose's bits cannot depend on it: slices of the big batch == the same poses solved
+    as small batches (thread-local state) == the oracle; host path (chunked, three streams) == device path."""
+    import torch
+    from many_bone_ik_b200._capi import MBIK_IO_DEVICE
+    cases = dict(rigs.RIGS)
+    cases.update(rig_cases.LARGE_RIGS)
+    rig = cases[name]()
+    R = BatchedIKRig(rig)
+    T = rigs.random_targets(rig, 0, n)
+    t_dev = torch.from_numpy(T).cuda()
+    o_dev = torch.empty((n, rig.n_bones, 10), dtype=torch.float32, device="cuda")
+    st_dev = torch.empty(n, dtype=torch.int32, device="cuda")
+    R.solve_raw(n, t_dev, o_dev, out_status=st_dev, device=0, flags=MBIK_IO_DEVICE, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    big = o_dev.cpu().numpy()
+    for lo in (0, n // 2 - 50, n - 130):
+        small, st = R.solve(T[lo:lo + 130])
+        assert _same(big[lo:lo + 130], small), lo
+        assert np.array_equal(st_dev.cpu().numpy()[lo:lo + 130].astype(np.uint32), st)
+    ref, _ = O.solve_batch(rig, T[-24:], threads=8)
+    assert _same(big[-24:], ref)
+    if n < 100000:
+        host, _ = R.solve(T)
+        assert _same(host, big)
