@@ -66,6 +66,11 @@ struct BlobStep { // 64 bytes
 	int32_t seg_len;
 };
 
+// BlobBone::flags / BlobFk::pad bit: the bone is one of the most-read local poses of the rig's effector walks, few enough to stay
+// in L2 for a whole resident batch -- the streamed-walk instantiation reads and writes it with an L2 evict_last policy and
+// everything else with evict_first (solve_body GLW)
+constexpr uint32_t BONE_L2_KEEP = 0x10000u;
+
 struct BlobBone { // per solved bone, t order; 208 bytes; every 3x3 is padded to 12 floats so that it starts on a
                   // 16-byte boundary and is read from shared memory with three 128-bit loads
 	int32_t skel_bone;
@@ -99,7 +104,7 @@ struct BlobFk { // 8 bytes
 	int16_t child;
 	int8_t src_slot, push_slot;
 	int16_t eff;
-	int16_t pad;
+	int16_t pad; // 1 = the child is a BONE_L2_KEEP bone
 };
 
 struct BlobCone { // 160 bytes

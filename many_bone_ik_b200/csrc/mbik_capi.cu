@@ -311,13 +311,12 @@ void set_launch_hints(mbik::SolveArgs &a, const mbik::FlatRig &F, uint32_t flags
 	a.sp_team_bytes = (int32_t)((size_t)F.sp_team_bufs * F.sp_team_headings * 6 * 32 * sizeof(float));
 	a.sp_gain = F.sp_critical_cost > 0 ? (float)(F.sp_serial_cost / F.sp_critical_cost) : 1.0f;
 	a.sched_mode = (flags & MBIK_SCHED_THROUGHPUT) ? 1 : ((flags & MBIK_SCHED_SEGMENT_PARALLEL) ? 2 : 0);
-	// Streamed-walk instantiation for large batches of rigs whose effector walks are long (>= 16 products per bone-step on
-	// average: chains -- chain64 31, chain200 98; trees stay below -- quad80 8, humanoid22 3.5): measured +14 ... +22 % on
-	// chain64, -8 ... -17 % on quad80 (profiles/r2_exp_glw_e.log).  MBIK_GLW=0 / 1 overrides (A/B, tests).
+	// Streamed-walk instantiation for the large batches of the 64-bone-and-up variants (local poses of 3 KB and more per pose:
+	// a resident batch does not fit L2).  Measured against thread-local state (profiles/r2_exp_glw_*.log): chain64 +26 ... +33 %,
+	// chain150 +38 %, chain200 +38 %, quad80 +4 %.  MBIK_GLW=0 / 1 overrides (A/B).
 	{
 		static const int forced = getenv("MBIK_GLW") ? atoi(getenv("MBIK_GLW")) : -1;
-		const bool dense = !F.steps.empty() && F.fk.size() >= 16 * F.steps.size();
-		a.use_glw = (forced >= 0 ? forced != 0 : dense) && F.stabilization_passes == 0 ? 1 : 0;
+		a.use_glw = (forced >= 0 ? forced != 0 : true) && F.stabilization_passes == 0 ? 1 : 0;
 	}
 	a.sp_trace = nullptr;
 }

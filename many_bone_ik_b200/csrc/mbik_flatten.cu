@@ -1178,6 +1178,40 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	hdr.sp_team_headings = R.sp_team_headings;
 	std::vector<float> rest(nb * 12);
 	memcpy(rest.data(), d->rest_local, sizeof(float) * 12 * nb);
+	{
+		// L2-keep set of the streamed-walk instantiation: the most-read local poses (effector walks + segment-chain refreshes per
+		// iteration), as many as fit 24 MB of L2 for a resident batch of 148 x 512 poses (48 B each): 6 bones.  Measured
+		// (chain64, 75 776 poses, profiles/r2_exp_glw_keep_mb.log): what pays is the evict_first policy on everything else --
+		// 59.0 ms without policies, 53.4 ms with an empty keep set, 53.0 / 53.1 / 54.1 / 55.7 / 57.0 ms keeping 24 / 40 / 56 / 72 /
+		// 88 MB: the streamed poses no longer push the kernel's code, the targets and the thread-local scratch out of L2
+		std::vector<double> reads(R.bones.size(), 0.0);
+		for (const BlobStep &st : R.steps) {
+			const double passes = ((st.flags & STEP_TRANSLATE) && st.eff_cnt > 16) ? 2.0 : 1.0;
+			for (int k = 0; k < st.fk_cnt; k++) {
+				reads[(size_t)R.fk[(size_t)st.fk_off + k].child] += passes;
+			}
+			if (st.flags & STEP_SEG_FIRST) {
+				for (int k = 0; k < st.chain_cnt; k++) {
+					reads[(size_t)R.chain[(size_t)st.chain_off + k]] += 1.0;
+				}
+			}
+		}
+		std::vector<int> order(R.bones.size());
+		for (size_t i = 0; i < order.size(); i++) {
+			order[i] = (int)i;
+		}
+		std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return reads[(size_t)x] > reads[(size_t)y]; });
+		static const double keep_mb = getenv("MBIK_GLW_KEEP_MB") ? atof(getenv("MBIK_GLW_KEEP_MB")) : 24.0; // tuning knob
+		const size_t keep = (size_t)(keep_mb * 1.0e6 / (48.0 * 148 * 512));
+		for (size_t i = 0; i < order.size() && i < keep; i++) {
+			if (reads[(size_t)order[i]] >= 4.0) {
+				R.bones[(size_t)order[i]].flags |= BONE_L2_KEEP;
+			}
+		}
+		for (BlobFk &op : R.fk) {
+			op.pad = (R.bones[(size_t)op.child].flags & BONE_L2_KEEP) ? 1 : 0;
+		}
+	}
 	std::vector<int16_t> list_row(ns, 0); // t index -> position in bone_list
 	for (size_t i = 0; i < R.bone_order.size(); i++) {
 		list_row[(size_t)R.t_of_bone[R.bone_order[i]]] = (int16_t)i;
@@ -1212,8 +1246,10 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 		}
 	};
 	assemble(false);
-	if (R.blob.size() > kResidentBlobBudget) {
-		// the walk list (quadratic in chain depth) and the segment-parallel tables stay in global memory
+	// the walk list (quadratic in chain depth) and the segment-parallel tables stay in global memory when the blob would not
+	// fit shared memory -- and already when a rig of the {256, 256, 32} variant would leave no room for the streamed-walk
+	// instantiation's cp.async ring (144 KiB at 512 threads)
+	if (R.blob.size() > kResidentBlobBudget || (ns > 128 && R.blob.size() > (size_t)(227 - 144 - 1) * 1024)) {
 		assemble(true);
 	}
 	hdr.total_bytes = (uint32_t)R.blob.size();

@@ -208,6 +208,9 @@ struct Scratch {
 // (stall_long_sb 20 %, issue 62 %, 5.4 TB/s = 82 % of the measured peak; 69.3 -> 55.4 ms per 75 776 poses under ncu,
 // profiles/r2_exp_glw_kernel_chain64_75776.txt).  Rigs with short walks (quad80: L2 hit rate 55 %) lose 8-17 % to the
 // extra address arithmetic of the global path and keep thread-local state: the host picks per rig (FlatRig walk density).
+#ifndef MBIK_GLW_HOT
+#define MBIK_GLW_HOT 1
+#endif
 #ifndef MBIK_GLW_DEPTH
 #define MBIK_GLW_DEPTH 4
 #endif
@@ -244,13 +247,33 @@ struct GStore {
 		q[64] = make_float4(t.b.m[8], t.o.x, t.o.y, t.o.z);
 	}
 	__device__ __forceinline__ void prefetch_l2(int) const {}
+	uint64_t pol_keep, pol_stream; // L2 cache policies (MBIK_GLW_HOT): evict_last for the BONE_L2_KEEP bones, evict_first for the rest
 	// asynchronous copy of bone i into ring slot `slot` (this thread's column only: no other thread reads it)
-	__device__ __forceinline__ void fetch(int i, int slot) const {
+	__device__ __forceinline__ void fetch(int i, int slot, bool keep = false) const {
 		const char *q = col + (size_t)(uint32_t)i * 1536u;
 		const uint32_t d = ring + (uint32_t)slot * (48u * RT);
+#if MBIK_GLW_HOT
+		const uint64_t pol = keep ? pol_keep : pol_stream;
+		asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(q), "l"(pol) : "memory");
+		asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d + 16u * RT), "l"(q + 512), "l"(pol) : "memory");
+		asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d + 32u * RT), "l"(q + 1024), "l"(pol) : "memory");
+#else
 		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q) : "memory");
 		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * RT), "l"(q + 512) : "memory");
 		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 32u * RT), "l"(q + 1024) : "memory");
+#endif
+	}
+	// the step's result with the bone's policy
+	__device__ __forceinline__ void st_hint(int i, const X34 &t, bool keep) const {
+#if MBIK_GLW_HOT
+		char *q = const_cast<char *>(col) + (size_t)(uint32_t)i * 1536u;
+		const uint64_t pol = keep ? pol_keep : pol_stream;
+		asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(q), "f"(t.b.m[0]), "f"(t.b.m[1]), "f"(t.b.m[2]), "f"(t.b.m[3]), "l"(pol) : "memory");
+		asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(q + 512), "f"(t.b.m[4]), "f"(t.b.m[5]), "f"(t.b.m[6]), "f"(t.b.m[7]), "l"(pol) : "memory");
+		asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(q + 1024), "f"(t.b.m[8]), "f"(t.o.x), "f"(t.o.y), "f"(t.o.z), "l"(pol) : "memory");
+#else
+		st(i, t);
+#endif
 	}
 	__device__ __forceinline__ X34 slot_ld(int slot) const {
 		const uint32_t d = ring + (uint32_t)slot * (48u * RT);
@@ -262,6 +285,17 @@ struct GStore {
 	}
 };
 
+__device__ __forceinline__ uint64_t glw_policy(bool keep) {
+	uint64_t p = 0;
+#if MBIK_GLW_HOT
+	if (keep) {
+		asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	} else {
+		asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	}
+#endif
+	return p;
+}
 template <bool G>
 struct PickStore {
 	template <class A, class B>
@@ -854,7 +888,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	const GStore<GLW ? GLWT : 32> L_glw{
 		reinterpret_cast<const char *>(a.workspace) +
 				(GLW ? ((((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * glw_tile_float4(H.n_solved) + (threadIdx.x & 31)) * 16 : 0),
-		smem_u32(smem + ((a.blob_bytes + 127u) & ~127u)) + threadIdx.x * 16u };
+		smem_u32(smem + ((a.blob_bytes + 127u) & ~127u)) + threadIdx.x * 16u, glw_policy(true), glw_policy(false) };
 	const auto &L = PickStore<GLW>::get(L_plain, L_glw);
 	// globals of the parents of the current segment's bones (ancestors do not move while a segment is being solved,
 	// so this replaces the reference's lazy global-transform cache) and of the branch points of the current walk
@@ -961,7 +995,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 #pragma unroll
 					for (int j = 0; j < MBIK_GLW_DEPTH; j++) { // the same ring as the effector walk (idle here)
 						if (j < S.chain_cnt) {
-							L.fetch(chain[S.chain_off + j], j);
+							L.fetch(chain[S.chain_off + j], j, (bones[chain[S.chain_off + j]].flags & BONE_L2_KEEP) != 0);
 						}
 						cp_async_commit();
 					}
@@ -977,7 +1011,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					const X34 l = l_next; // software-pipelined like the effector walk below
 					if constexpr (GLW) {
 						if (k + MBIK_GLW_DEPTH < S.chain_cnt) {
-							L.fetch(chain[S.chain_off + k + MBIK_GLW_DEPTH], k % MBIK_GLW_DEPTH);
+							L.fetch(chain[S.chain_off + k + MBIK_GLW_DEPTH], k % MBIK_GLW_DEPTH, (bones[chain[S.chain_off + k + MBIK_GLW_DEPTH]].flags & BONE_L2_KEEP) != 0);
 						}
 						cp_async_commit();
 					} else if (k + 1 < S.chain_cnt) {
@@ -1006,7 +1040,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					L0 = L.slot_ld(MBIK_GLW_DEPTH + (glw_step & 1));
 					if (n_steps > 1) { // (a one-bone rig re-reads the bone this step writes: requested after the store below)
 						const int s_next = s + 1 < n_steps ? s + 1 : 0;
-						L.fetch(steps[s_next].bone, MBIK_GLW_DEPTH + ((glw_step + 1) & 1));
+						L.fetch(steps[s_next].bone, MBIK_GLW_DEPTH + ((glw_step + 1) & 1), (bones[steps[s_next].bone].flags & BONE_L2_KEEP) != 0);
 					}
 					cp_async_commit();
 				} else {
@@ -1125,7 +1159,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 #pragma unroll
 						for (int j = 0; j < MBIK_GLW_DEPTH; j++) {
 							if (j < S.fk_cnt) {
-								L.fetch(fk[S.fk_off + j].child, j);
+								L.fetch(fk[S.fk_off + j].child, j, fk[S.fk_off + j].pad != 0);
 							}
 							cp_async_commit();
 						}
@@ -1161,7 +1195,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						if constexpr (GLW) {
 							// refill the slot just consumed (after the product: its operands are in registers by now)
 							if (k + MBIK_GLW_DEPTH < S.fk_cnt) {
-								L.fetch(fk[S.fk_off + k + MBIK_GLW_DEPTH].child, k % MBIK_GLW_DEPTH);
+								L.fetch(fk[S.fk_off + k + MBIK_GLW_DEPTH].child, k % MBIK_GLW_DEPTH, fk[S.fk_off + k + MBIK_GLW_DEPTH].pad != 0);
 							}
 							cp_async_commit();
 						}
@@ -1380,7 +1414,11 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					prev_dev = (double)INFINITY; // :178-180
 				}
 			}
-			L.st(b, Lb);
+			if constexpr (GLW) {
+				L.st_hint(b, Lb, (B.flags & BONE_L2_KEEP) != 0);
+			} else {
+				L.st(b, Lb);
+			}
 			if constexpr (GLW) {
 				if (n_steps == 1) {
 					L.fetch(b, MBIK_GLW_DEPTH + (glw_step & 1));
