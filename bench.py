@@ -607,7 +607,7 @@ def main():
             alg_bytes = rg.n_pins * 48 + rg.n_bones * 40
             fp32 = {"achieved": fl * m / (ms * 1e-3) / 1e12, "peak": float(tf.value), "unit": "TFLOP/s",
                     "frac": fl * m / (ms * 1e-3) / 1e12 / float(tf.value) if tf.value else None, "flops_per_solve": fl}
-            roof = {"bound": "hbm", "kernel": "mbik_solve_kernel<64,16,8,*>", "unit": "GB/s", "peak": hbm_peak,
+            roof = {"bound": "hbm", "kernel": traffic_table.get("other_rigs", {}).get(name, {}).get("kernel", "mbik_solve_kernel_glw<64,*>"), "unit": "GB/s", "peak": hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
                     "algorithmic_bytes_per_solve": alg_bytes, "algorithmic_gbs": alg_bytes * m / (ms * 1e-3) / 1e9, "fp32": fp32}
             tr = traffic_table.get("other_rigs", {}).get(name)
@@ -615,8 +615,11 @@ def main():
                 t_bytes = float(tr["dram_bytes"]) / float(tr["poses"]) * m
                 roof.update({"achieved": t_bytes / (ms * 1e-3) / 1e9, "frac": t_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": t_bytes,
                              "traffic_source": tr["source"],
-                             "note": "achieved = measured DRAM traffic of the launch / its duration: the walk re-reads the per-pose local transforms "
-                                     "(they do not fit L2), so the kernel is bound by HBM on bytes the algorithm would not need on chip"})
+                             "note": "achieved = measured DRAM traffic of the launch (committed ncu capture of the same kernel) / its duration measured here: the "
+                                     "effector walks re-read the per-pose local transforms, which do not fit L2 for a resident batch.  With thread-local state (round 1) "
+                                     "these rigs waited on HBM (chain64: 4.3 TB/s, stall_long_sb 50 %); the streamed-walk instantiation (cp.async ring + L2 policies) "
+                                     "cut the traffic by a third and hid its latency, so the kernel is now limited by dependent-instruction latency like humanoid22 -- "
+                                     "the FP32 fraction is under `fp32`"})
             cfg = {"workload": f"{name}: {rg.n_bones} bones, {rg.n_pins} effectors, {rg.iterations} iterations, {m} random-target poses",
                    "value": m / (ms * 1e-3), "unit": UNIT, "poses": m, "iterations": rg.iterations, "ms_per_launch": ms,
                    "e2e": {"value": e2e_g, "unit": UNIT, "h2d_bytes_per_step": int(m * rg.n_pins * 48), "d2h_bytes_per_step": int(m * ns_g * 40)},

@@ -11,7 +11,7 @@ echo "reference arm rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_bench.log 2>&1
 echo "launch list rc=$?"
-for spec in humanoid22:303104 chain64:65536 quad80:65536; do
+for spec in ${NCU_SPECS:-humanoid22:303104 chain64:65536 quad80:65536}; do
   rig=${spec%%:*}; poses=${spec##*:}
   ncu --set full --clock-control none --import-source on --launch-skip 2 --launch-count 1 -f -o $out/${tag}_${rig} \
       python profiles/run_kernel.py --rig $rig --poses $poses --launches 3 > $out/${tag}_ncu_${rig}.log 2>&1
