@@ -34,7 +34,7 @@ extern "C" {
 #define MBIK_OK 0
 #define MBIK_ERR_INVALID_ARG (-1)
 #define MBIK_ERR_CUDA (-2)
-#define MBIK_ERR_UNSUPPORTED (-3) /* rig larger than the compiled kernel variants */
+#define MBIK_ERR_UNSUPPORTED (-3) /* rig beyond the schedule's index types (16 383 solved bones, walk stack depth 127) */
 #define MBIK_ERR_NO_DEVICE (-4)   /* no CUDA device: there is NO CPU fallback */
 #define MBIK_ERR_ALLOC (-5)
 
@@ -141,7 +141,7 @@ typedef struct mbik_rig_info {
 	int32_t max_headings;     /* largest heading count of any segment */
 	int32_t n_cones;
 	int32_t iterations;
-	int32_t kernel_capacity;  /* solved-bone capacity of the kernel variant that will run */
+	int32_t kernel_capacity;  /* solved-bone capacity of the kernel variant that will run (16383 = the unbounded variant) */
 	int64_t rig_blob_bytes;   /* constants staged to shared memory per CTA */
 	double flops_per_solve;   /* algorithmic flop floor, SURVEY.md section 8(d) convention */
 	int32_t max_segment_len;  /* bones in the longest kept segment */
