@@ -50,6 +50,7 @@ struct BlobHeader {
 	uint32_t off_steps, off_bones, off_effs, off_fk, off_cones, off_pass, off_rest, off_chain, off_sched;
 	uint32_t off_step_path, off_path_refs, off_paths; // BlobPathRef tables of the team steps (see BlobSpan)
 	uint32_t off_list_row; // int16 list_row[n_solved]: index of solved bone t in bone_list (row of the compact output layout)
+	int32_t glw_keep_lo, glw_keep_n; // streamed-walk instantiation: the t range of solved bones kept in L2 with evict_last (BONE_L2_KEEP)
 };
 
 struct BlobStep { // 64 bytes
@@ -66,7 +67,7 @@ struct BlobStep { // 64 bytes
 	int32_t seg_len;
 };
 
-// BlobBone::flags / BlobFk::pad bit: the bone is one of the most-read local poses of the rig's effector walks, few enough to stay
+// BlobBone::flags bit / BlobFk::pad bit 0: the bone is one of the most-read local poses of the rig's effector walks, few enough to stay
 // in L2 for a whole resident batch -- the streamed-walk instantiation reads and writes it with an L2 evict_last policy and
 // everything else with evict_first (solve_body GLW)
 constexpr uint32_t BONE_L2_KEEP = 0x10000u;
@@ -104,7 +105,9 @@ struct BlobFk { // 8 bytes
 	int16_t child;
 	int8_t src_slot, push_slot;
 	int16_t eff;
-	int16_t pad; // 1 = the child is a BONE_L2_KEEP bone
+	int16_t pad; // bit 0: the child is a BONE_L2_KEEP bone; bits 1..: length of the plain run that starts here -- consecutive ops
+	             // without stack traffic whose children are consecutive t indices, only the last of which may reach an effector
+	             // (0: this op reads or writes the stack)
 };
 
 struct BlobCone { // 160 bytes

@@ -1178,6 +1178,7 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	hdr.sp_team_headings = R.sp_team_headings;
 	std::vector<float> rest(nb * 12);
 	memcpy(rest.data(), d->rest_local, sizeof(float) * 12 * nb);
+	int hdr_keep_lo = 0, hdr_keep_n = 0;
 	{
 		// L2-keep set of the streamed-walk instantiation: the most-read local poses (effector walks + segment-chain refreshes per
 		// iteration), as many as fit 24 MB of L2 for a resident batch of 148 x 512 poses (48 B each): 6 bones.  Measured
@@ -1196,22 +1197,47 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 				}
 			}
 		}
-		std::vector<int> order(R.bones.size());
-		for (size_t i = 0; i < order.size(); i++) {
-			order[i] = (int)i;
-		}
-		std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return reads[(size_t)x] > reads[(size_t)y]; });
+		// a contiguous t range (chains: the deepest bones), so that the kernel tests membership with one compare
 		static const double keep_mb = getenv("MBIK_GLW_KEEP_MB") ? atof(getenv("MBIK_GLW_KEEP_MB")) : 24.0; // tuning knob
-		const size_t keep = (size_t)(keep_mb * 1.0e6 / (48.0 * 148 * 512));
-		for (size_t i = 0; i < order.size() && i < keep; i++) {
-			if (reads[(size_t)order[i]] >= 4.0) {
-				R.bones[(size_t)order[i]].flags |= BONE_L2_KEEP;
+		const int keep = (int)(keep_mb * 1.0e6 / (48.0 * 148 * 512));
+		int best_lo = 0, best_n = 0;
+		double best_sum = 0.0;
+		for (int lo = 0; lo < (int)reads.size() && keep > 0; lo++) {
+			double sum = 0.0;
+			for (int n = 1; n <= keep && lo + n <= (int)reads.size(); n++) {
+				sum += reads[(size_t)(lo + n - 1)];
+				if (sum > best_sum && reads[(size_t)(lo + n - 1)] >= 4.0) {
+					best_sum = sum;
+					best_lo = lo;
+					best_n = n;
+				}
 			}
 		}
-		for (BlobFk &op : R.fk) {
-			op.pad = (R.bones[(size_t)op.child].flags & BONE_L2_KEEP) ? 1 : 0;
+		hdr_keep_lo = best_lo;
+		hdr_keep_n = best_n;
+		for (int t = best_lo; t < best_lo + best_n; t++) {
+			R.bones[(size_t)t].flags |= BONE_L2_KEEP;
+		}
+		// plain runs of the walk lists (BlobFk::pad >> 1), per step from the back
+		for (const BlobStep &st : R.steps) {
+			int next_run = 0;
+			for (int k = st.fk_cnt - 1; k >= 0; k--) {
+				BlobFk &op = R.fk[(size_t)st.fk_off + k];
+				int run = 0;
+				if (op.src_slot < 0 && op.push_slot < 0) {
+					run = 1;
+					if (k + 1 < st.fk_cnt && op.eff < 0 && next_run > 0 && R.fk[(size_t)st.fk_off + k + 1].child == op.child + 1) {
+						run = next_run + 1;
+					}
+				}
+				run = run > 16000 ? 16000 : run;
+				op.pad = (int16_t)(((R.bones[(size_t)op.child].flags & BONE_L2_KEEP) ? 1 : 0) | (run << 1));
+				next_run = run;
+			}
 		}
 	}
+	hdr.glw_keep_lo = hdr_keep_lo;
+	hdr.glw_keep_n = hdr_keep_n;
 	std::vector<int16_t> list_row(ns, 0); // t index -> position in bone_list
 	for (size_t i = 0; i < R.bone_order.size(); i++) {
 		list_row[(size_t)R.t_of_bone[R.bone_order[i]]] = (int16_t)i;

@@ -247,7 +247,9 @@ struct GStore {
 		q[64] = make_float4(t.b.m[8], t.o.x, t.o.y, t.o.z);
 	}
 	__device__ __forceinline__ void prefetch_l2(int) const {}
-	uint64_t pol_keep, pol_stream; // L2 cache policies (MBIK_GLW_HOT): evict_last for the BONE_L2_KEEP bones, evict_first for the rest
+	uint64_t pol_keep, pol_stream; // L2 cache policies (MBIK_GLW_HOT): evict_last for the L2-keep bones, evict_first for the rest
+	int keep_lo, keep_n;           // the L2-keep bones are the t range [keep_lo, keep_lo + keep_n) (BlobHeader)
+	__device__ __forceinline__ bool keep(int t) const { return (unsigned)(t - keep_lo) < (unsigned)keep_n; }
 	// asynchronous copy of bone i into ring slot `slot` (this thread's column only: no other thread reads it)
 	__device__ __forceinline__ void fetch(int i, int slot, bool keep = false) const {
 		const char *q = col + (size_t)(uint32_t)i * 1536u;
@@ -255,8 +257,8 @@ struct GStore {
 #if MBIK_GLW_HOT
 		const uint64_t pol = keep ? pol_keep : pol_stream;
 		asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(q), "l"(pol) : "memory");
-		asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d + 16u * RT), "l"(q + 512), "l"(pol) : "memory");
-		asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d + 32u * RT), "l"(q + 1024), "l"(pol) : "memory");
+		asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0+%3], [%1+512], 16, %2;" ::"r"(d), "l"(q), "l"(pol), "n"(16 * RT) : "memory");
+		asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0+%3], [%1+1024], 16, %2;" ::"r"(d), "l"(q), "l"(pol), "n"(32 * RT) : "memory");
 #else
 		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q) : "memory");
 		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * RT), "l"(q + 512) : "memory");
@@ -279,8 +281,8 @@ struct GStore {
 		const uint32_t d = ring + (uint32_t)slot * (48u * RT);
 		float4 a, b, c;
 		asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(d));
-		asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(d + 16u * RT));
-		asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(d + 32u * RT));
+		asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(d), "n"(16 * RT));
+		asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(d), "n"(32 * RT));
 		return unpack(a, b, c);
 	}
 };
@@ -888,7 +890,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	const GStore<GLW ? GLWT : 32> L_glw{
 		reinterpret_cast<const char *>(a.workspace) +
 				(GLW ? ((((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * glw_tile_float4(H.n_solved) + (threadIdx.x & 31)) * 16 : 0),
-		smem_u32(smem + ((a.blob_bytes + 127u) & ~127u)) + threadIdx.x * 16u, glw_policy(true), glw_policy(false) };
+		smem_u32(smem + ((a.blob_bytes + 127u) & ~127u)) + threadIdx.x * 16u, glw_policy(true), glw_policy(false), H.glw_keep_lo, H.glw_keep_n };
 	const auto &L = PickStore<GLW>::get(L_plain, L_glw);
 	// globals of the parents of the current segment's bones (ancestors do not move while a segment is being solved,
 	// so this replaces the reference's lazy global-transform cache) and of the branch points of the current walk
@@ -995,7 +997,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 #pragma unroll
 					for (int j = 0; j < MBIK_GLW_DEPTH; j++) { // the same ring as the effector walk (idle here)
 						if (j < S.chain_cnt) {
-							L.fetch(chain[S.chain_off + j], j, (bones[chain[S.chain_off + j]].flags & BONE_L2_KEEP) != 0);
+							L.fetch(chain[S.chain_off + j], j, L.keep(chain[S.chain_off + j]));
 						}
 						cp_async_commit();
 					}
@@ -1011,7 +1013,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					const X34 l = l_next; // software-pipelined like the effector walk below
 					if constexpr (GLW) {
 						if (k + MBIK_GLW_DEPTH < S.chain_cnt) {
-							L.fetch(chain[S.chain_off + k + MBIK_GLW_DEPTH], k % MBIK_GLW_DEPTH, (bones[chain[S.chain_off + k + MBIK_GLW_DEPTH]].flags & BONE_L2_KEEP) != 0);
+							L.fetch(chain[S.chain_off + k + MBIK_GLW_DEPTH], k % MBIK_GLW_DEPTH, L.keep(chain[S.chain_off + k + MBIK_GLW_DEPTH]));
 						}
 						cp_async_commit();
 					} else if (k + 1 < S.chain_cnt) {
@@ -1040,7 +1042,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					L0 = L.slot_ld(MBIK_GLW_DEPTH + (glw_step & 1));
 					if (n_steps > 1) { // (a one-bone rig re-reads the bone this step writes: requested after the store below)
 						const int s_next = s + 1 < n_steps ? s + 1 : 0;
-						L.fetch(steps[s_next].bone, MBIK_GLW_DEPTH + ((glw_step + 1) & 1), (bones[steps[s_next].bone].flags & BONE_L2_KEEP) != 0);
+						L.fetch(steps[s_next].bone, MBIK_GLW_DEPTH + ((glw_step + 1) & 1), L.keep(steps[s_next].bone));
 					}
 					cp_async_commit();
 				} else {
@@ -1153,17 +1155,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					// (lockstepped) warps of the CTA at once.
 					X34 run = Gb;
 					X34 child = x_identity();
-					if constexpr (GLW) {
-						// ring prologue: the first MBIK_GLW_DEPTH children in flight; one group per product, empty past the end of
-						// the walk so that the group count stays uniform (cp.async.wait_group takes an immediate)
-#pragma unroll
-						for (int j = 0; j < MBIK_GLW_DEPTH; j++) {
-							if (j < S.fk_cnt) {
-								L.fetch(fk[S.fk_off + j].child, j, fk[S.fk_off + j].pad != 0);
-							}
-							cp_async_commit();
-						}
-					} else if (MBIK_PIPE_CHILD && S.fk_cnt > 0) {
+					if (!GLW && MBIK_PIPE_CHILD && S.fk_cnt > 0) {
 						child = L.ld(fk[S.fk_off].child);
 					}
 #if MBIK_PIPE_CHILD >= 2
@@ -1176,29 +1168,92 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						child2 = L.ld(fk[S.fk_off + 1].child);
 					}
 #endif
+					// what happens at a walk product that reaches an effector's bone
+					auto on_effector = [&](int eff, const X34 &at, X34 T) {
+						const BlobEff &E = effs[S.eff_off + eff];
+						const V3 tO = xform_zero(at);
+						if (STAB) {
+							TipO[3 * eff] = tO.x; TipO[3 * eff + 1] = tO.y; TipO[3 * eff + 2] = tO.z;
+						}
+						if (!MBIK_PIPE_T) {
+							T = ldg_x34(my_targets + (size_t)E.pin * 12);
+						}
+						if (ECACHE > 0 && cache_frames && pass_i == 0) {
+							st_x34(Efr, eff, at);
+						}
+						effector_headings(A, pass_i, translate, E, at, ld_m3v(bones[E.bone].dir_basis), T, bo, tO);
+					};
+					if constexpr (GLW) {
+						// Streamed walk.  The request side runs MBIK_GLW_DEPTH products ahead of the products themselves with its own
+						// cursor over the walk list: inside a *plain run* (BlobFk::pad >> 1: consecutive ops without stack traffic whose
+						// children are consecutive t indices -- a chain) the next child is the previous one + 1 and no list entry is
+						// read at all; the products of a run but its last carry nothing, so they are a bare wait / load / multiply /
+						// request loop.  (chain64: 49 % of all executed instructions sit in the per-product path; the generic path
+						// spent 75 of its 138 instructions per product on list bookkeeping.)
+						const int cnt = S.fk_cnt;
+						int pk = 0, pchild = 0, prem = 0; // request cursor: ops requested so far, last child requested, ops left in its run
+						auto request_next = [&](int slot) {
+							if (pk < cnt) {
+								if (prem > 0) {
+									pchild++;
+									prem--;
+								} else {
+									const BlobFk q = fk[S.fk_off + pk];
+									pchild = q.child;
+									prem = (q.pad >> 1) - 1;
+									prem = prem < 0 ? 0 : prem;
+								}
+								pk++;
+								L.fetch(pchild, slot, L.keep(pchild));
+							}
+							cp_async_commit();
+						};
+#pragma unroll
+						for (int j = 0; j < MBIK_GLW_DEPTH; j++) {
+							request_next(j);
+						}
+						int k = 0;
+						while (k < cnt) {
+							BlobFk op = fk[S.fk_off + k];
+							const int n_plain = (op.pad >> 1) > 1 ? (op.pad >> 1) - 1 : 0;
+							for (int j = 0; j < n_plain; j++, k++) {
+								cp_async_wait<MBIK_GLW_DEPTH - 1>();
+								child = L.slot_ld(k % MBIK_GLW_DEPTH);
+								run = x_mul(run, child);
+								request_next(k % MBIK_GLW_DEPTH);
+							}
+							if (n_plain > 0) {
+								op = fk[S.fk_off + k]; // the run's last op: may reach an effector
+							}
+							cp_async_wait<MBIK_GLW_DEPTH - 1>();
+							child = L.slot_ld(k % MBIK_GLW_DEPTH);
+							if (op.src_slot >= 0) {
+								run = Gstk.ld(op.src_slot);
+							}
+							run = x_mul(run, child);
+							request_next(k % MBIK_GLW_DEPTH);
+							if (op.push_slot >= 0) {
+								Gstk.st(op.push_slot, run);
+							}
+							if (op.eff >= 0) {
+								on_effector(op.eff, run, x_identity());
+							}
+							k++;
+						}
+					} else
 					for (int k = 0; k < S.fk_cnt; k++) {
 						const BlobFk op = fk[S.fk_off + k];
 						X34 T = x_identity();
 						if (MBIK_PIPE_T && op.eff >= 0) {
 							T = ldg_x34(my_targets + (size_t)effs[S.eff_off + op.eff].pin * 12);
 						}
-						if constexpr (GLW) {
-							cp_async_wait<MBIK_GLW_DEPTH - 1>(); // group k has landed
-							child = L.slot_ld(k % MBIK_GLW_DEPTH);
-						} else if (!MBIK_PIPE_CHILD) {
+						if (!MBIK_PIPE_CHILD) {
 							child = L.ld(op.child);
 						}
 						if (op.src_slot >= 0) {
 							run = Gstk.ld(op.src_slot);
 						}
 						run = x_mul(run, child);
-						if constexpr (GLW) {
-							// refill the slot just consumed (after the product: its operands are in registers by now)
-							if (k + MBIK_GLW_DEPTH < S.fk_cnt) {
-								L.fetch(fk[S.fk_off + k + MBIK_GLW_DEPTH].child, k % MBIK_GLW_DEPTH, fk[S.fk_off + k + MBIK_GLW_DEPTH].pad != 0);
-							}
-							cp_async_commit();
-						}
 #if MBIK_PIPE_CHILD >= 2
 						if (!SP) {
 							child = child2;
@@ -1217,18 +1272,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 							Gstk.st(op.push_slot, run);
 						}
 						if (op.eff >= 0) {
-							const BlobEff &E = effs[S.eff_off + op.eff];
-							const V3 tO = xform_zero(run);
-							if (STAB) {
-								TipO[3 * op.eff] = tO.x; TipO[3 * op.eff + 1] = tO.y; TipO[3 * op.eff + 2] = tO.z;
-							}
-							if (!MBIK_PIPE_T) {
-								T = ldg_x34(my_targets + (size_t)E.pin * 12);
-							}
-							if (ECACHE > 0 && cache_frames && pass_i == 0) {
-								st_x34(Efr, op.eff, run);
-							}
-							effector_headings(A, pass_i, translate, E, run, ld_m3v(bones[E.bone].dir_basis), T, bo, tO);
+							on_effector(op.eff, run, T);
 						}
 					}
 					if (pass_i == 0) {
@@ -1415,7 +1459,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				}
 			}
 			if constexpr (GLW) {
-				L.st_hint(b, Lb, (B.flags & BONE_L2_KEEP) != 0);
+				L.st_hint(b, Lb, L.keep(b));
 			} else {
 				L.st(b, Lb);
 			}

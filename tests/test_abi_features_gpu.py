@@ -223,3 +223,15 @@ def test_streamed_walk_instantiation_keeps_every_pose_bit_identical(name, n):
     if n < 100000:
         host, _ = R.solve(T)
         assert _same(host, big)
+
+
+def test_unbounded_variant_with_stabilisation_passes():
+    rig = rig_cases.chain300()
+    rig.stabilization_passes = 2
+    rig.name = "chain300_stabilized"
+    R = BatchedIKRig(rig)
+    T = rigs.random_targets(rig, 9, 96)
+    ref = O.solve_batch(rig, T, want_local=True, threads=8)
+    got = R.solve(T, want_local=True)
+    for a, b in zip(got, ref):
+        assert _same(a, b)
