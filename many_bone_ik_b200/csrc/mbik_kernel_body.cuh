@@ -41,9 +41,6 @@
 #ifndef MBIK_ECACHE_SMALL
 #define MBIK_ECACHE_SMALL 8
 #endif
-#ifndef MBIK_PIPE_T
-#define MBIK_PIPE_T 0
-#endif
 #ifndef MBIK_PIPE_CHILD
 #define MBIK_PIPE_CHILD 1
 #endif
@@ -1158,16 +1155,8 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					if (!GLW && MBIK_PIPE_CHILD && S.fk_cnt > 0) {
 						child = L.ld(fk[S.fk_off].child);
 					}
-#if MBIK_PIPE_CHILD >= 2
-					// MBIK_PIPE_CHILD == 2 (experiment, off): two walk children in flight per thread.  Measured on chain64
-					// (75 776 poses): 71.8 ms vs 69.3 ms with one -- like the prefetch knobs above, more requests in
-					// flight do not raise the 4.3 TB/s the memory system delivers for this stream; 24 more live registers
-					// cost a few spills.
-					X34 child2 = x_identity();
-					if (!SP && S.fk_cnt > 1) {
-						child2 = L.ld(fk[S.fk_off + 1].child);
-					}
-#endif
+					// (Two children in flight per thread -- MBIK_PIPE_CHILD == 2 in round 1 -- measured 71.8 vs 69.3 ms on chain64: the
+					// 24 extra live registers spill.  The streamed-walk instantiation above is what that experiment wanted to be.)
 					// what happens at a walk product that reaches an effector's bone
 					auto on_effector = [&](int eff, const X34 &at, X34 T) {
 						const BlobEff &E = effs[S.eff_off + eff];
@@ -1175,9 +1164,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						if (STAB) {
 							TipO[3 * eff] = tO.x; TipO[3 * eff + 1] = tO.y; TipO[3 * eff + 2] = tO.z;
 						}
-						if (!MBIK_PIPE_T) {
-							T = ldg_x34(my_targets + (size_t)E.pin * 12);
-						}
+						T = ldg_x34(my_targets + (size_t)E.pin * 12); // (hoisting it above the product costs more registers than it hides latency)
 						if (ECACHE > 0 && cache_frames && pass_i == 0) {
 							st_x34(Efr, eff, at);
 						}
@@ -1240,39 +1227,48 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 							}
 							k++;
 						}
-					} else
-					for (int k = 0; k < S.fk_cnt; k++) {
-						const BlobFk op = fk[S.fk_off + k];
-						X34 T = x_identity();
-						if (MBIK_PIPE_T && op.eff >= 0) {
-							T = ldg_x34(my_targets + (size_t)effs[S.eff_off + op.eff].pin * 12);
-						}
-						if (!MBIK_PIPE_CHILD) {
-							child = L.ld(op.child);
-						}
-						if (op.src_slot >= 0) {
-							run = Gstk.ld(op.src_slot);
-						}
-						run = x_mul(run, child);
-#if MBIK_PIPE_CHILD >= 2
-						if (!SP) {
-							child = child2;
-							if (k + 2 < S.fk_cnt) {
-								child2 = L.ld(fk[S.fk_off + k + 2].child);
+					} else {
+						// Thread-local / shared-memory state: the local pose of the next walk child is requested before the product
+						// of the current one (one product of look-ahead: the registers it lands in are live until used).  Plain runs
+						// (BlobFk::pad >> 1) skip the list: their children are consecutive t indices and all products but the last
+						// carry nothing.
+						const int cnt = S.fk_cnt;
+						int k = 0;
+						while (k < cnt) {
+							BlobFk op = fk[S.fk_off + k];
+							const int n_plain = (op.pad >> 1) > 1 ? (op.pad >> 1) - 1 : 0;
+							for (int j = 0, c = op.child; j < n_plain; j++, k++, c++) {
+								if (!MBIK_PIPE_CHILD) {
+									child = L.ld(c);
+								}
+								run = x_mul(run, child);
+								if (MBIK_PIPE_CHILD) {
+									child = L.ld(c + 1); // the run goes on: op k + 1 exists and its child is c + 1
+								}
 							}
-						} else
-#endif
-						if (!GLW && MBIK_PIPE_CHILD && k + 1 < S.fk_cnt) {
-							child = L.ld(fk[S.fk_off + k + 1].child);
-						}
-						if (!SP && MBIK_PREFETCH_DIST > 0 && k + MBIK_PREFETCH_DIST < S.fk_cnt) {
-							L.prefetch_l2(fk[S.fk_off + k + MBIK_PREFETCH_DIST].child);
-						}
-						if (op.push_slot >= 0) {
-							Gstk.st(op.push_slot, run);
-						}
-						if (op.eff >= 0) {
-							on_effector(op.eff, run, T);
+							if (n_plain > 0) {
+								op = fk[S.fk_off + k]; // the run's last op: may reach an effector
+							}
+							if (!MBIK_PIPE_CHILD) {
+								child = L.ld(op.child);
+							}
+							if (op.src_slot >= 0) {
+								run = Gstk.ld(op.src_slot);
+							}
+							run = x_mul(run, child);
+							if (MBIK_PIPE_CHILD && k + 1 < cnt) {
+								child = L.ld(fk[S.fk_off + k + 1].child);
+							}
+							if (!SP && MBIK_PREFETCH_DIST > 0 && k + MBIK_PREFETCH_DIST < cnt) {
+								L.prefetch_l2(fk[S.fk_off + k + MBIK_PREFETCH_DIST].child);
+							}
+							if (op.push_slot >= 0) {
+								Gstk.st(op.push_slot, run);
+							}
+							if (op.eff >= 0) {
+								on_effector(op.eff, run, x_identity());
+							}
+							k++;
 						}
 					}
 					if (pass_i == 0) {
