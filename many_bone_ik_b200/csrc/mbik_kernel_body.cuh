@@ -1227,48 +1227,29 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 							}
 							k++;
 						}
-					} else {
-						// Thread-local / shared-memory state: the local pose of the next walk child is requested before the product
-						// of the current one (one product of look-ahead: the registers it lands in are live until used).  Plain runs
-						// (BlobFk::pad >> 1) skip the list: their children are consecutive t indices and all products but the last
-						// carry nothing.
-						const int cnt = S.fk_cnt;
-						int k = 0;
-						while (k < cnt) {
-							BlobFk op = fk[S.fk_off + k];
-							const int n_plain = (op.pad >> 1) > 1 ? (op.pad >> 1) - 1 : 0;
-							for (int j = 0, c = op.child; j < n_plain; j++, k++, c++) {
-								if (!MBIK_PIPE_CHILD) {
-									child = L.ld(c);
-								}
-								run = x_mul(run, child);
-								if (MBIK_PIPE_CHILD) {
-									child = L.ld(c + 1); // the run goes on: op k + 1 exists and its child is c + 1
-								}
-							}
-							if (n_plain > 0) {
-								op = fk[S.fk_off + k]; // the run's last op: may reach an effector
-							}
-							if (!MBIK_PIPE_CHILD) {
-								child = L.ld(op.child);
-							}
-							if (op.src_slot >= 0) {
-								run = Gstk.ld(op.src_slot);
-							}
-							run = x_mul(run, child);
-							if (MBIK_PIPE_CHILD && k + 1 < cnt) {
-								child = L.ld(fk[S.fk_off + k + 1].child);
-							}
-							if (!SP && MBIK_PREFETCH_DIST > 0 && k + MBIK_PREFETCH_DIST < cnt) {
-								L.prefetch_l2(fk[S.fk_off + k + MBIK_PREFETCH_DIST].child);
-							}
-							if (op.push_slot >= 0) {
-								Gstk.st(op.push_slot, run);
-							}
-							if (op.eff >= 0) {
-								on_effector(op.eff, run, x_identity());
-							}
-							k++;
+					} else
+					// (the plain-run fast path of the streamed walk does not pay here: humanoid22 31.72 vs 31.42 ms with it -- its walks are
+					// 3.5 products long on average; one list entry per product, one product of look-ahead)
+					for (int k = 0; k < S.fk_cnt; k++) {
+						const BlobFk op = fk[S.fk_off + k];
+						if (!MBIK_PIPE_CHILD) {
+							child = L.ld(op.child);
+						}
+						if (op.src_slot >= 0) {
+							run = Gstk.ld(op.src_slot);
+						}
+						run = x_mul(run, child);
+						if (!GLW && MBIK_PIPE_CHILD && k + 1 < S.fk_cnt) {
+							child = L.ld(fk[S.fk_off + k + 1].child);
+						}
+						if (!SP && MBIK_PREFETCH_DIST > 0 && k + MBIK_PREFETCH_DIST < S.fk_cnt) {
+							L.prefetch_l2(fk[S.fk_off + k + MBIK_PREFETCH_DIST].child);
+						}
+						if (op.push_slot >= 0) {
+							Gstk.st(op.push_slot, run);
+						}
+						if (op.eff >= 0) {
+							on_effector(op.eff, run, x_identity());
 						}
 					}
 					if (pass_i == 0) {
