@@ -312,8 +312,8 @@ void set_launch_hints(mbik::SolveArgs &a, const mbik::FlatRig &F, uint32_t flags
 	a.sp_gain = F.sp_critical_cost > 0 ? (float)(F.sp_serial_cost / F.sp_critical_cost) : 1.0f;
 	a.sched_mode = (flags & MBIK_SCHED_THROUGHPUT) ? 1 : ((flags & MBIK_SCHED_SEGMENT_PARALLEL) ? 2 : 0);
 	// Streamed-walk instantiation for the large batches of the 64-bone-and-up variants (local poses of 3 KB and more per pose:
-	// a resident batch does not fit L2).  Measured against thread-local state (profiles/r2_exp_glw_*.log): chain64 +26 ... +33 %,
-	// chain150 +38 %, chain200 +38 %, quad80 +4 %.  MBIK_GLW=0 / 1 overrides (A/B).
+	// a resident batch does not fit L2).  Measured against thread-local state (profiles/r2_exp_glw_*.log): chain64 +47 ... +50 %,
+	// chain150 +52 %, chain200 +49 %, quad80 +9 ... +11 %.  MBIK_GLW=0 / 1 overrides (A/B).
 	{
 		static const int forced = getenv("MBIK_GLW") ? atoi(getenv("MBIK_GLW")) : -1;
 		a.use_glw = (forced >= 0 ? forced != 0 : true) && F.stabilization_passes == 0 ? 1 : 0;
