@@ -6,6 +6,9 @@
 // as is, 29.3 M without the walk's child prefetch, 30.7 M with scalar Vector3 ops on top (112 B / 252 B of spill stores / loads left),
 // 28.9 M with every packed composite off (76 B / 164 B) -- against 33.3 M at 512 threads: per full wave the 20-warp builds deliver what
 // the 16-warp build does (the 96-register schedule is ~25 % slower per warp), and 2^20 poses quantise worse (11.07 waves -> 12).
+#ifndef MBIK_V0_GLW
+#define MBIK_V0_GLW 0
+#endif
 #ifndef MBIK_V0_BIG
 #define MBIK_V0_BIG 512
 #endif
@@ -25,6 +28,10 @@ cudaError_t launch_v0(const SolveArgs &a, int threads, cudaStream_t stream) {
 		case 256:
 			return launch_variant<20, 4, 2, 256>(a, stream);
 		case 512:
+#if MBIK_V0_GLW
+			// experiment: the streamed-walk instantiation on the small variant (needs thread-local scratch: -DMBIK_SCRATCH_LIMIT_KB=0)
+			return launch_variant_glw<20, 4, 2, 512>(a, a.sm_count, stream);
+#endif
 			return launch_variant<20, 4, 2, MBIK_V0_BIG>(a, stream);
 		case 384: // wave-balanced sizes for large batches (launch_solve): the last wave of CTAs is as full as the others
 			return launch_variant<20, 4, 2, 384>(a, stream);
