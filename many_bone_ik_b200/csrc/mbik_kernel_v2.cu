@@ -20,17 +20,29 @@ cudaError_t launch_v2(const SolveArgs &a, int threads, cudaStream_t stream) {
 			return launch_variant<64, 8, 1, 128>(a, stream);
 		case 384: // wave-balanced sizes for large batches (launch_solve): the last wave of CTAs is as full as the others
 			if (a.use_glw && glw_fits<384>(a)) {
-				return launch_variant_glw<64, 8, 1, 384>(a, a.sm_count, stream);
+				const cudaError_t e = launch_variant_glw<64, 8, 1, 384>(a, a.sm_count, stream);
+				if (e != cudaErrorMemoryAllocation && e != cudaErrorNotSupported) {
+					return e;
+				}
+				cudaGetLastError(); // no workspace (pool exhausted / no stream-ordered allocator): thread-local state instead
 			}
 			return launch_variant<64, 8, 1, 384>(a, stream);
 		case 448:
 			if (a.use_glw && glw_fits<448>(a)) {
-				return launch_variant_glw<64, 8, 1, 448>(a, a.sm_count, stream);
+				const cudaError_t e = launch_variant_glw<64, 8, 1, 448>(a, a.sm_count, stream);
+				if (e != cudaErrorMemoryAllocation && e != cudaErrorNotSupported) {
+					return e;
+				}
+				cudaGetLastError(); // no workspace (pool exhausted / no stream-ordered allocator): thread-local state instead
 			}
 			return launch_variant<64, 8, 1, 448>(a, stream);
 		default:
-			if (a.use_glw && glw_fits<kBlockThreads>(a)) { // long effector walks: local poses streamed from a global workspace
-				return launch_variant_glw<64, 8, 1, kBlockThreads>(a, a.sm_count, stream);
+			if (a.use_glw && glw_fits<kBlockThreads>(a)) {
+				const cudaError_t e = launch_variant_glw<64, 8, 1, kBlockThreads>(a, a.sm_count, stream);
+				if (e != cudaErrorMemoryAllocation && e != cudaErrorNotSupported) {
+					return e;
+				}
+				cudaGetLastError(); // no workspace (pool exhausted / no stream-ordered allocator): thread-local state instead
 			}
 			return launch_variant<64, 8, 1, kBlockThreads>(a, stream);
 	}

@@ -20,8 +20,12 @@ cudaError_t launch_v5(const SolveArgs &a, int threads, cudaStream_t stream) {
 		case 128:
 			return launch_variant<256, 256, 32, 128>(a, stream);
 		default:
-			if (a.use_glw && glw_fits<kBlockThreads>(a)) { // long effector walks: local poses streamed from a global workspace
-				return launch_variant_glw<256, 256, 32, kBlockThreads>(a, a.sm_count, stream);
+			if (a.use_glw && glw_fits<kBlockThreads>(a)) {
+				const cudaError_t e = launch_variant_glw<256, 256, 32, kBlockThreads>(a, a.sm_count, stream);
+				if (e != cudaErrorMemoryAllocation && e != cudaErrorNotSupported) {
+					return e;
+				}
+				cudaGetLastError(); // no workspace (pool exhausted / no stream-ordered allocator): thread-local state instead
 			}
 			return launch_variant<256, 256, 32, kBlockThreads>(a, stream);
 	}
