@@ -1240,7 +1240,7 @@ int mbik_stream_submit(mbik_stream *st, const float *targets, float *out_pose, u
 		return cuda_fail(e, "cudaSetDevice");
 	}
 	const mbik::FlatRig &F = st->rig->flat;
-	const size_t nb = (size_t)F.n_bones, np = F.pins.size(), n = st->n_poses;
+	const size_t np = F.pins.size(), n = st->n_poses;
 	const int slot = (int)(st->frames & 1);
 	// the slot's previous frame (f-2) must have finished downloading before its buffers are overwritten
 	if (st->slot_used[slot]) {

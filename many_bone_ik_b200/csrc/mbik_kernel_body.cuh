@@ -813,7 +813,7 @@ __device__ __forceinline__ void team_barrier(int id, int n_threads) { asm volati
 template <int NB, int NSEG, int NSTK, bool STAB, int SCR_STRIDE, bool SP = false, bool LIMS = false, bool DYN = false, int GLWT = 0>
 __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	constexpr bool GLW = GLWT > 0; // GLWT = CTA size of the GLW instantiation
-	static_assert(!GLW || (!SP && !DYN && SCR_STRIDE == 0), "GLW: thread-per-pose mapping with thread-local scratch only");
+	static_assert(!GLW || (!SP && SCR_STRIDE == 0), "GLW: thread-per-pose mapping, scratch not in shared memory");
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) uint64_t bar;
 
@@ -894,9 +894,13 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	float Pseg_local[(SCR_STRIDE > 0 || DYN) ? 1 : NSEG * 12];
 	float Gstk_local[(SCR_STRIDE > 0 || DYN) ? 1 : NSTK * 12];
 	float *scr = reinterpret_cast<float *>(smem + ((a.blob_bytes + 127u) & ~127u)) + threadIdx.x; // (SP: SCR_STRIDE == 0, unused)
-	const Scratch<DYN ? -1 : SCR_STRIDE> Pseg{ DYN ? ws_col + (size_t)H.n_solved * 12 * ws_threads : (SCR_STRIDE > 0 ? scr : Pseg_local), ws_threads };
-	const Scratch<DYN ? -1 : SCR_STRIDE> Gstk{ DYN ? ws_col + (size_t)(H.n_solved + H.max_seg_len) * 12 * ws_threads
-	                                                  : (SCR_STRIDE > 0 ? scr + NSEG * 12 * SCR_STRIDE : Gstk_local), ws_threads };
+	// DYN scratch columns: behind the n_solved pose slots of the scalar layout, or -- DYN + GLW -- behind the warp tiles of the poses
+	float *dyn_scr = DYN ? (GLW ? a.workspace + (size_t)(ws_threads >> 5) * glw_tile_float4(H.n_solved) * 4 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x)
+	                            : ws_col + (size_t)H.n_solved * 12 * ws_threads)
+	                     : nullptr;
+	const Scratch<DYN ? -1 : SCR_STRIDE> Pseg{ DYN ? dyn_scr : (SCR_STRIDE > 0 ? scr : Pseg_local), ws_threads };
+	const Scratch<DYN ? -1 : SCR_STRIDE> Gstk{ DYN ? dyn_scr + (size_t)H.max_seg_len * 12 * ws_threads
+	                                               : (SCR_STRIDE > 0 ? scr + NSEG * 12 * SCR_STRIDE : Gstk_local), ws_threads };
 	// stabilisation only (STAB variants): effector-bone origins from before the step (what the step's target
 	// headings were built from) and the segment's previous_deviation (src/ik_bone_segment_3d.h:63)
 	float TipO[STAB ? kMaxStabEffectors * 3 : 1];
@@ -1626,11 +1630,13 @@ static cudaError_t launch_variant(const SolveArgs &a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------
 template <bool STAB, bool LIMS>
 __global__ void __launch_bounds__(128) mbik_solve_kernel_dyn(SolveArgs a) {
-	solve_body<32767, 1, 1, STAB, 0, false, LIMS, true>(a);
+	solve_body<32767, 1, 1, STAB, 0, false, LIMS, true, 128>(a); // + streamed walk: poses in warp tiles, cp.async ring (the only shared memory)
 }
 template <bool STAB, bool LIMS>
 static cudaError_t launch_variant_dyn(const SolveArgs &a0, int sm_count, cudaStream_t stream) {
-	const size_t per_thread = (size_t)(a0.n_solved + a0.max_seg_len + a0.max_stack) * 12 * sizeof(float);
+	// per thread: its share of a warp tile of poses (n_solved x 48 B + padding) and max_seg_len + max_stack scratch transforms
+	const size_t per_thread = glw_tile_float4(a0.n_solved) * sizeof(float4) / 32 + (size_t)(a0.max_seg_len + a0.max_stack) * 12 * sizeof(float);
+	const size_t ring_bytes = (size_t)(MBIK_GLW_DEPTH + 2) * 3 * sizeof(float4) * 128;
 	size_t threads = ((a0.n_poses + 127) / 128) * 128;
 	const size_t resident = (size_t)(sm_count > 0 ? sm_count : 148) * 128 * 4;
 	threads = threads < resident ? threads : resident;
@@ -1659,7 +1665,8 @@ static cudaError_t launch_variant_dyn(const SolveArgs &a0, int sm_count, cudaStr
 		a.out_local = a0.out_local ? a0.out_local + first * (size_t)a0.n_bones * 12 : nullptr;
 		a.out_status = a0.out_status ? a0.out_status + first : nullptr;
 		a.limit_index = a0.limit_index ? a0.limit_index + first : nullptr;
-		mbik_solve_kernel_dyn<STAB, LIMS><<<(unsigned)((a.n_poses + 127) / 128), 128, 0, stream>>>(a);
+		a.blob_bytes = 0; // nothing is staged: the ring starts at the beginning of the dynamic shared memory
+		mbik_solve_kernel_dyn<STAB, LIMS><<<(unsigned)((a.n_poses + 127) / 128), 128, ring_bytes, stream>>>(a);
 		e = cudaGetLastError();
 	}
 	cudaFreeAsync(ws, stream);
