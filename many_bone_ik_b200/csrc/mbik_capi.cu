@@ -316,7 +316,7 @@ void set_launch_hints(mbik::SolveArgs &a, const mbik::FlatRig &F, uint32_t flags
 	// chain150 +52 %, chain200 +49 %, quad80 +9 ... +11 %.  MBIK_GLW=0 / 1 overrides (A/B).
 	{
 		static const int forced = getenv("MBIK_GLW") ? atoi(getenv("MBIK_GLW")) : -1;
-		a.use_glw = (forced >= 0 ? forced != 0 : true) && F.stabilization_passes == 0 ? 1 : 0;
+		a.use_glw = (forced >= 0 ? forced != 0 : true) ? 1 : 0;
 	}
 	a.sp_trace = nullptr;
 }

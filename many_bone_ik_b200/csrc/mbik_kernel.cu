@@ -155,19 +155,21 @@ cudaError_t launch_solve(const SolveArgs &a, int variant, int sm_count, cudaStre
 		}
 	}
 	if (lims) {
+		SolveArgs b = a;
+		b.sm_count = sm_count;
 		switch (variant) {
 			case 0:
 				return launch_lims_v0(a, stream);
 			case 1:
 				return launch_lims_v1(a, stream);
 			case 2:
-				return launch_lims_v2(a, stream);
+				return launch_lims_v2(b, stream);
 			case 3:
-				return launch_lims_v3(a, stream);
+				return launch_lims_v3(b, stream);
 			case 4:
-				return launch_lims_v4(a, stream);
+				return launch_lims_v4(b, stream);
 			default:
-				return launch_lims_v5(a, stream);
+				return launch_lims_v5(b, stream);
 		}
 	}
 	const int threads = throughput_block_threads(a, variant, sm_count);

@@ -1549,23 +1549,23 @@ static cudaError_t launch_variant_lims(const SolveArgs &a, cudaStream_t stream) 
 	return cudaGetLastError();
 }
 // GLW instantiation (large rigs, MBIK_GLW): local poses in a global float4 workspace, walk through a cp.async ring
-template <int NB, int NSEG, int NSTK, int THREADS>
+template <int NB, int NSEG, int NSTK, int THREADS, bool STAB, bool LIMS>
 __global__ void __launch_bounds__(THREADS, 1) mbik_solve_kernel_glw(SolveArgs a) {
-	solve_body<NB, NSEG, NSTK, false, 0, false, false, false, THREADS>(a);
+	solve_body<NB, NSEG, NSTK, STAB, 0, false, LIMS, false, THREADS>(a);
 }
 // true if the ring of this CTA size fits beside the rig blob (else the caller launches the thread-local instantiation)
 template <int THREADS>
 static bool glw_fits(const SolveArgs &a) {
 	return (((size_t)a.blob_bytes + 127) & ~(size_t)127) + (size_t)(MBIK_GLW_DEPTH + 2) * 3 * sizeof(float4) * THREADS <= 227 * 1024;
 }
-template <int NB, int NSEG, int NSTK, int THREADS>
+template <int NB, int NSEG, int NSTK, int THREADS, bool STAB = false, bool LIMS = false>
 static cudaError_t launch_variant_glw(const SolveArgs &a0, int sm_count, cudaStream_t stream) {
 	static_assert(ScratchStride<NSEG, NSTK, THREADS>::value == 0, "GLW expects thread-local scratch");
 	const size_t smem = (((size_t)a0.blob_bytes + 127) & ~(size_t)127) + (size_t)(MBIK_GLW_DEPTH + 2) * 3 * sizeof(float4) * THREADS;
 	if (smem > 227 * 1024) {
 		return cudaErrorInvalidValue;
 	}
-	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel_glw<NB, NSEG, NSTK, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(mbik_solve_kernel_glw<NB, NSEG, NSTK, THREADS, STAB, LIMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) {
 		return e;
 	}
@@ -1589,7 +1589,8 @@ static cudaError_t launch_variant_glw(const SolveArgs &a0, int sm_count, cudaStr
 		a.out_pose = a0.out_pose ? a0.out_pose + first * out_rows * 10 : nullptr;
 		a.out_local = a0.out_local ? a0.out_local + first * (size_t)a0.n_bones * 12 : nullptr;
 		a.out_status = a0.out_status ? a0.out_status + first : nullptr;
-		mbik_solve_kernel_glw<NB, NSEG, NSTK, THREADS><<<(unsigned)((a.n_poses + THREADS - 1) / THREADS), THREADS, smem, stream>>>(a);
+		a.limit_index = a0.limit_index ? a0.limit_index + first : nullptr;
+		mbik_solve_kernel_glw<NB, NSEG, NSTK, THREADS, STAB, LIMS><<<(unsigned)((a.n_poses + THREADS - 1) / THREADS), THREADS, smem, stream>>>(a);
 		e = cudaGetLastError();
 	}
 	cudaFreeAsync(ws, stream);

@@ -13,6 +13,13 @@ cudaError_t launch_lims_v5(const SolveArgs &a, cudaStream_t stream) {
 	if (a.stabilize) {
 		return launch_variant_lims<256, 256, 32, kStabBlockThreads, true>(a, stream);
 	}
+	if (a.use_glw && glw_fits<kBlockThreads>(a)) { // long walks: the streamed-walk instantiation reads the pose's limit-set record too
+		const cudaError_t e = launch_variant_glw<256, 256, 32, kBlockThreads, false, true>(a, a.sm_count, stream);
+		if (e != cudaErrorMemoryAllocation && e != cudaErrorNotSupported) {
+			return e;
+		}
+		cudaGetLastError();
+	}
 	return launch_variant_lims<256, 256, 32, kBlockThreads>(a, stream);
 }
 

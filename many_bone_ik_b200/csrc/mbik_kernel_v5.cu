@@ -14,6 +14,13 @@ namespace mbik {
 cudaError_t launch_v5(const SolveArgs &a, int threads, cudaStream_t stream) {
 	switch (threads) {
 		case 0: // stabilisation passes > 0: separate instantiation, the default path pays nothing for it
+			if (a.use_glw && ScratchStride<256, 32, kStabBlockThreads>::value == 0 && glw_fits<kStabBlockThreads>(a)) { // long walks: streamed
+				const cudaError_t e = launch_variant_glw<256, 256, 32, kStabBlockThreads, true>(a, a.sm_count, stream);
+				if (e != cudaErrorMemoryAllocation && e != cudaErrorNotSupported) {
+					return e;
+				}
+				cudaGetLastError(); // no workspace: thread-local state instead
+			}
 			return launch_variant<256, 256, 32, kStabBlockThreads, true>(a, stream);
 		case 32: // small batches: one warp per SM (latency, not throughput)
 			return launch_variant<256, 256, 32, 32>(a, stream);

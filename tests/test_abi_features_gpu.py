@@ -235,3 +235,34 @@ def test_unbounded_variant_with_stabilisation_passes():
     got = R.solve(T, want_local=True)
     for a, b in zip(got, ref):
         assert _same(a, b)
+
+
+def test_streamed_walk_with_limit_sets_and_with_stabilisation():
+    """The streamed-walk instantiation also exists with per-pose limit sets and with stabilisation passes (large batches of
+    long-walk rigs); slices of the big batch == the same poses solved as small batches == the oracle."""
+    import limit_set_cases as LS
+    n = 19000
+    # limit sets
+    rig = rigs.chain64()
+    R = BatchedIKRig(rig)
+    sets = LS.variants(rig, 3)
+    h = R.create_limit_sets(sets)
+    T = rigs.random_targets(rig, 5, n)
+    idx = (np.arange(n) % 3).astype(np.int32)
+    big, st = R.solve_with_limits(h, idx, T)
+    small, _ = R.solve_with_limits(h, idx[-200:], T[-200:])
+    assert _same(big[-200:], small)
+    for s_i in range(3):
+        want, _ = O.solve_batch(LS.rig_with(rig, sets[s_i]), T[:30], threads=8)
+        m = idx[:30] == s_i
+        assert _same(big[:30][m], want[m])
+    R.destroy_limit_sets(h)
+    # stabilisation
+    rig = rig_cases.chain64_stabilized()
+    R = BatchedIKRig(rig)
+    T = rigs.random_targets(rig, 6, n)
+    big, st = R.solve(T, sched="throughput")
+    small, _ = R.solve(T[-150:], sched="throughput")
+    assert _same(big[-150:], small)
+    want, wst = O.solve_batch(rig, T[:24], threads=8)
+    assert _same(big[:24], want) and np.array_equal(st[:24], wst)
