@@ -1233,7 +1233,8 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						}
 					} else
 					// (the plain-run fast path of the streamed walk does not pay here: humanoid22 31.72 vs 31.42 ms with it -- its walks are
-					// 3.5 products long on average; one list entry per product, one product of look-ahead)
+					// 3.5 products long on average -- and on the large variants' small batches, where one warp per SM is bound by the
+					// product chain itself, chain64's 4096-pose p50 stays at 27.2 ms with or without it)
 					for (int k = 0; k < S.fk_cnt; k++) {
 						const BlobFk op = fk[S.fk_off + k];
 						if (!MBIK_PIPE_CHILD) {
