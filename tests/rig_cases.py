@@ -153,11 +153,14 @@ def perturbed_start_pose(rig, n, seed=7, angle_deg=12.0, offset=0.02):
     return out
 
 
-def random_rig(seed):
+def random_rig(seed, n_bones=None):
     """Random skeleton tree with random pins / kusudama rows / damping: fuzzes the flattener (segment building,
-    dropped segments, effector lists, mpf cut-offs, weights) and every kernel stage against the oracle."""
+    dropped segments, effector lists, mpf cut-offs, weights) and every kernel stage against the oracle.
+    n_bones: override the random size (3..40) -- larger rigs land on the 64-bone-and-up kernel variants."""
     rng = np.random.default_rng(1000 + seed)
     n = int(rng.integers(3, 41))
+    if n_bones is not None:
+        n = int(n_bones)
     parent = np.full(n, -1, np.int32)
     for b in range(1, n):
         # mostly chains with occasional branching; a second root now and then

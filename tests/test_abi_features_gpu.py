@@ -195,7 +195,9 @@ def test_unbounded_variant_equals_the_oracle(monkeypatch):
     R.destroy_limit_sets(h)
 
 
-@pytest.mark.parametrize("name,n", [("chain64", 19000), ("chain64", 148 * 512 * 4 + 1000), ("chain150", 19000), ("chain200", 19000)])
+@pytest.mark.parametrize("name,n", [("chain64", 19000), ("chain64", 148 * 512 * 4 + 1000), ("chain150", 19000), ("chain200", 19000),
+                                    ("quad80", 19000), ("quad80", 80000), ("big_tree120", 19000), ("big_tree240", 19000), ("random_rig_64a", 19000),
+                                    ("random_rig_64b", 19000)])
 def test_streamed_walk_instantiation_keeps_every_pose_bit_identical(name, n):
     """Large batches of rigs with long effector walks (chains) run the streamed-walk instantiation: local poses in a global
     float4 workspace, walk children through a cp.async ring (mbik_kernel_body.cuh, GLW); more than four waves = several
@@ -205,8 +207,13 @@ def test_streamed_walk_instantiation_keeps_every_pose_bit_identical(name, n):
     from many_bone_ik_b200._capi import MBIK_IO_DEVICE
     cases = dict(rigs.RIGS)
     cases.update(rig_cases.LARGE_RIGS)
+    cases.update(rig_cases.EDGE_RIGS)
+    # trees exercise the walk stack (branch points pushed and re-read) and short plain runs; random 40..64-bone rigs the rest
+    cases["random_rig_64a"] = lambda: rig_cases.random_rig(3022, n_bones=100)  # 54 solved bones, walk stack 3
+    cases["random_rig_64b"] = lambda: rig_cases.random_rig(3015, n_bones=64)   # 36 solved bones, walk stack 3
     rig = cases[name]()
     R = BatchedIKRig(rig)
+    assert R.info["kernel_capacity"] >= 64, "the streamed walk belongs to the 64-bone-and-up variants"
     T = rigs.random_targets(rig, 0, n)
     t_dev = torch.from_numpy(T).cuda()
     o_dev = torch.empty((n, rig.n_bones, 10), dtype=torch.float32, device="cuda")
