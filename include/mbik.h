@@ -228,7 +228,7 @@ int64_t mbik_stream_frames(const mbik_stream *stream); /* frames submitted so fa
  *
  * A limit set is one alternative fill of the rig's constraint tables -- the same rows (same bones, same cone counts),
  * other values: joint_twist from / range, cone centres and radii.  mbik_limit_sets_create runs the reference's
- * constraint authoring for every set on the HOST (IKKusudama3D::_update_constraint / set_axial_limits,
+ * constraint authoring -- only that part of the rig flattening, not the rig's topology again -- for every set on the HOST (IKKusudama3D::_update_constraint / set_axial_limits,
  * IKLimitCone3D::update_tangent_handles: reference src/ik_kusudama_3d.cpp:37-115, src/ik_open_cone_3d.cpp:36-180 --
  * the tangent-circle construction goes through libm sin / cos / acos / tan, which only the host evaluates bit-identically
  * to the reference) and uploads the resulting cone / tangent-circle geometry and twist frames as a device table;
@@ -256,6 +256,11 @@ typedef struct mbik_limit_sets_info {
 	int32_t author_threads;  /* host threads it ran on */
 } mbik_limit_sets_info;
 int mbik_limit_sets_get_info(mbik_limit_sets *sets, mbik_limit_sets_info *out_info); /* waits for the authoring */
+/* The authored geometry of one set, in the layouts of mbik_rig_get_cone_geometry (per cone of the RIG's cone table:
+ * control point, tangent centres -- the triples the reference's editor gizmo draws,
+ * editor/many_bone_ik_3d_gizmo_plugin.cpp:149-176) and of mbik_rig_get_bone_frames' twist output.  Either output may be
+ * NULL.  Waits for the authoring; returns the cone count or a negative error. */
+int mbik_limit_sets_get_geometry(mbik_limit_sets *sets, int32_t set, float *out_cones /* [n_cones][9] */, float *out_twist_basis /* [n_solved][9] */);
 int mbik_limit_sets_destroy(mbik_limit_sets *sets);
 /* set_index: [n_poses] int32, host or device memory like the other buffers (params->flags); values are clamped to
  * [0, n_sets).  Other arguments as mbik_solve_batch. */

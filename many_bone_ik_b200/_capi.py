@@ -73,7 +73,7 @@ EXPORTED_SYMBOLS = [
     "mbik_stream_create", "mbik_stream_destroy", "mbik_stream_submit", "mbik_stream_sync", "mbik_stream_read_local",
     "mbik_stream_reset", "mbik_stream_frames", "mbik_stage_qcp", "mbik_stage_clamp", "mbik_stage_point_in_limits",
     "mbik_limit_sets_create", "mbik_limit_sets_destroy", "mbik_solve_batch_limits",
-    "mbik_limit_sets_create_async", "mbik_limit_sets_wait", "mbik_limit_sets_get_info", "mbik_stream_create_ex", "mbik_stage_qcp_newton",
+    "mbik_limit_sets_create_async", "mbik_limit_sets_wait", "mbik_limit_sets_get_info", "mbik_limit_sets_get_geometry", "mbik_stream_create_ex", "mbik_stage_qcp_newton",
 ]
 
 
@@ -195,6 +195,7 @@ def load_library():
     lib.mbik_limit_sets_create_async.argtypes = lib.mbik_limit_sets_create.argtypes
     lib.mbik_limit_sets_wait.argtypes = [vp]
     lib.mbik_limit_sets_get_info.argtypes = [vp, C.POINTER(LimitSetsInfo)]
+    lib.mbik_limit_sets_get_geometry.argtypes = [vp, C.c_int32, fp, fp]
     lib.mbik_stream_create_ex.argtypes = [vp, C.c_int32, C.c_size_t, vp, C.c_uint32, C.POINTER(vp)]
     lib.mbik_stage_qcp_newton.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, C.c_int32, vp]
     lib.mbik_solve_batch_limits.argtypes = [vp, vp, C.POINTER(SolveParams), C.c_size_t, vp, vp, vp, vp, vp, vp]

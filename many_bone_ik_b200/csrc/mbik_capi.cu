@@ -770,7 +770,7 @@ int mbik_solve_batch(mbik_rig *rig, const mbik_solve_params *params, size_t n_po
 
 namespace {
 
-// Runs the reference's constraint authoring (flatten_rig: IKKusudama3D::_update_constraint / set_axial_limits,
+// Runs the reference's constraint authoring (author_constraints: IKKusudama3D::_update_constraint / set_axial_limits,
 // IKLimitCone3D::update_tangent_handles on the host libm) for every set, on a pool of host threads: sets are independent.
 int author_limit_sets(mbik_limit_sets *ls, const mbik_constraint_desc *constraints, const mbik_cone_desc *cones, int32_t cones_per_set) {
 	mbik_rig *rig = ls->rig;
@@ -816,30 +816,30 @@ int author_limit_sets(mbik_limit_sets *ls, const mbik_constraint_desc *constrain
 			if (!rows_ok) {
 				return;
 			}
+			// only the limit-dependent part of the flattening runs per set (author_constraints); rows name the rig's own bones
+			// and cone counts (checked above), so steps, limit flags and cone ranges are the rig's by construction
 			mbik_rig_desc d = rig->desc.view();
 			d.constraints = rows;
 			d.cones = cones ? cones + (size_t)s * cones_per_set : nullptr;
-			mbik::FlatRig Fs;
-			int rc = mbik::flatten_rig(&d, Fs);
+			std::vector<mbik::BlobBone> set_bones = F.bones;
+			std::vector<mbik::BlobCone> set_cones;
+			set_cones.reserve(F.cones.size());
+			mbik::ConstraintTables tables;
+			std::string err;
+			int rc = mbik::author_constraints(&d, F, set_bones, set_cones, tables, err);
 			if (rc != MBIK_OK) {
-				set_fail(rc, "limit set " + std::to_string(s) + ": " + Fs.error);
+				set_fail(rc, "limit set " + std::to_string(s) + ": " + err);
 				return;
 			}
-			// the schedule must be the rig's: same steps, same limit flags, same cone ranges
-			bool same = Fs.steps.size() == F.steps.size() && Fs.cones.size() == F.cones.size() && Fs.bones.size() == F.bones.size();
-			for (size_t i = 0; same && i < F.steps.size(); i++) {
-				same = Fs.steps[i].bone == F.steps[i].bone && Fs.steps[i].flags == F.steps[i].flags && Fs.steps[i].cone_off == F.steps[i].cone_off &&
-						Fs.steps[i].cone_cnt == F.steps[i].cone_cnt;
-			}
-			if (!same) {
+			if (set_cones.size() != F.cones.size()) {
 				set_fail(MBIK_ERR_INVALID_ARG, "limit set " + std::to_string(s) + " changes the rig's schedule (which bones are limited, or cone counts)");
 				return;
 			}
 			unsigned char *rec = ls->table.data() + (size_t)s * ls->stride;
 			if (cone_bytes) {
-				memcpy(rec, Fs.cones.data(), cone_bytes);
+				memcpy(rec, set_cones.data(), cone_bytes);
 			}
-			memcpy(rec + cone_bytes, Fs.bones.data(), bone_bytes);
+			memcpy(rec + cone_bytes, set_bones.data(), bone_bytes);
 		}
 	};
 	const auto t0 = std::chrono::steady_clock::now();
@@ -940,6 +940,38 @@ int mbik_limit_sets_get_info(mbik_limit_sets *sets, mbik_limit_sets_info *out) {
 	out->author_seconds = sets->author_seconds;
 	out->author_threads = sets->author_threads;
 	return rc;
+}
+
+int mbik_limit_sets_get_geometry(mbik_limit_sets *sets, int32_t set, float *out_cones, float *out_twist_basis) {
+	if (!sets) {
+		return fail(MBIK_ERR_INVALID_ARG, "sets is NULL");
+	}
+	int rc = mbik_limit_sets_wait(sets);
+	if (rc != MBIK_OK) {
+		return rc;
+	}
+	if (set < 0 || set >= sets->n_sets) {
+		return fail(MBIK_ERR_INVALID_ARG, "set index out of range");
+	}
+	const mbik::FlatRig &F = sets->rig->flat;
+	const unsigned char *rec = sets->table.data() + (size_t)set * sets->stride;
+	const mbik::BlobCone *set_cones = reinterpret_cast<const mbik::BlobCone *>(rec);
+	const mbik::BlobBone *set_bones = reinterpret_cast<const mbik::BlobBone *>(rec + F.cones.size() * sizeof(mbik::BlobCone));
+	for (size_t i = 0; out_cones && i < F.cone_row_index.size(); i++) {
+		float *o = out_cones + 9 * i;
+		const int k = F.cone_row_index[i];
+		if (k < 0) {
+			memset(o, 0, sizeof(float) * 9);
+			continue;
+		}
+		memcpy(o, set_cones[k].cp, sizeof(float) * 3);
+		memcpy(o + 3, set_cones[k].tc1, sizeof(float) * 3);
+		memcpy(o + 6, set_cones[k].tc2, sizeof(float) * 3);
+	}
+	for (size_t i = 0; out_twist_basis && i < F.bone_order.size(); i++) {
+		memcpy(out_twist_basis + 9 * i, set_bones[F.t_of_bone[F.bone_order[i]]].twist_basis, sizeof(float) * 9);
+	}
+	return (int)F.cone_row_index.size();
 }
 
 int mbik_limit_sets_destroy(mbik_limit_sets *sets) {

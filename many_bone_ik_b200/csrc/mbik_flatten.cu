@@ -199,6 +199,170 @@ uint32_t append_section(std::vector<unsigned char> &blob, const std::vector<T> &
 
 } // namespace
 
+// The limit-dependent part of the flattening: kusudama cone / tangent-circle geometry and twist frames of every constraint
+// row (many_bone_ik_3d.cpp:1037-1067), written into the twist fields of `bones` ([t]; the other fields are left alone) and
+// `cones`.  Everything it needs from the rig besides the rows is the topology (R.topo, R.t_of_bone, R.ik_parent) and the
+// setup-time global basis of each constrained bone's parent (R.setup_parent_basis) -- which is why per-pose limit sets are
+// authored by this function alone, not by re-flattening the rig (mbik_limit_sets_create: 1 / 15 of the work per set).
+int author_constraints(const mbik_rig_desc *d, const FlatRig &R, std::vector<BlobBone> &bones, std::vector<BlobCone> &cones, ConstraintTables &T,
+		std::string &error) {
+	struct BoneConstraint {
+		bool present = false;
+		std::vector<HostCone> cones;
+		std::vector<int> desc_cone_index;
+		Q4 twist_center_rot = q4(0, 0, 0, 1);
+		float twist_cos = 0;
+	};
+	const int nb = R.n_bones, ns = (int)R.topo.size();
+	std::vector<BoneConstraint> cons(nb);
+	std::vector<M3> twist_basis(nb, m3_identity());
+	int n_desc_cones = 0;
+	for (int ci = 0; ci < d->n_constraints; ci++) {
+		n_desc_cones = std::max(n_desc_cones, d->constraints[ci].cone_offset + std::max(0, d->constraints[ci].n_cones));
+	}
+	T.cone_row_index.assign(n_desc_cones, -1);
+	for (int ci = 0; ci < d->n_constraints; ci++) {
+		const mbik_constraint_desc &cd = d->constraints[ci];
+		int b = cd.bone;
+		if (b < 0 || b >= nb || R.t_of_bone[b] < 0) {
+			continue; // not in bone_list: the row is ignored
+		}
+		if (cd.n_cones < 0 || (cd.n_cones > 0 && !d->cones)) {
+			error = "bad cone table";
+			return MBIK_ERR_INVALID_ARG;
+		}
+		BoneConstraint bc;
+		bc.present = true;
+		bc.cones.reserve((size_t)cd.n_cones);
+		bc.desc_cone_index.reserve((size_t)cd.n_cones);
+		auto update_tangent_radii = [&]() { // src/ik_kusudama_3d.cpp:91-101
+			for (size_t i = 0; i + 1 < bc.cones.size(); i++) {
+				update_tangent_handles(bc.cones[i], bc.cones[i + 1]);
+			}
+		};
+		for (int j = 0; j < cd.n_cones; j++) {
+			const mbik_cone_desc &c = d->cones[cd.cone_offset + j];
+			V3 ctr = v3(c.center[0], c.center[1], c.center[2]);
+			if (f_is_zero_approx(vlen2(ctr))) {
+				ctr = v3(0, 1, 0); // set_kusudama_open_cone_center (many_bone_ik_3d.cpp:586-601)
+			}
+			HostCone hc;
+			hc.radius = std::max(1.0e-38, (double)c.radius);
+			hc.radius_cos = cos(hc.radius);
+			hc.cp = set_control_point(vnorm(ctr));
+			bc.cones.push_back(hc);
+			bc.desc_cone_index.push_back(cd.cone_offset + j);
+			// add_open_cone (src/ik_kusudama_3d.cpp:160-166) updates the tangent radii here, after every cone.  The handles are
+			// a pure function of the two cones' control points and radii and are all rewritten by the update that ends
+			// _update_constraint below, after the control points were re-normalised: only that one is evaluated.
+		}
+		// set_axial_limits (src/ik_kusudama_3d.cpp:103-115)
+		{
+			V3 y_axis = v3(0, 1, 0), z_axis = v3(0, 0, 1);
+			Q4 twist_min_rot = quat_axis_angle_len2(y_axis, cd.twist_from);
+			V3 twist_min_vec = vnorm(q_xform(twist_min_rot, z_axis));
+			V3 twist_center_vec = vnorm(q_xform(twist_min_rot, twist_min_vec));
+			bc.twist_center_rot = q_shortest_arc(z_axis, twist_center_vec);
+			bc.twist_cos = cosf(r_div(cd.twist_range, 4.0f));
+		}
+		// _update_constraint(twist node) (src/ik_kusudama_3d.cpp:37-89)
+		{
+			std::vector<V3> directions;
+			if (bc.cones.size() == 1) {
+				directions.push_back(bc.cones[0].cp);
+			} else {
+				for (size_t i = 0; i + 1 < bc.cones.size(); i++) {
+					V3 a = bc.cones[i].cp, n = bc.cones[i + 1].cp;
+					Q4 q = q_shortest_arc(a, n);
+					V3 axis;
+					if (fabsf(q.w) > r_sub(1.0f, kCmpEps)) {
+						axis = v3(q.x, q.y, q.z);
+					} else {
+						float r = r_div(1.0f, r_sqrt(r_sub(1.0f, r_mul(q.w, q.w))));
+						axis = v3(r_mul(q.x, r), r_mul(q.y, r), r_mul(q.z, r));
+					}
+					float full = r_mul(2.0f, godot_acosf(q.w));
+					double angle = (double)full / 2.0;
+					V3 half = m3_xform(m3_axis_angle(axis, (float)angle), a);
+					half = vmuls(half, full);
+					half = vnorm(half);
+					directions.push_back(half);
+				}
+			}
+			V3 new_y = v3(0, 0, 0);
+			for (V3 dv : directions) {
+				new_y = vadd(new_y, dv);
+			}
+			if (!directions.empty()) {
+				new_y = vdivs(new_y, (float)directions.size());
+				new_y = vnorm(new_y);
+			}
+			if (R.ik_parent[b] >= 0) { // the twist node's parent is the parent bone's aligned node (src/ik_bone_3d.cpp:52-54)
+				M3 P = R.setup_parent_basis[b];
+				M3 Gtw = m3_mul(P, twist_basis[b]);
+				Q4 q = q_shortest_arc(vnorm(m3_col(Gtw, 1)), vnorm(m3_xform(Gtw, new_y)));
+				twist_basis[b] = m3_mul(m3_mul(m3_mul(m3_inverse(P), m3_from_quat(q)), P), twist_basis[b]);
+			}
+			for (auto &c : bc.cones) {
+				c.cp = set_control_point(vnorm(c.cp));
+			}
+			update_tangent_radii();
+		}
+		cons[b] = std::move(bc);
+	}
+
+	// ---- emit the limit fields of the per-bone constants, and the cones ----
+	T.present.assign(nb, 0);
+	T.cone_off.assign(nb, 0);
+	T.cone_cnt.assign(nb, 0);
+	cones.clear();
+	for (int t = 0; t < ns; t++) {
+		int b = R.topo[t];
+		BlobBone &B = bones[t];
+		B.twist_cos = cons[b].twist_cos;
+		memcpy(B.twist_basis, twist_basis[b].m, sizeof(float) * 9);
+		M3 tc = m3_from_quat(cons[b].twist_center_rot);
+		memcpy(B.twist_center, tc.m, sizeof(float) * 9);
+		if (cons[b].present) {
+			T.present[b] = 1;
+			T.cone_off[b] = (int)cones.size();
+			T.cone_cnt[b] = (int)cons[b].cones.size();
+			for (size_t i = 0; i < cons[b].cones.size(); i++) {
+				const HostCone &c = cons[b].cones[i];
+				BlobCone bc;
+				memset(&bc, 0, sizeof(bc));
+				V3 ncp = vnorm(c.cp);
+				bc.cp[0] = c.cp.x; bc.cp[1] = c.cp.y; bc.cp[2] = c.cp.z;
+				bc.ncp[0] = ncp.x; bc.ncp[1] = ncp.y; bc.ncp[2] = ncp.z;
+				float rf = (float)c.radius;
+				bc.sin_half_r = sinf(r_mul(rf, 0.5f));
+				bc.cos_half_r = cosf(r_mul(rf, 0.5f));
+				bc.radius_cos = c.radius_cos;
+				if (i + 1 < cons[b].cones.size()) {
+					const HostCone &n = cons[b].cones[i + 1];
+					bc.tan_cos = c.tan_cos;
+					bc.tc1[0] = c.tc1.x; bc.tc1[1] = c.tc1.y; bc.tc1[2] = c.tc1.z;
+					bc.tc2[0] = c.tc2.x; bc.tc2[1] = c.tc2.y; bc.tc2[2] = c.tc2.z;
+					float tf = (float)c.tan_r;
+					bc.sin_half_t = sinf(r_mul(tf, 0.5f));
+					bc.cos_half_t = cosf(r_mul(tf, 0.5f));
+					V3 a = vcross(c.cp, n.cp);
+					V3 e1 = vnorm(vcross(c.cp, c.tc1)), e2 = vnorm(vcross(c.tc1, n.cp));
+					V3 e3 = vnorm(vcross(c.tc2, c.cp)), e4 = vnorm(vcross(n.cp, c.tc2));
+					bc.c1xc2[0] = a.x; bc.c1xc2[1] = a.y; bc.c1xc2[2] = a.z;
+					bc.c1xt1[0] = e1.x; bc.c1xt1[1] = e1.y; bc.c1xt1[2] = e1.z;
+					bc.t1xc2[0] = e2.x; bc.t1xc2[1] = e2.y; bc.t1xc2[2] = e2.z;
+					bc.t2xc1[0] = e3.x; bc.t2xc1[1] = e3.y; bc.t2xc1[2] = e3.z;
+					bc.c2xt2[0] = e4.x; bc.c2xt2[1] = e4.y; bc.c2xt2[2] = e4.z;
+				}
+				T.cone_row_index[cons[b].desc_cone_index[i]] = (int)cones.size();
+				cones.push_back(bc);
+			}
+		}
+	}
+	return MBIK_OK;
+}
+
 int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 	if (!d || d->n_bones <= 0 || !d->parent || !d->rest_local) {
 		R.error = "rig description needs n_bones > 0, parent[] and rest_local[]";
@@ -538,110 +702,16 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 		}
 	}
 
-	// ---- constraints (many_bone_ik_3d.cpp:1037-1067) ----
-	struct BoneConstraint {
-		bool present = false;
-		std::vector<HostCone> cones;
-		std::vector<int> desc_cone_index;
-		Q4 twist_center_rot = q4(0, 0, 0, 1);
-		float twist_cos = 0;
-	};
-	std::vector<BoneConstraint> cons(nb);
-	std::vector<M3> twist_basis(nb, m3_identity());
-	int n_desc_cones = 0;
+	// ---- constraints (many_bone_ik_3d.cpp:1037-1067): per-bone constants, cones ----
+	R.ik_parent = ik_parent;
+	R.setup_parent_basis.assign(nb, m3_identity());
 	for (int ci = 0; ci < d->n_constraints; ci++) {
-		n_desc_cones = std::max(n_desc_cones, d->constraints[ci].cone_offset + std::max(0, d->constraints[ci].n_cones));
+		const int b = d->constraints[ci].bone;
+		if (b >= 0 && b < nb && R.t_of_bone[b] >= 0 && ik_parent[b] >= 0) {
+			R.setup_parent_basis[b] = ik_global(ik_parent[b]).b;
+		}
 	}
-	R.cone_row_index.assign(n_desc_cones, -1);
-	for (int ci = 0; ci < d->n_constraints; ci++) {
-		const mbik_constraint_desc &cd = d->constraints[ci];
-		int b = cd.bone;
-		if (b < 0 || b >= nb || R.t_of_bone[b] < 0) {
-			continue; // not in bone_list: the row is ignored
-		}
-		if (cd.n_cones < 0 || (cd.n_cones > 0 && !d->cones)) {
-			R.error = "bad cone table";
-			return MBIK_ERR_INVALID_ARG;
-		}
-		BoneConstraint bc;
-		bc.present = true;
-		auto update_tangent_radii = [&]() { // src/ik_kusudama_3d.cpp:91-101
-			for (size_t i = 0; i + 1 < bc.cones.size(); i++) {
-				update_tangent_handles(bc.cones[i], bc.cones[i + 1]);
-			}
-		};
-		for (int j = 0; j < cd.n_cones; j++) {
-			const mbik_cone_desc &c = d->cones[cd.cone_offset + j];
-			V3 ctr = v3(c.center[0], c.center[1], c.center[2]);
-			if (f_is_zero_approx(vlen2(ctr))) {
-				ctr = v3(0, 1, 0); // set_kusudama_open_cone_center (many_bone_ik_3d.cpp:586-601)
-			}
-			HostCone hc;
-			hc.radius = std::max(1.0e-38, (double)c.radius);
-			hc.radius_cos = cos(hc.radius);
-			hc.cp = set_control_point(vnorm(ctr));
-			bc.cones.push_back(hc);
-			bc.desc_cone_index.push_back(cd.cone_offset + j);
-			update_tangent_radii(); // add_open_cone (src/ik_kusudama_3d.cpp:160-166)
-		}
-		// set_axial_limits (src/ik_kusudama_3d.cpp:103-115)
-		{
-			V3 y_axis = v3(0, 1, 0), z_axis = v3(0, 0, 1);
-			Q4 twist_min_rot = quat_axis_angle_len2(y_axis, cd.twist_from);
-			V3 twist_min_vec = vnorm(q_xform(twist_min_rot, z_axis));
-			V3 twist_center_vec = vnorm(q_xform(twist_min_rot, twist_min_vec));
-			bc.twist_center_rot = q_shortest_arc(z_axis, twist_center_vec);
-			bc.twist_cos = cosf(r_div(cd.twist_range, 4.0f));
-		}
-		// _update_constraint(twist node) (src/ik_kusudama_3d.cpp:37-89)
-		{
-			std::vector<V3> directions;
-			if (bc.cones.size() == 1) {
-				directions.push_back(bc.cones[0].cp);
-			} else {
-				for (size_t i = 0; i + 1 < bc.cones.size(); i++) {
-					V3 a = bc.cones[i].cp, n = bc.cones[i + 1].cp;
-					Q4 q = q_shortest_arc(a, n);
-					V3 axis;
-					if (fabsf(q.w) > r_sub(1.0f, kCmpEps)) {
-						axis = v3(q.x, q.y, q.z);
-					} else {
-						float r = r_div(1.0f, r_sqrt(r_sub(1.0f, r_mul(q.w, q.w))));
-						axis = v3(r_mul(q.x, r), r_mul(q.y, r), r_mul(q.z, r));
-					}
-					float full = r_mul(2.0f, godot_acosf(q.w));
-					double angle = (double)full / 2.0;
-					V3 half = m3_xform(m3_axis_angle(axis, (float)angle), a);
-					half = vmuls(half, full);
-					half = vnorm(half);
-					directions.push_back(half);
-				}
-			}
-			V3 new_y = v3(0, 0, 0);
-			for (V3 dv : directions) {
-				new_y = vadd(new_y, dv);
-			}
-			if (!directions.empty()) {
-				new_y = vdivs(new_y, (float)directions.size());
-				new_y = vnorm(new_y);
-			}
-			if (ik_parent[b] >= 0) { // the twist node's parent is the parent bone's aligned node (src/ik_bone_3d.cpp:52-54)
-				M3 P = ik_global(ik_parent[b]).b;
-				M3 Gtw = m3_mul(P, twist_basis[b]);
-				Q4 q = q_shortest_arc(vnorm(m3_col(Gtw, 1)), vnorm(m3_xform(Gtw, new_y)));
-				twist_basis[b] = m3_mul(m3_mul(m3_mul(m3_inverse(P), m3_from_quat(q)), P), twist_basis[b]);
-			}
-			for (auto &c : bc.cones) {
-				c.cp = set_control_point(vnorm(c.cp));
-			}
-			update_tangent_radii();
-		}
-		cons[b] = bc;
-	}
-
-	// ---- emit per-bone constants, cones ----
 	R.bones.resize(ns);
-	std::vector<int> cone_off(nb, 0), cone_cnt(nb, 0);
 	for (int t = 0; t < ns; t++) {
 		int b = R.topo[t];
 		BlobBone &B = R.bones[t];
@@ -649,49 +719,20 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 		B.skel_bone = b;
 		B.parent = ik_parent[b] >= 0 ? R.t_of_bone[ik_parent[b]] : -1;
 		B.flags = node_has_parent[b] ? STEP_NODE_PARENT : 0;
-		B.twist_cos = cons[b].twist_cos;
 		M3 ident = m3_identity();
 		memcpy(B.dir_basis, dir_basis[b].m, sizeof(float) * 9);
 		memcpy(B.orient_basis, ident.m, sizeof(float) * 9);
-		memcpy(B.twist_basis, twist_basis[b].m, sizeof(float) * 9);
-		M3 tc = m3_from_quat(cons[b].twist_center_rot);
-		memcpy(B.twist_center, tc.m, sizeof(float) * 9);
-		if (cons[b].present) {
-			cone_off[b] = (int)R.cones.size();
-			cone_cnt[b] = (int)cons[b].cones.size();
-			for (size_t i = 0; i < cons[b].cones.size(); i++) {
-				const HostCone &c = cons[b].cones[i];
-				BlobCone bc;
-				memset(&bc, 0, sizeof(bc));
-				V3 ncp = vnorm(c.cp);
-				bc.cp[0] = c.cp.x; bc.cp[1] = c.cp.y; bc.cp[2] = c.cp.z;
-				bc.ncp[0] = ncp.x; bc.ncp[1] = ncp.y; bc.ncp[2] = ncp.z;
-				float rf = (float)c.radius;
-				bc.sin_half_r = sinf(r_mul(rf, 0.5f));
-				bc.cos_half_r = cosf(r_mul(rf, 0.5f));
-				bc.radius_cos = c.radius_cos;
-				if (i + 1 < cons[b].cones.size()) {
-					const HostCone &n = cons[b].cones[i + 1];
-					bc.tan_cos = c.tan_cos;
-					bc.tc1[0] = c.tc1.x; bc.tc1[1] = c.tc1.y; bc.tc1[2] = c.tc1.z;
-					bc.tc2[0] = c.tc2.x; bc.tc2[1] = c.tc2.y; bc.tc2[2] = c.tc2.z;
-					float tf = (float)c.tan_r;
-					bc.sin_half_t = sinf(r_mul(tf, 0.5f));
-					bc.cos_half_t = cosf(r_mul(tf, 0.5f));
-					V3 a = vcross(c.cp, n.cp);
-					V3 e1 = vnorm(vcross(c.cp, c.tc1)), e2 = vnorm(vcross(c.tc1, n.cp));
-					V3 e3 = vnorm(vcross(c.tc2, c.cp)), e4 = vnorm(vcross(n.cp, c.tc2));
-					bc.c1xc2[0] = a.x; bc.c1xc2[1] = a.y; bc.c1xc2[2] = a.z;
-					bc.c1xt1[0] = e1.x; bc.c1xt1[1] = e1.y; bc.c1xt1[2] = e1.z;
-					bc.t1xc2[0] = e2.x; bc.t1xc2[1] = e2.y; bc.t1xc2[2] = e2.z;
-					bc.t2xc1[0] = e3.x; bc.t2xc1[1] = e3.y; bc.t2xc1[2] = e3.z;
-					bc.c2xt2[0] = e4.x; bc.c2xt2[1] = e4.y; bc.c2xt2[2] = e4.z;
-				}
-				R.cone_row_index[cons[b].desc_cone_index[i]] = (int)R.cones.size();
-				R.cones.push_back(bc);
-			}
+	}
+	ConstraintTables cons_tables;
+	{
+		int rc = author_constraints(d, R, R.bones, R.cones, cons_tables, R.error);
+		if (rc != MBIK_OK) {
+			return rc;
 		}
 	}
+	R.cone_row_index = cons_tables.cone_row_index;
+	const std::vector<char> &cons_present = cons_tables.present;
+	const std::vector<int> &cone_off = cons_tables.cone_off, &cone_cnt = cons_tables.cone_cnt;
 
 	// ---- per-segment effector entries ----
 	std::vector<int> seg_eff_off(R.segments.size(), 0);
@@ -741,7 +782,7 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 		st.parent = ik_parent[b] >= 0 ? R.t_of_bone[ik_parent[b]] : -1;
 		bool translate = S.parent_seg < 0;
 		st.flags = (translate ? STEP_TRANSLATE : 0) | (node_has_parent[b] ? STEP_NODE_PARENT : 0) | (ik_parent[b] >= 0 ? STEP_IK_PARENT : 0) |
-				(cons[b].present ? (STEP_SWING | STEP_TWIST) : 0) | (b == S.root_bone ? STEP_SEG_ROOT : 0) | (S.stabilize > 0 ? STEP_STABILIZE : 0);
+				(cons_present[b] ? (STEP_SWING | STEP_TWIST) : 0) | (b == S.root_bone ? STEP_SEG_ROOT : 0) | (S.stabilize > 0 ? STEP_STABILIZE : 0);
 		{
 			const BlobBone &BB = R.bones[R.t_of_bone[b]];
 			const M3 ident = m3_identity();
@@ -882,7 +923,7 @@ int flatten_rig(const mbik_rig_desc *d, FlatRig &R) {
 		}
 		double H = st.n_headings;
 		double fs = A + 34 * H + (translate ? 20 * H + 8 : 0) + 82 + 40 + 150 + (translate ? 3 : 0) + 63.0 * st.eff_cnt;
-		if ((st.flags & STEP_IK_PARENT) && cons[b].present) {
+		if ((st.flags & STEP_IK_PARENT) && cons_present[b]) {
 			fs += 82 + 14.0 * st.cone_cnt + 400;
 			n_constrained++;
 		}

@@ -48,6 +48,9 @@ struct FlatRig {
 	std::vector<BlobCone> cones;        // per constraint row order of appearance on solved bones
 	std::vector<int> cone_row_index;    // for mbik_rig_get_cone_geometry: desc cone index -> blob cone index or -1
 	std::vector<BlobPass> pass;
+	// what author_constraints needs besides the constraint rows
+	std::vector<int> ik_parent;             // skeleton id -> IK parent bone (skeleton id) or -1
+	std::vector<M3> setup_parent_basis;     // skeleton id -> setup-time global basis of the IK parent (constrained bones only)
 	std::vector<unsigned char> blob;
 	int max_headings = 0;
 	int n_effectors = 0;
@@ -68,6 +71,17 @@ struct FlatRig {
 
 // Returns MBIK_OK or a negative error code (message in out.error).
 int flatten_rig(const mbik_rig_desc *desc, FlatRig &out);
+
+// Side tables of author_constraints, per skeleton bone id
+struct ConstraintTables {
+	std::vector<char> present;
+	std::vector<int> cone_off, cone_cnt; // the bone's range in `cones`
+	std::vector<int> cone_row_index;     // desc cone index -> blob cone index or -1
+};
+// Limit-dependent part of flatten_rig, callable on its own for a rig that is already flattened (`bones`: a copy of
+// rig.bones; only its twist fields are written).  `desc` must name the same bones / cone counts in its constraint rows.
+int author_constraints(const mbik_rig_desc *desc, const FlatRig &rig, std::vector<BlobBone> &bones, std::vector<BlobCone> &cones, ConstraintTables &tables,
+		std::string &error);
 
 // Range-checks every index of the schedule against the capacities {solved bones, segment slots, stack slots} of the
 // kernel variant that will run it (the kernel itself does no bounds checking).  Returns true if consistent.

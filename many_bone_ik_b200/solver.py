@@ -158,6 +158,19 @@ class BatchedIKRig:
             raise MbikError(rc, "mbik_limit_sets_get_info")
         return {f[0]: getattr(info, f[0]) for f in LimitSetsInfo._fields_}
 
+    def limit_set_geometry(self, sets, set_index):
+        """(cones [n_cones, 9], twist_basis [n_solved, 9]) of one authored set: cone_geometry() / bone_frames()[1] layouts."""
+        fp = C.POINTER(C.c_float)
+        n = self.lib.mbik_limit_sets_get_geometry(sets, int(set_index), None, None)
+        if n < 0:
+            raise MbikError(n, "mbik_limit_sets_get_geometry")
+        cones = np.zeros((n, 9), np.float32)
+        twist = np.zeros((self.info["n_solved"], 9), np.float32)
+        rc = self.lib.mbik_limit_sets_get_geometry(sets, int(set_index), cones.ctypes.data_as(fp), twist.ctypes.data_as(fp))
+        if rc < 0:
+            raise MbikError(rc, "mbik_limit_sets_get_geometry")
+        return cones, twist
+
     def destroy_limit_sets(self, sets):
         self.lib.mbik_limit_sets_destroy(sets)
 

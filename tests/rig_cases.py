@@ -153,10 +153,11 @@ def perturbed_start_pose(rig, n, seed=7, angle_deg=12.0, offset=0.02):
     return out
 
 
-def random_rig(seed, n_bones=None):
+def random_rig(seed, n_bones=None, n_pins=None):
     """Random skeleton tree with random pins / kusudama rows / damping: fuzzes the flattener (segment building,
     dropped segments, effector lists, mpf cut-offs, weights) and every kernel stage against the oracle.
-    n_bones: override the random size (3..40) -- larger rigs land on the 64-bone-and-up kernel variants."""
+    n_bones: override the random size (3..40) -- larger rigs land on the 64-bone-and-up kernel variants; n_pins: override the
+    random pin count (1..7) -- many pins on a large tree = many solved bones."""
     rng = np.random.default_rng(1000 + seed)
     n = int(rng.integers(3, 41))
     if n_bones is not None:
@@ -180,7 +181,8 @@ def random_rig(seed, n_bones=None):
             off[:] = 0.0  # coincident joints
         rest[b] = _xf(_axis_angle(ax, ang), off)
     r = Rig(f"random{seed}", [f"b{i}" for i in range(n)], parent, rest.astype(np.float32), iterations=int(rng.integers(1, 6)), config_id=100 + seed)
-    n_pins = int(rng.integers(1, min(n, 7) + 1))
+    n_pins_drawn = int(rng.integers(1, min(n, 7) + 1))
+    n_pins = n_pins_drawn if n_pins is None else min(int(n_pins), n)
     bones = rng.choice(n, size=n_pins, replace=False)
     for b in bones:
         pr = tuple(float(x) for x in np.where(rng.random(3) < 0.6, rng.uniform(0.05, 0.6, 3), 0.0))

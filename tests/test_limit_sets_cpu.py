@@ -65,6 +65,32 @@ def test_limit_sets_parallel_and_asynchronous_authoring_build_the_same_table(mon
     R.destroy_limit_sets(h3)
 
 
+@pytest.mark.parametrize("name", ["humanoid22", "quad80", "chain64", "humanoid_stabilized", "scaled_bones", "chain300"])
+def test_authored_set_geometry_equals_a_rig_flattened_with_that_set(name):
+    """A set is authored by the limit-dependent part of the flattener alone (author_constraints on the rig's topology), not
+    by flattening the rig again: its cone / tangent-circle triples and twist frames must be the bits that a rig created with
+    the set's constraint values holds -- and those are pinned to the reference's own geometry by test_reference_cpu /
+    test_host_cpu.  Same through the thread pool and the asynchronous entry point."""
+    import rig_cases
+    rig = (rigs.RIGS.get(name) or getattr(rig_cases, name))()
+    R = BatchedIKRig(rig)
+    sets = LS.variants(rig, 5, seed=11)
+    handles = [R.create_limit_sets(sets), R.create_limit_sets(sets, asynchronous=True)]
+    for s_i, cons in enumerate(sets):
+        Rs = BatchedIKRig(LS.rig_with(rig, cons))
+        want_cones, want_twist = Rs.cone_geometry(), Rs.bone_frames()[1]
+        for h in handles:
+            cones, twist = R.limit_set_geometry(h, s_i)
+            assert cones.shape == want_cones.shape and np.array_equal(cones.view(np.uint32), want_cones.view(np.uint32))
+            assert np.array_equal(twist.view(np.uint32), want_twist.view(np.uint32))
+    if len(sets) > 1 and R.info["n_cones"] > 0:
+        assert not np.array_equal(R.limit_set_geometry(handles[0], 0)[0], R.limit_set_geometry(handles[0], 1)[0])
+    with pytest.raises(MbikError):
+        R.limit_set_geometry(handles[0], len(sets))
+    for h in handles:
+        R.destroy_limit_sets(h)
+
+
 def test_limit_set_solve_without_gpu_fails_loudly():
     if device_count() > 0:
         pytest.skip("a CUDA device is present")

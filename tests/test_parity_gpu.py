@@ -118,6 +118,17 @@ def test_bit_exact_random_rigs(seed):
     _compare(rig_cases.random_rig(seed), 96)
 
 
+@pytest.mark.parametrize("seed,n_bones,n_pins", [(201, 70, 12), (202, 100, 16), (203, 140, 24), (204, 200, 30), (205, 256, 40), (206, 300, 50),
+                                                 (207, 420, 60), (208, 64, 10), (209, 128, 20), (210, 90, 14), (211, 330, 64), (212, 500, 80)])
+def test_bit_exact_random_dense_rigs(seed, n_bones, n_pins):
+    """The same fuzz on large random trees with many pins: 28 ... 290 solved bones, i.e. every compiled kernel variant (32 /
+    64 / 128 / 256 bones, with and without stabilisation passes) and the unbounded one, in every mapping the variant has,
+    plain and from a perturbed start pose."""
+    rig = rig_cases.random_rig(seed, n_bones=n_bones, n_pins=n_pins)
+    _compare(rig, 128)
+    _compare(rig, 64, start_pose=rig_cases.perturbed_start_pose(rig, 64, seed=seed), first=7)
+
+
 @pytest.mark.parametrize("name", ["humanoid22", "quad80", "star_mixed_pins"])
 def test_bit_exact_with_start_pose(name):
     """Warm start: seeding from caller-supplied local poses (IKBone3D::set_initial_pose, src/ik_bone_3d.cpp:161)."""
