@@ -2,6 +2,8 @@
 // The large-rig variants are register-starved at 128 registers (64+ local poses to address): with the packed FP32x2
 // composites they spill and run 2-3 % slower (chain64 71.6 vs 69.4 ms, quad80 13.8 vs 13.5 ms per 75776-pose launch),
 // so this translation unit keeps the scalar formulations (same bits either way).
+// (The streamed-walk instantiations do not spill with them -- and gain nothing: chain64 +0.9 %, quad80 +0.9 %, big_tree240
+// -0.5 %, profiles/r2_exp_f2_large_rigs.log -- they wait on the per-pose state, not on issue slots.)
 #define MBIK_F2_MAT 0
 #define MBIK_F2_VEC 0
 #define MBIK_F2_DOT 0

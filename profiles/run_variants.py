@@ -26,7 +26,12 @@ if a.child:
     import torch
     from many_bone_ik_b200 import BatchedIKRig, rigs
     from many_bone_ik_b200._capi import MBIK_IO_DEVICE
-    rig = rigs.RIGS[a.rig]()
+    if a.rig in rigs.RIGS:
+        rig = rigs.RIGS[a.rig]()
+    else:  # the large / edge rigs of the tests
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import rig_cases
+        rig = getattr(rig_cases, a.rig)()
     R = BatchedIKRig(rig)
     T = torch.from_numpy(rigs.random_targets(rig, 0, a.poses)).cuda()
     O = torch.empty((a.poses, rig.n_bones, 10), dtype=torch.float32, device="cuda")
