@@ -307,6 +307,10 @@ void set_launch_hints(mbik::SolveArgs &a, const mbik::FlatRig &F, uint32_t flags
 	a.n_pins = (int32_t)F.pins.size();
 	a.max_seg_len = F.max_seg_len;
 	a.max_stack = F.max_stack;
+	a.max_list_effs = 0;
+	for (const mbik::FlatSegment &seg : F.segments) {
+		a.max_list_effs = std::max(a.max_list_effs, (int32_t)seg.effectors.size());
+	}
 	a.sp_roles = F.sp_roles;
 	a.sp_team_bytes = (int32_t)((size_t)F.sp_team_bufs * F.sp_team_headings * 6 * 32 * sizeof(float));
 	a.sp_gain = F.sp_critical_cost > 0 ? (float)(F.sp_serial_cost / F.sp_critical_cost) : 1.0f;
@@ -618,11 +622,14 @@ int mbik_rig_create(const mbik_rig_desc *desc, mbik_rig **out_rig) {
 			return fail(MBIK_ERR_UNSUPPORTED, verr);
 		}
 	}
-	if (desc->stabilization_passes > 0) {
-		for (int si : rig->flat.root_segments) {
-			if ((int)rig->flat.segments[si].effectors.size() > mbik::kMaxStabEffectors) {
+	if (desc->stabilization_passes > 0 && rig->variant != mbik::kDynVariant) {
+		// the stabilisation variants keep one pre-step tip origin per effector of a list in max(32, bone capacity) slots; a list
+		// has at most one effector per solved bone, so this cannot trip -- checked because the kernel does not
+		const int cap = std::max(mbik::kMinStabEffectors, mbik::kVariants[rig->variant][0]);
+		for (const mbik::FlatSegment &seg : rig->flat.segments) {
+			if ((int)seg.effectors.size() > cap) {
 				delete rig;
-				return fail(MBIK_ERR_UNSUPPORTED, "stabilization_passes > 0 supports at most 32 effectors per root segment");
+				return fail(MBIK_ERR_UNSUPPORTED, "internal: effector list longer than the kernel variant's bone capacity");
 			}
 		}
 	}

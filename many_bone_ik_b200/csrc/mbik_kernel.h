@@ -9,7 +9,7 @@ namespace mbik {
 
 constexpr int kBlockThreads = 512; // poses per CTA: one CTA per SM (128 registers per thread), all of its warps kept in lockstep
 constexpr int kStabBlockThreads = 512; // CTA size of the stabilisation variants
-constexpr int kMaxStabEffectors = 32;  // effectors per root-segment list the stabilisation variants can hold
+constexpr int kMinStabEffectors = 32;  // effector slots of the stabilisation variants: max(this, the variant's bone capacity); unbounded variant: workspace
 
 struct SolveArgs {
 	const unsigned char *blob; // device copy of the rig blob (16-byte aligned)
@@ -41,6 +41,7 @@ struct SolveArgs {
 	float *workspace = nullptr;
 	// streamed-walk instantiation (solve_body GLW): chosen by the host for rigs with long effector walks; sm_count sizes its workspace
 	int32_t use_glw = 0, sm_count = 0;
+	int32_t max_list_effs = 0; // longest effector list of the rig (stabilisation scratch of the unbounded variant)
 	int32_t newton_iters = 0;  // mbik_solve_params::newton_iters (0 = the reference's QCP: no eigenvalue refinement)
 	uint32_t out_flags = 0;    // OUT_* below
 };

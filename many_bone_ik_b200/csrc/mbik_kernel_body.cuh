@@ -903,7 +903,29 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 	                                               : (SCR_STRIDE > 0 ? scr + NSEG * 12 * SCR_STRIDE : Gstk_local), ws_threads };
 	// stabilisation only (STAB variants): effector-bone origins from before the step (what the step's target
 	// headings were built from) and the segment's previous_deviation (src/ik_bone_segment_3d.h:63)
-	float TipO[STAB ? kMaxStabEffectors * 3 : 1];
+	// (a list holds at most one effector per solved bone, so the compiled variants size it by their bone capacity; the unbounded
+	// variant keeps it in its workspace column, behind the chain and stack slots: max_list_effs x 3 words)
+	constexpr int TIP_CAP = (STAB && !DYN) ? (NB > kMinStabEffectors ? NB : kMinStabEffectors) : 1;
+	float TipO_local[TIP_CAP * 3];
+	float *tip_g = (STAB && DYN) ? dyn_scr + (size_t)(H.max_seg_len + H.max_stack) * 12 * ws_threads : nullptr;
+	auto tip_st = [&](int e, const V3 &v) {
+		if constexpr (DYN) {
+			tip_g[(size_t)(3 * e) * ws_threads] = v.x;
+			tip_g[(size_t)(3 * e + 1) * ws_threads] = v.y;
+			tip_g[(size_t)(3 * e + 2) * ws_threads] = v.z;
+		} else {
+			TipO_local[3 * e] = v.x;
+			TipO_local[3 * e + 1] = v.y;
+			TipO_local[3 * e + 2] = v.z;
+		}
+	};
+	auto tip_ld = [&](int e) -> V3 {
+		if constexpr (DYN) {
+			return v3(tip_g[(size_t)(3 * e) * ws_threads], tip_g[(size_t)(3 * e + 1) * ws_threads], tip_g[(size_t)(3 * e + 2) * ws_threads]);
+		} else {
+			return v3(TipO_local[3 * e], TipO_local[3 * e + 1], TipO_local[3 * e + 2]);
+		}
+	};
 	// translating (root) segments build every heading twice (centroid pass, inner-product pass): on the large-rig
 	// variants the effector frames of the first pass are kept, so the second pass needs no walk (chain64: 8 steps x
 	// 56-bone walks per iteration)
@@ -1134,7 +1156,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 							const X34 Ge = (e == 0 && (flags & STEP_SELF_EFF)) ? Gb : ld_x34(Efr, e);
 							const V3 tO = xform_zero(Ge);
 							if (STAB) {
-								TipO[3 * e] = tO.x; TipO[3 * e + 1] = tO.y; TipO[3 * e + 2] = tO.z;
+								tip_st(e, tO);
 							}
 							effector_headings(A, 1, true, E, Ge, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, tO);
 						}
@@ -1144,7 +1166,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						const BlobEff &E = effs[S.eff_off];
 						const V3 tO = xform_zero(Gb);
 						if (STAB) {
-							TipO[0] = tO.x; TipO[1] = tO.y; TipO[2] = tO.z;
+							tip_st(0, tO);
 						}
 						effector_headings(A, pass_i, translate, E, Gb, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo, tO);
 					}
@@ -1166,7 +1188,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						const BlobEff &E = effs[S.eff_off + eff];
 						const V3 tO = xform_zero(at);
 						if (STAB) {
-							TipO[3 * eff] = tO.x; TipO[3 * eff + 1] = tO.y; TipO[3 * eff + 2] = tO.z;
+							tip_st(eff, tO);
 						}
 						T = ldg_x34(my_targets + (size_t)E.pin * 12); // (hoisting it above the product costs more registers than it hides latency)
 						if (ECACHE > 0 && cache_frames && pass_i == 0) {
@@ -1327,7 +1349,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 				// constraint mode skips the QCP passes, but the step's target headings still date from here (:135)
 				if (flags & STEP_SELF_EFF) {
 					const V3 tO = xform_zero(Gb);
-					TipO[0] = tO.x; TipO[1] = tO.y; TipO[2] = tO.z;
+					tip_st(0, tO);
 				}
 				if (flags & STEP_PUSH_SELF) {
 					Gstk.st(0, Gb);
@@ -1344,7 +1366,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					}
 					if (op.eff >= 0) {
 						const V3 tO = xform_zero(run);
-						TipO[3 * op.eff] = tO.x; TipO[3 * op.eff + 1] = tO.y; TipO[3 * op.eff + 2] = tO.z;
+						tip_st(op.eff, tO);
 					}
 				}
 			}
@@ -1408,7 +1430,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 					if (flags & STEP_SELF_EFF) {
 						const BlobEff &E = effs[S.eff_off];
 						effector_headings(A, 2, false, E, Gp, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo2,
-								v3(TipO[0], TipO[1], TipO[2]));
+								tip_ld(0));
 					}
 					if (flags & STEP_PUSH_SELF) {
 						Gstk.st(0, Gp);
@@ -1426,7 +1448,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a) {
 						if (op.eff >= 0) {
 							const BlobEff &E = effs[S.eff_off + op.eff];
 							effector_headings(A, 2, false, E, run, ld_m3v(bones[E.bone].dir_basis), ldg_x34(my_targets + (size_t)E.pin * 12), bo2,
-									v3(TipO[3 * op.eff], TipO[3 * op.eff + 1], TipO[3 * op.eff + 2]));
+									tip_ld(op.eff));
 						}
 					}
 					const double current_msd = (double)r_div(A.msd, r_mul(A.msd_wsum, A.msd_wsum));
@@ -1637,7 +1659,8 @@ __global__ void __launch_bounds__(128) mbik_solve_kernel_dyn(SolveArgs a) {
 template <bool STAB, bool LIMS>
 static cudaError_t launch_variant_dyn(const SolveArgs &a0, int sm_count, cudaStream_t stream) {
 	// per thread: its share of a warp tile of poses (n_solved x 48 B + padding) and max_seg_len + max_stack scratch transforms
-	const size_t per_thread = glw_tile_float4(a0.n_solved) * sizeof(float4) / 32 + (size_t)(a0.max_seg_len + a0.max_stack) * 12 * sizeof(float);
+	const size_t per_thread = glw_tile_float4(a0.n_solved) * sizeof(float4) / 32 + (size_t)(a0.max_seg_len + a0.max_stack) * 12 * sizeof(float) +
+			(STAB ? (size_t)a0.max_list_effs * 3 * sizeof(float) : 0);
 	const size_t ring_bytes = (size_t)(MBIK_GLW_DEPTH + 2) * 3 * sizeof(float4) * 128;
 	size_t threads = ((a0.n_poses + 127) / 128) * 128;
 	const size_t resident = (size_t)(sm_count > 0 ? sm_count : 148) * 128 * 4;

@@ -207,6 +207,42 @@ def random_rig(seed, n_bones=None, n_pins=None):
     return r
 
 
+def soak_rig(k):
+    """Rig k of the parity soak (profiles/run_fuzz_soak.py): random_rig(1000 + k); every 8th one is a dense large tree (64 ... 520
+    bones, one pin per 5 ... 11 bones), every 40th a 600 ... 900-bone one (past 256 solved bones: the unbounded kernel variant)."""
+    seed = 1000 + k
+    rng = np.random.default_rng(seed)
+    if k % 8 == 7:
+        nb = int(rng.integers(64, 521)) if k % 40 != 39 else int(rng.integers(600, 901))
+        return random_rig(seed, n_bones=nb, n_pins=max(2, nb // int(rng.integers(5, 12))))
+    return random_rig(seed)
+
+
+def star_stabilized(n_arms=40, arm_len=2):
+    """A hub with n_arms arms of arm_len bones, every arm tip pinned, stabilisation passes on: one root-segment effector list of
+    n_arms entries (the reference has no limit on it; the stabilisation variants keep one pre-step tip origin per entry)."""
+    n = 1 + arm_len * n_arms
+    parent = np.full(n, -1, np.int32)
+    rest = np.zeros((n, 12))
+    rest[0] = _xf(np.eye(3), np.zeros(3))
+    for a in range(n_arms):
+        ang = 2 * np.pi * a / n_arms
+        d = np.array([np.cos(ang), 0.3 * np.sin(3 * ang), np.sin(ang)])
+        for j in range(arm_len):
+            b = 1 + arm_len * a + j
+            parent[b] = 0 if j == 0 else b - 1
+            rest[b] = _xf(_axis_angle(np.array([0.0, 1.0, 0.0]), ang * 0.1) if j == 0 else np.eye(3), (0.2 + 0.05 * j) * d)
+    r = Rig(f"star_stabilized{n_arms}x{arm_len}", [f"b{i}" for i in range(n)], parent, rest.astype(np.float32), iterations=4, config_id=300 + n_arms)
+    for a in range(n_arms):
+        r.pins.append(dict(bone=arm_len * (a + 1), weight=1.0 if a % 3 else 0.5, mpf=1.0 if a % 2 else 0.6,
+                           priorities=(0.2, 0.0, 0.3) if a % 4 == 0 else (0.0, 0.0, 0.0)))
+    for a in range(0, n_arms, 3):
+        r.constraints.append(dict(bone=1 + arm_len * a, twist_from=0.1, twist_range=2.0, cones=[(0.0, 1.0, 0.0, 0.8)]))
+    r.default_damp = float(np.float32(0.2))
+    r.stabilization_passes = 2
+    return r
+
+
 def no_pins():
     """No pins at all: nothing is solved; every bone passes through (reference early-out, many_bone_ik_3d.cpp:649)."""
     r = rigs.humanoid22()

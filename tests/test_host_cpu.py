@@ -330,3 +330,10 @@ def test_numa_helpers_degrade_to_a_no_op():
     assert "node" in done and ("skipped" in done or done["node"] is not None)
     if "skipped" in done:
         assert os.sched_getaffinity(0) == before
+
+
+def test_stabilised_rigs_have_no_effector_list_limit():
+    """Round 1 rejected stabilisation passes with more than 32 effectors in a list; the reference has no such limit."""
+    for n_arms, arm_len, cap in ((40, 1, 64), (70, 2, 256), (90, 3, 16383)):
+        R = BatchedIKRig(rig_cases.star_stabilized(n_arms, arm_len))
+        assert R.info["n_effectors"] == n_arms and R.info["kernel_capacity"] == cap

@@ -129,6 +129,22 @@ def test_bit_exact_random_dense_rigs(seed, n_bones, n_pins):
     _compare(rig, 64, start_pose=rig_cases.perturbed_start_pose(rig, 64, seed=seed), first=7)
 
 
+@pytest.mark.parametrize("n_arms,arm_len", [(40, 1), (40, 2), (70, 2), (90, 3)])
+def test_stabilisation_with_long_effector_lists(n_arms, arm_len):
+    """Stabilisation passes with 40 ... 90 effectors in one list (the reference has no limit, src/ik_bone_segment_3d.cpp:114-180):
+    the 64 / 128 / 256-bone variants and the unbounded one, every mapping the variant has, plain and from a perturbed pose."""
+    rig = rig_cases.star_stabilized(n_arms, arm_len)
+    _compare(rig, 96)
+    _compare(rig, 40, start_pose=rig_cases.perturbed_start_pose(rig, 40, seed=n_arms), first=3)
+
+
+@pytest.mark.parametrize("k", [39, 343])
+def test_soak_rigs_that_exposed_the_effector_list_limit(k):
+    """The two rigs of the 400-rig parity soak (profiles/r2_fuzz_soak.log) that the stabilisation variants' former 32-effector
+    limit rejected: 68 effectors on the unbounded variant, 86 on the 256-bone one."""
+    _compare(rig_cases.soak_rig(k), 64)
+
+
 @pytest.mark.parametrize("name", ["humanoid22", "quad80", "star_mixed_pins"])
 def test_bit_exact_with_start_pose(name):
     """Warm start: seeding from caller-supplied local poses (IKBone3D::set_initial_pose, src/ik_bone_3d.cpp:161)."""
