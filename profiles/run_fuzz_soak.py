@@ -18,6 +18,8 @@ from oracle import oracle_py as O  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--rigs", type=int, default=300)
 ap.add_argument("--poses", type=int, default=48)
+ap.add_argument("--first", type=int, default=0)
+ap.add_argument("--extreme", action="store_true", help="targets scaled by 1e5 ... 1e37 / 1e-30, 12 iterations: poses overflow to Inf / NaN part-way")
 a = ap.parse_args()
 
 
@@ -28,9 +30,11 @@ def same(x, y):
 t0 = time.time()
 n_ok = n_fail = n_rejected = 0
 variants = {}
-for k in range(a.rigs):
+for k in range(a.first, a.first + a.rigs):
     seed = 1000 + k
     rig = rig_cases.soak_rig(k)
+    if a.extreme:
+        rig.iterations = 12
     try:
         R = BatchedIKRig(rig)
     except MbikError as e:
@@ -39,6 +43,15 @@ for k in range(a.rigs):
         continue
     variants[R.info["kernel_capacity"]] = variants.get(R.info["kernel_capacity"], 0) + 1
     T = rigs.random_targets(rig, seed, a.poses)
+    if a.extreme:
+        erng = np.random.default_rng(seed)
+        T[:, :, 9:] *= np.float32(10.0) ** erng.integers(5, 38, size=(a.poses, 1, 1)).astype(np.float32)
+        if k % 3 == 0:
+            T[:, :, :9] *= np.float32(10.0) ** erng.integers(0, 20, size=(a.poses, 1, 1)).astype(np.float32)
+        if k % 4 == 0:
+            T[::5] = np.float32(1e-30) * T[::5]
+        if k % 5 == 0:
+            T[1::7, :, 3] = np.nan
     start = rig_cases.perturbed_start_pose(rig, a.poses, seed=seed) if k % 3 == 0 else None
     ref = O.solve_batch(rig, T, start_pose=start, want_local=True, threads=8)
     bad = []
@@ -51,6 +64,6 @@ for k in range(a.rigs):
         print("MISMATCH seed", seed, "bones", rig.n_bones, "solved", R.info["n_solved"], "mappings", bad, flush=True)
     else:
         n_ok += 1
-print(f"fuzz soak: {n_ok} rigs bit-identical to the oracle in all three mappings, {n_fail} mismatching, {n_rejected} rejected by the flattener; "
+print(f"fuzz soak{' (extreme inputs)' if a.extreme else ''}: {n_ok} rigs bit-identical to the oracle in all three mappings, {n_fail} mismatching, {n_rejected} rejected by the flattener; "
       f"{a.poses} poses each; rigs per kernel capacity {dict(sorted(variants.items()))}; {time.time() - t0:.0f} s")
 sys.exit(1 if n_fail else 0)
