@@ -686,6 +686,44 @@ def main():
     except Exception as e:
         limit_sets = {"error": str(e)}
 
+    # ---- side measurement: stabilisation passes: the headline rig with stabilization_passes = 1 -- every
+    # bone-step walks its effectors a second time for the accept / revert test (src/ik_bone_segment_3d.cpp:163-176) ----
+    stabilisation = None
+    try:
+        import copy
+        rig_s = copy.deepcopy(rig)
+        rig_s.stabilization_passes = 1
+        rig_s.name = rig.name + "_stabilized"
+        Rs_ = BatchedIKRig(rig_s)
+        for _ in range(2):
+            Rs_.solve_raw(n, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+        s0_, s1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0_.record()
+        for _ in range(3):
+            Rs_.solve_raw(n, t_dev, o_dev, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+        s1_.record()
+        torch.cuda.synchronize()
+        sms = s0_.elapsed_time(s1_) / 3
+        lat_s = []
+        for i in range(60):
+            c_, d_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c_.record()
+            Rs_.solve_raw(LATENCY_BATCH, lt, lo_, device=local_rank, flags=MBIK_IO_DEVICE, stream=stream)
+            d_.record()
+            torch.cuda.synchronize()
+            if i >= 10:
+                lat_s.append(c_.elapsed_time(d_))
+        stabilisation = {"workload": f"{rig.name} with stabilization_passes = 1, {n} poses, device-resident", "poses": n, "ms_per_launch": sms,
+                         "solves_per_s": n / (sms * 1e-3), "relative_to_plain": (dev_ms / args.steps) / sms, "latency_p50_ms_4096": float(np.median(lat_s)),
+                         "flops_per_solve": Rs_.info["flops_per_solve"]}
+        if not args.no_cpu_baseline and world == 1:
+            cb_s, _ = time_cpu_reference(rig_s, budget_s=4.0, with_port=False)
+            stabilisation["cpu_baseline"] = cb_s
+            stabilisation["over_cpu_baseline"] = stabilisation["solves_per_s"] / cb_s["value"] if cb_s.get("value") else None
+        del Rs_
+    except Exception as e:
+        stabilisation = {"error": str(e)}
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         cpu_baseline, _ = time_cpu_reference(rig, budget_s=12.0)
@@ -715,6 +753,7 @@ def main():
         "host_link": host_link,
         "numa_binding_rank0": numa_binding,
         "limit_sets_device_resident": limit_sets,
+        "stabilisation_device_resident": stabilisation,
         "clocks": clocks,
         "device_equals_host_path": same,
     }
