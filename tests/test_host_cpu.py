@@ -91,6 +91,24 @@ def test_flattener_matches_reference_setup_random_rigs(seed):
     assert np.array_equal(R.cone_geometry(), O.cone_geometry(rig), equal_nan=True)
 
 
+@pytest.mark.parametrize("first", [0, 60, 120])
+def test_flattener_matches_reference_setup_soak_rigs(first):
+    """The same on the rigs of the GPU parity soaks (rig_cases.soak_rig: every 8th a dense tree of 64 ... 900 bones), 60 per case,
+    plus the schedule's own consistency check against the variant that will run it (done by mbik_rig_create)."""
+    for k in range(first, first + 60):
+        rig = rig_cases.soak_rig(k)
+        R = BatchedIKRig(rig)
+        F = O.rig_facts(rig)
+        assert np.array_equal(R.bone_order(), F["bone_order"]), k
+        assert R.info["n_segments"] == F["n_segments"], k
+        d, t = R.bone_frames()
+        assert np.array_equal(d, F["dir_basis"], equal_nan=True) and np.array_equal(t, F["twist_basis"], equal_nan=True), k
+        for s in range(0, R.info["n_steps"], 7 if R.info["n_steps"] > 64 else 1):
+            assert np.array_equal(R.step_weights(s), O.step_weights(rig, s)), (k, s)
+        assert np.array_equal(R.cone_geometry(), O.cone_geometry(rig), equal_nan=True), k
+        R.close()
+
+
 def test_schedule_facts_of_the_benchmark_rigs():
     """The segment structure SURVEY.md section 8(d) states for the canonical rigs."""
     h = BatchedIKRig(rigs.humanoid22())
